@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — CTR training samples/s of DeepFM on a synthetic Criteo-shaped batch (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: clear_grad -> DeepFMLayer.forward (fused
+gather+FM kernel, MLP tower) -> log_loss -> backward (sort/segment-reduce scatter-add, fused FM
+grad) -> optimizer step (lazy Adam on the touched rows, Adam on the dense parameters).
+
+Workload (config.workload): DeepFM, 26 sparse + 13 dense slots, hashed vocab V=1e8, D=16,
+B=65536 per GPU, fc [400,400,400], uniform hashed ids with 2 % padding, 8 rotating batches
+(per-step working set: 164 MB feat + 6.4 GB table >> 126 MB L2, so no L2 flush is needed).
+N>1: tables row-sharded (owner = id mod N), NCCL all-to-all of ids/rows/grads, dense grads
+all-reduced; weak scaling (B per GPU fixed).
+
+Printed JSON (one line, rank 0): see the contract in the task statement; extra keys `roofline`
+(fused gather+FM forward kernel, algorithmic bytes / CUDA-event time inside the timed region
+against MEASURED_PEAKS.json), `cpu_baseline` (oracle port timed on the host cores, N=1 only),
+`e2e` (same metric through DygraphModel.train_forward with HOST buffers: H2D of the batch and
+D2H of the loss inside the timed region), `clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_SPARSE, N_DENSE = 26, 13
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
+    p.add_argument("--vocab", type=int, default=100_000_000)
+    p.add_argument("--dim", type=int, default=16)
+    p.add_argument("--fc", type=str, default="400,400,400")
+    p.add_argument("--precision", default="bf16x3", choices=["fp32", "tf32", "bf16x3"])
+    p.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
+    p.add_argument("--nbatches", type=int, default=8)
+    p.add_argument("--cpu-batch", type=int, default=65536)
+    p.add_argument("--cpu-steps", type=int, default=4)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def algorithmic_bytes_fwd(D, F=F_SPARSE, Dn=N_DENSE):
+    """ids + dense + rows + first-order scalars + feat write + (y1,y2)."""
+    return F * 8 + Dn * 4 + F * 4 * D + F * 4 + (F + Dn) * 4 * D + 8
+
+
+def make_batches(n, B, V, dist, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        if dist == "zipf":
+            r = torch.rand(B, F_SPARSE, generator=g, dtype=torch.float64)
+            ids = (float(V) ** r).to(torch.int64).clamp_(1, V - 1)
+        else:
+            ids = torch.randint(1, V, (B, F_SPARSE), generator=g)
+        ids[torch.rand(B, F_SPARSE, generator=g) < 0.02] = 0
+        dense = torch.rand(B, N_DENSE, generator=g)
+        dense[torch.rand(B, N_DENSE, generator=g) < 0.3] = 0.0
+        label = (torch.rand(B, 1, generator=g) < 0.29).to(torch.int64)
+        if pin:
+            ids, dense, label = ids.pin_memory(), dense.pin_memory(), label.pin_memory()
+        out.append((label, ids, dense))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
+                          if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path = the oracle port (Paddle is not
+    installable here), on all host threads, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle.cpu_train import CpuDeepFM, time_steps
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fc = [int(x) for x in args.fc.split(",")]
+    V = args.vocab
+    try:
+        import psutil
+        need = V * (args.dim + 1) * 4 * 3.2
+        if psutil.virtual_memory().available < need * 1.3:
+            V = max(1_000_001, int(psutil.virtual_memory().available / 1.3 / ((args.dim + 1) * 4 * 3.2)))
+    except ImportError:
+        pass
+    model = CpuDeepFM(V, args.dim, fc=fc)
+    B = args.cpu_batch
+    batches = [(i, d, l.float()) for (l, i, d) in make_batches(2, B, V, args.dist, 12345, False)]
+    K = max(1, min(args.steps, args.cpu_steps))
+    W = max(1, min(args.warmup, 1))
+    secs, loss = time_steps(model, batches, K, W)
+    value = B * K / secs
+    sample = ("%d steps of B=%d (after %d warm-up) of the same DeepFM step, V=%d, fp32, lazy Adam"
+              % (K, B, W, V))
+    line = {
+        "impl": "reference", "metric": "DeepFM Criteo-shape CTR training samples/sec",
+        "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "DeepFM Criteo-shape: 26 sparse + 13 dense slots, hashed vocab %d, D=%d, "
+                        "B=%d per GPU, fc [%s], %s ids (2%% padding)" %
+                        (args.vocab, args.dim, args.batch, args.fc, args.dist),
+            "global_batch": args.batch * world, "tower_matmul": args.precision,
+            "optimizer": "Adam (lazy rows on the tables)",
+            "parallelism": "single GPU" if world == 1 else
+            "tables row-sharded (id mod %d) + NCCL all-to-all; dense params data-parallel" % world,
+            "l2": "inputs larger than L2 (8 rotating batches; 164 MB feat + 6.4 GB table per step)"}
+
+
+# ------------------------------------------------------------------------------------- our arm
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from paddlerec_b200 import nn as bnn
+    from paddlerec_b200 import ops
+    from paddlerec_b200.rank.deepfm.dygraph_model import DygraphModel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    bnn.set_matmul_precision(args.precision)
+    fc = [int(x) for x in args.fc.split(",")]
+    config = {
+        "hyper_parameters.sparse_feature_number": args.vocab,
+        "hyper_parameters.sparse_feature_dim": args.dim,
+        "hyper_parameters.fc_sizes": fc,
+        "hyper_parameters.dense_input_dim": N_DENSE,
+        "hyper_parameters.sparse_inputs_slots": F_SPARSE + 1,
+        "hyper_parameters.optimizer.learning_rate": 1e-3,
+    }
+    torch.manual_seed(12345)
+    dm = DygraphModel()
+    dm.device = dev
+    if world > 1:
+        from paddlerec_b200 import sharded
+        model = sharded.create_sharded_deepfm(config, dev, rank, world)
+        optimizer = sharded.create_optimizer(model, config)
+    else:
+        model = dm.create_model(config)
+        optimizer = dm.create_optimizer(model, config)
+    model.train()
+
+    host = make_batches(args.nbatches, args.batch, args.vocab, args.dist, 12345 + rank, pin=True)
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    label_f = [b[0].to(torch.float32) for b in resident]
+
+    def step_resident(i):
+        label, ids, dense = resident[i % len(resident)]
+        optimizer.clear_grad()
+        pred = model(ids, dense)
+        loss = dm.create_loss(pred, label_f[i % len(resident)])
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    def step_e2e(i):
+        optimizer.clear_grad()
+        loss, _, _ = dm.train_forward(model, None, host[i % len(host)], config)
+        loss.backward()
+        optimizer.step()
+        return loss.item()  # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, collect_events=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ops.EVENTS = [] if collect_events else None
+        n0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.LAUNCHES - n0
+        events, ops.EVENTS = ops.EVENTS, None
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, events, clocks
+
+    K, W = args.steps, max(args.warmup, 3)
+    ms, launches, events, clocks = timed(step_resident, K, W, collect_events=True)
+    value = args.batch * world * K / (ms / 1e3)
+    k_ms = [s.elapsed_time(e) for (name, s, e) in events if name == "embed_fm_fwd"]
+    kernel_ms = sum(k_ms) / max(len(k_ms), 1)
+    ms_e2e, _, _, _ = timed(step_e2e, K, 3)
+    e2e_value = args.batch * world * K / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes_fwd(args.dim) * args.batch
+    achieved = alg / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
+    line = {
+        "metric": "DeepFM Criteo-shape CTR training samples/sec", "value": value,
+        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, world),
+        "roofline": {"kernel": "embed_fm_fwd_kernel (fused 26-slot gather + FM, forward)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
+                     "kernel_share_of_step": kernel_ms / (ms / K), "traffic": None,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": args.batch * (F_SPARSE * 8 + N_DENSE * 4 + 8),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args)
+        except Exception as exc:  # the GPU numbers stand on their own
+            line["cpu_baseline"] = {"error": repr(exc)}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    from oracle.cpu_train import CpuDeepFM, time_steps
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    V = args.vocab
+    note = ""
+    try:
+        import psutil
+        need = V * (args.dim + 1) * 4 * 3.2
+        avail = psutil.virtual_memory().available
+        if avail < need * 1.3:
+            V = max(1_000_001, int(avail / 1.3 / ((args.dim + 1) * 4 * 3.2)))
+            note = " (V reduced from %d: host RAM)" % args.vocab
+    except ImportError:
+        pass
+    model = CpuDeepFM(V, args.dim, fc=[int(x) for x in args.fc.split(",")])
+    B = args.cpu_batch
+    batches = [(i, d, l.float()) for (l, i, d) in make_batches(2, B, V, args.dist, 12345, False)]
+    secs, _ = time_steps(model, batches, args.cpu_steps, 1)
+    return {"value": B * args.cpu_steps / secs, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of B=%d after 1 warm-up, same DeepFM step, V=%d%s, fp32, sparse grads "
+                      "+ lazy Adam (oracle/cpu_train.py)" % (args.cpu_steps, B, V, note)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

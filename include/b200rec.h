@@ -1,0 +1,159 @@
+/*
+ * b200rec.h — C ABI of the B200-native sparse-embedding + feature-interaction engine.
+ *
+ * This is the drop-in boundary for the one hot path of PaddleRec's rank models
+ * (reference checkout /root/reference, commit 656326ad):
+ *
+ *   paddle.nn.Embedding fwd/bwd   models/rank/deepfm/net.py:66-86,108,117
+ *                                 models/rank/dcn_v2/net.py:45-54,95
+ *                                 models/rank/din/net.py:33-82,141-147
+ *                                 models/rank/wide_deep/net.py:47-53,90
+ *   FM first/second order         models/rank/deepfm/net.py:105-139
+ *   CrossNetV2 / CrossNetMix      models/rank/dcn_v2/net.py:222-226,278-320
+ *   DIN attention pooling         models/rank/din/net.py:155-173
+ *   sparse (row-wise) optimizers  models/rank/deepfm/static_model.py:101-103 (lazy Adam),
+ *                                 models/rank/din/dygraph_model.py:64-73 (SGD),
+ *                                 models/rank/slot_dnn/config_online.yaml:57-79 (AdaGrad rule)
+ *   sharded table key exchange    tools/static_gpubox_trainer.py:152-159,244-259 (PSGPU pull/push)
+ *
+ * PaddleRec has no FFI of its own: the arithmetic above lives in Paddle
+ * core operators that net.py calls.  A Paddle custom-op (`PD_BUILD_OP`) or any other host
+ * binds these entry points; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns every buffer (outputs and workspace; query sizes first) — the
+ *     library never allocates on the hot path;
+ *   - all tensors are dense row-major fp32, all ids int64;
+ *   - functions enqueue on `stream` (a cudaStream_t passed as void*) and return
+ *     without synchronising; they are re-entrant;
+ *   - return 0 on success, a negative B200REC_ERR_* otherwise; the message is
+ *     available from b200rec_last_error() (thread-local); nothing throws;
+ *   - ids outside [0,V) are treated like the padding row (zero output, no
+ *     gradient) and counted in a device-side counter readable with
+ *     b200rec_oob_count() (Paddle raises on such ids; we stay UB-free and report).
+ */
+#ifndef B200REC_H_
+#define B200REC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REC_ABI_VERSION 1
+
+#define B200REC_OK 0
+#define B200REC_ERR_INVALID (-1)   /* bad argument (shape, alignment, NULL) */
+#define B200REC_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed   */
+#define B200REC_ERR_WORKSPACE (-3) /* workspace too small                    */
+
+/* ---- library ------------------------------------------------------------ */
+int b200rec_abi_version(void);
+const char* b200rec_last_error(void);
+/* number of out-of-range ids seen since the last reset (synchronises `stream`). */
+int b200rec_oob_count(uint64_t* count_host, int reset, void* stream);
+
+/* ---- K1: fused multi-slot gather + FM (DeepFM forward) ------------------- */
+/* Replaces FM.forward, models/rank/deepfm/net.py:105-139.
+ *   feat[b,f,:]   = W[ids[b,f],:]                (zeros if ids==padding_idx)     f <  F
+ *   feat[b,F+j,:] = dense[b,j] * dense_w[j,:]                                    j <  Dn
+ *   y1[b] = sum_f W1[ids[b,f]] + sum_j dense[b,j]*dense_w1[j]
+ *   S[b,:] = sum_n feat[b,n,:] ;  y2[b] = 0.5 * sum_d ( S[b,d]^2 - sum_n feat[b,n,d]^2 )
+ * feat:[B,F+Dn,D]  y1,y2:[B]  S:[B,D] (saved for backward; may be NULL).
+ * padding_idx < 0 means "no padding row".  D must be <=128 (D%4==0), <=64 (D%2==0) or <=32. */
+int b200rec_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids, const float* dense,
+                         const float* dense_w, const float* dense_w1, float* feat, float* y1,
+                         float* y2, float* S, int64_t B, int F, int Dn, int D, int64_t V,
+                         int64_t padding_idx, void* stream);
+
+/* ---- grouping of ids (sort + run-length) shared by every backward -------- */
+/* Stable-sorts the n ids, dropping padding / out-of-range ones, and produces
+ *   unique_ids[u]            the u-th distinct id (ascending)             u < *num_unique
+ *   seg_offsets[u..u+1]      range in sorted_pos of the positions holding that id
+ *   sorted_pos[i]            original position (0..n-1), ascending inside a segment
+ * num_unique is a device int32[2]: {#distinct ids, #positions kept}.
+ * Output arrays must hold n (seg_offsets: n+1) elements. */
+int b200rec_group_ids_workspace_bytes(int64_t n, int64_t V, size_t* bytes_host);
+int b200rec_group_ids(const int64_t* ids, int64_t n, int64_t V, int64_t padding_idx,
+                      int64_t* unique_ids, int32_t* seg_offsets, int32_t* sorted_pos,
+                      int32_t* num_unique, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2: DeepFM backward (analytic FM grad fused into the segmented reduce) */
+/* Backward of b200rec_embed_fm_fwd (autograd of net.py:105-139).
+ *   dfeat[b,n,:] = gy2[b]*(S[b,:] - feat[b,n,:]) + dfeat_dnn[b,n,:]   (dfeat_dnn may be NULL)
+ *   dW_rows[u,:] = sum_{p in segment u} dfeat[p]        dW1_rows[u] = sum_{p in seg u} gy1[b(p)]
+ *   ddense_w[j,:] = sum_b dense[b,j]*dfeat[b,F+j,:]     ddense_w1[j] = sum_b gy1[b]*dense[b,j]
+ * dW_rows:[n,D], dW1_rows:[n] with n=B*F; only the first num_unique[0] rows are written
+ * (a SelectedRows{rows=unique_ids, value=dW_rows} in Paddle terms).  Deterministic. */
+int b200rec_embed_fm_bwd_workspace_bytes(int64_t B, int F, int Dn, int D, size_t* bytes_host);
+int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_dnn,
+                         const float* gy1, const float* gy2, const float* dense,
+                         const int32_t* seg_offsets, const int32_t* sorted_pos,
+                         const int32_t* num_unique, float* dW_rows, float* dW1_rows,
+                         float* ddense_w, float* ddense_w1, int64_t B, int F, int Dn, int D,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- plain gather / segmented scatter-add (W&D, DCN-V2, DIN lookups) ------ */
+/* out[i,:] = W[ids[i],:]  (zeros if ids[i]==padding_idx).  Replaces paddle.nn.Embedding
+ * forward (lookup_table_v2), e.g. models/rank/wide_deep/net.py:90, dcn_v2/net.py:95. */
+int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D, int64_t V,
+                   int64_t padding_idx, void* stream);
+/* rows[u,:] = sum_{p in segment u} dOut[p,:]  — the SelectedRows merge of
+ * lookup_table_v2_grad.  Deterministic (fixed order inside a segment). */
+int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
+                           const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
+                           int64_t n, int D, void* stream);
+/* dW[unique_ids[u],:] += rows[u,:] into a dense [V,D] gradient (small tables / tests). */
+int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const int32_t* num_unique,
+                          float* dW, int64_t n, int D, int64_t V, void* stream);
+
+/* ---- row-wise ("lazy") optimizers applied to the touched rows only -------- */
+/* W[id] -= lr * g */
+int b200rec_sparse_sgd(float* W, const int64_t* unique_ids, const float* rows,
+                       const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                       void* stream);
+/* Adam(lazy_mode=True): m=b1*m+(1-b1)g; v=b2*v+(1-b2)g^2;
+ * W -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps*sqrt(1-b2^t)); bias terms from the host. */
+int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
+                        const float* rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
+                        float lr, float beta1, float beta2, float eps, float beta1_pow_t,
+                        float beta2_pow_t, void* stream);
+/* SparseAdaGradSGDRule: one g2sum scalar per row.
+ *   W -= lr * g * sqrt(g0/(g0+g2sum)); clamp to [lo,hi]; g2sum += mean_d(g^2). */
+int b200rec_sparse_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
+                           const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                           float initial_g2sum, float lo, float hi, void* stream);
+
+/* ---- K3: CrossNet fused epilogues (GEMM itself is a library GEMM) --------- */
+/* CrossNetV2 step, models/rank/dcn_v2/net.py:222-226, after xw = x_l @ W_l:
+ *   out = xl + x0 * (xw + bias)           all [B,C], bias [C] */
+int b200rec_cross_v2_fwd(const float* x0, const float* xl, const float* xw, const float* bias,
+                         float* out, int64_t B, int C, void* stream);
+/* Given dout: dxw = dout*x0 ; dx0 = dout*(xw+bias) ; dbias[c] = sum_b dxw[b,c]
+ * (the caller finishes dxl = dout + dxw@W^T and dW = xl^T@dxw with library GEMMs).  dbias needs a workspace of b200rec_cross_bwd_workspace_bytes. */
+int b200rec_cross_bwd_workspace_bytes(int64_t B, int C, size_t* bytes_host);
+int b200rec_cross_v2_bwd(const float* dout, const float* x0, const float* xw, const float* bias,
+                         float* dxw, float* dx0, float* dbias, int64_t B, int C,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: row-cyclic sharding helpers (owner = id mod world) --------------- */
+/* Stable bucketing of n ids by owner rank (bucket order = owner-major, original order inside).
+ *   send_ids[k]   local row (id div world) of the k-th id in bucket order; -1 if out of range
+ *   perm[i]       slot of position i in bucket order: rows_back[perm[i]] is the row of ids[i],
+ *                 so `perm` is the `ids` argument of embed_fm_fwd / gather over the received rows
+ *   inv_perm[k]   position held by slot k: the `sorted_pos` argument (with seg_offsets = iota)
+ *                 that makes embed_fm_bwd / segment_reduce emit gradients in bucket order
+ *   counts[r]     number of ids owned by rank r (device int64[world])
+ * The padding id travels to its natural owner (padding_idx mod world), whose gather zeroes it. */
+int b200rec_shard_bucketize_workspace_bytes(int64_t n, int world, size_t* bytes_host);
+int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V, int64_t* send_ids,
+                            int64_t* perm, int32_t* inv_perm, int64_t* counts, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H_ */

@@ -1,0 +1,221 @@
+// libb200rec.so — the single translation unit behind include/b200rec.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+// kernels (order matters: embed_fm.cuh defines reduce_partials_kernel used by cross.cuh)
+#include "embed_fm.cuh"
+#include "group_ids.cuh"
+#include "gather_scatter.cuh"
+#include "cross.cuh"
+#include "shard.cuh"
+#include "din_attn.cuh"
+
+namespace b200rec {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+}  // namespace b200rec
+
+using namespace b200rec;
+
+#define ST(s) static_cast<cudaStream_t>(s)
+#define NOT_NULL(p) B200_REQUIRE((p) != nullptr, "%s: argument `%s` is NULL", __func__, #p)
+
+extern "C" {
+
+int b200rec_abi_version(void) { return B200REC_ABI_VERSION; }
+
+const char* b200rec_last_error(void) { return g_err; }
+
+int b200rec_oob_count(uint64_t* count_host, int reset, void* stream) {
+  NOT_NULL(count_host);
+  unsigned long long v = 0;
+  B200_CUDA(cudaStreamSynchronize(ST(stream)));
+  B200_CUDA(cudaMemcpyFromSymbol(&v, g_oob_count, sizeof(v)));
+  *count_host = (uint64_t)v;
+  if (reset) {
+    v = 0;
+    B200_CUDA(cudaMemcpyToSymbol(g_oob_count, &v, sizeof(v)));
+  }
+  return B200REC_OK;
+}
+
+int b200rec_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids, const float* dense,
+                         const float* dense_w, const float* dense_w1, float* feat, float* y1,
+                         float* y2, float* S, int64_t B, int F, int Dn, int D, int64_t V,
+                         int64_t padding_idx, void* stream) {
+  B200_REQUIRE(B >= 0 && F >= 0 && Dn >= 0 && D > 0 && V > 0, "embed_fm_fwd: bad sizes");
+  if (B > 0) {
+    NOT_NULL(W); NOT_NULL(W1); NOT_NULL(feat); NOT_NULL(y1); NOT_NULL(y2);
+    if (F > 0) NOT_NULL(ids);
+    if (Dn > 0) { NOT_NULL(dense); NOT_NULL(dense_w); NOT_NULL(dense_w1); }
+  }
+  return launch_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, feat, y1, y2, S, B, F, Dn, D, V,
+                             padding_idx, ST(stream));
+}
+
+int b200rec_group_ids_workspace_bytes(int64_t n, int64_t V, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  GroupPlan p;
+  int rc = make_group_plan(n, V, &p);
+  if (rc != B200REC_OK) return rc;
+  *bytes_host = p.total;
+  return B200REC_OK;
+}
+
+int b200rec_group_ids(const int64_t* ids, int64_t n, int64_t V, int64_t padding_idx,
+                      int64_t* unique_ids, int32_t* seg_offsets, int32_t* sorted_pos,
+                      int32_t* num_unique, void* workspace, size_t workspace_bytes, void* stream) {
+  NOT_NULL(seg_offsets); NOT_NULL(num_unique);
+  if (n > 0) { NOT_NULL(ids); NOT_NULL(unique_ids); NOT_NULL(sorted_pos); NOT_NULL(workspace); }
+  return launch_group_ids(ids, n, V, padding_idx, unique_ids, seg_offsets, sorted_pos, num_unique,
+                          workspace, workspace_bytes, ST(stream));
+}
+
+int b200rec_embed_fm_bwd_workspace_bytes(int64_t B, int F, int Dn, int D, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  (void)B; (void)F;
+  *bytes_host = (size_t)bwd_dense_grid() * ((size_t)Dn * D + Dn) * sizeof(float) + 16;
+  return B200REC_OK;
+}
+
+int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_dnn,
+                         const float* gy1, const float* gy2, const float* dense,
+                         const int32_t* seg_offsets, const int32_t* sorted_pos,
+                         const int32_t* num_unique, float* dW_rows, float* dW1_rows,
+                         float* ddense_w, float* ddense_w1, int64_t B, int F, int Dn, int D,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(B >= 0 && F >= 0 && Dn >= 0 && D > 0, "embed_fm_bwd: bad sizes");
+  if (B > 0) {
+    NOT_NULL(feat); NOT_NULL(S); NOT_NULL(gy1); NOT_NULL(gy2);
+    if (F > 0) {
+      NOT_NULL(seg_offsets); NOT_NULL(sorted_pos); NOT_NULL(num_unique);
+      NOT_NULL(dW_rows); NOT_NULL(dW1_rows);
+    }
+    if (Dn > 0) { NOT_NULL(dense); NOT_NULL(ddense_w); NOT_NULL(ddense_w1); NOT_NULL(workspace); }
+  }
+  return launch_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_pos,
+                             num_unique, dW_rows, dW1_rows, ddense_w, ddense_w1, B, F, Dn, D,
+                             workspace, workspace_bytes, ST(stream));
+}
+
+int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D, int64_t V,
+                   int64_t padding_idx, void* stream) {
+  B200_REQUIRE(n >= 0 && D > 0 && V > 0, "gather: bad sizes");
+  if (n > 0) { NOT_NULL(W); NOT_NULL(ids); NOT_NULL(out); }
+  return launch_gather(W, ids, out, n, D, V, padding_idx, ST(stream));
+}
+
+int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
+                           const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
+                           int64_t n, int D, void* stream) {
+  B200_REQUIRE(n >= 0 && D > 0, "segment_reduce: bad sizes");
+  if (n > 0) { NOT_NULL(dOut); NOT_NULL(seg_offsets); NOT_NULL(sorted_pos); NOT_NULL(num_unique); NOT_NULL(rows); }
+  return launch_segment_reduce(dOut, seg_offsets, sorted_pos, num_unique, rows, n, D, ST(stream));
+}
+
+int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const int32_t* num_unique,
+                          float* dW, int64_t n, int D, int64_t V, void* stream) {
+  B200_REQUIRE(n >= 0 && D > 0 && V > 0, "rows_to_dense: bad sizes");
+  if (n > 0) { NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); NOT_NULL(dW); }
+  RowsToDenseOp op{dW};
+  return launch_row_update("rows_to_dense", unique_ids, rows, num_unique, n, D, V, op, dW, nullptr,
+                           nullptr, ST(stream));
+}
+
+int b200rec_sparse_sgd(float* W, const int64_t* unique_ids, const float* rows,
+                       const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                       void* stream) {
+  B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_sgd: bad sizes");
+  if (n > 0) { NOT_NULL(W); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
+  SgdOp op{W, lr};
+  return launch_row_update("sparse_sgd", unique_ids, rows, num_unique, n, D, V, op, W, nullptr,
+                           nullptr, ST(stream));
+}
+
+int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
+                        const float* rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
+                        float lr, float beta1, float beta2, float eps, float beta1_pow_t,
+                        float beta2_pow_t, void* stream) {
+  B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_adam: bad sizes");
+  if (n > 0) { NOT_NULL(W); NOT_NULL(m); NOT_NULL(v); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
+  const double c2 = sqrt(1.0 - (double)beta2_pow_t);
+  AdamOp op{W, m, v, beta1, beta2, (float)((double)lr * c2 / (1.0 - (double)beta1_pow_t)),
+            (float)((double)eps * c2)};
+  return launch_row_update("sparse_adam", unique_ids, rows, num_unique, n, D, V, op, W, m, v,
+                           ST(stream));
+}
+
+int b200rec_sparse_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
+                           const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                           float initial_g2sum, float lo, float hi, void* stream) {
+  B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_adagrad: bad sizes");
+  if (n > 0) { NOT_NULL(W); NOT_NULL(g2sum); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
+  return launch_adagrad(W, g2sum, unique_ids, rows, num_unique, n, D, V, lr, initial_g2sum, lo, hi,
+                        ST(stream));
+}
+
+int b200rec_cross_v2_fwd(const float* x0, const float* xl, const float* xw, const float* bias,
+                         float* out, int64_t B, int C, void* stream) {
+  if (B > 0) { NOT_NULL(x0); NOT_NULL(xl); NOT_NULL(xw); NOT_NULL(bias); NOT_NULL(out); }
+  return launch_cross_v2_fwd(x0, xl, xw, bias, out, B, C, ST(stream));
+}
+
+int b200rec_cross_bwd_workspace_bytes(int64_t B, int C, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  *bytes_host = (size_t)cross_row_slices(B) * (size_t)C * sizeof(float) + 16;
+  return B200REC_OK;
+}
+
+int b200rec_cross_v2_bwd(const float* dout, const float* x0, const float* xw, const float* bias,
+                         float* dxw, float* dx0, float* dbias, int64_t B, int C,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  NOT_NULL(dbias);
+  if (B > 0) { NOT_NULL(dout); NOT_NULL(x0); NOT_NULL(xw); NOT_NULL(bias); NOT_NULL(dxw); NOT_NULL(dx0); NOT_NULL(workspace); }
+  return launch_cross_v2_bwd(dout, x0, xw, bias, dxw, dx0, dbias, B, C, workspace,
+                             workspace_bytes, ST(stream));
+}
+
+int b200rec_shard_bucketize_workspace_bytes(int64_t n, int world, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  ShardPlan p;
+  int rc = make_shard_plan(n, world, &p);
+  if (rc != B200REC_OK) return rc;
+  *bytes_host = p.total;
+  return B200REC_OK;
+}
+
+int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V, int64_t* send_ids,
+                            int64_t* perm, int32_t* inv_perm, int64_t* counts, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  NOT_NULL(counts);
+  if (n > 0) { NOT_NULL(ids); NOT_NULL(send_ids); NOT_NULL(perm); NOT_NULL(inv_perm); NOT_NULL(workspace); }
+  return launch_shard_bucketize(ids, n, world, V, send_ids, perm, inv_perm, counts, workspace,
+                                workspace_bytes, ST(stream));
+}
+
+#include "din_attn_api.inc"
+
+}  // extern "C"

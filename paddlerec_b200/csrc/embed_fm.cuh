@@ -1,0 +1,359 @@
+// K1 / K2: DeepFM's fused multi-slot gather + FM interaction, forward and backward.
+//
+// Replaces FM.forward of the reference (models/rank/deepfm/net.py:105-139) and its autograd
+// (SURVEY.md §8a rows A1-A3, A7).  HBM-bound: per sample the forward moves
+//   F*8 (ids) + Dn*4 (dense) + F*4D (rows) + F*4 (first-order) + (F+Dn)*4D (feat) + 8 (y1,y2)
+// algorithmic bytes (4532 B at F=26, Dn=13, D=16) and ~3 flops per byte, so the design goal is
+// to keep as many independent 128-bit row loads in flight as the LSU allows and to touch
+// every byte once:
+//   * ids/dense of a tile of samples are staged to shared memory with coalesced loads;
+//   * TPR lanes share one sample, each lane owns VEC consecutive floats of every row, so one
+//     warp instruction fetches 32/TPR random rows with full 32 B-sector use (D=16: 8 rows);
+//   * the running sum S and sum of squares Q stay in registers over all F+Dn fields; the
+//     first-order lookups are spread over the TPR lanes; a xor-shuffle finishes y1/y2;
+//   * feat is written once with evict-first stores (it is larger than L2 at B=65536).
+#pragma once
+
+#include "common.cuh"
+
+namespace b200rec {
+
+constexpr int kFieldUnroll = 8;  // independent row loads in flight per lane
+
+template <int TPR>
+struct FwdGeom {
+  static constexpr int kThreads = TPR >= 4 ? 256 : 64 * TPR;
+  static constexpr int kSamples = kThreads / TPR;  // samples per CTA (64 for TPR<=4)
+};
+
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(FwdGeom<TPR>::kThreads)
+embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
+                    const int64_t* __restrict__ ids, const float* __restrict__ dense,
+                    const float* __restrict__ dense_w, const float* __restrict__ dense_w1,
+                    float* __restrict__ feat, float* __restrict__ y1, float* __restrict__ y2,
+                    float* __restrict__ S, int64_t B, int F, int Dn, int D, int64_t V,
+                    int64_t pad) {
+  constexpr int kThreads = FwdGeom<TPR>::kThreads;
+  constexpr int SPB = FwdGeom<TPR>::kSamples;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int64_t* s_ids = reinterpret_cast<int64_t*>(smem_raw);  // [SPB*F]
+  float* s_dense = reinterpret_cast<float*>(s_ids + (size_t)SPB * F);  // [SPB*Dn]
+
+  const int64_t b0 = (int64_t)blockIdx.x * SPB;
+  const int nb = (int)min((int64_t)SPB, B - b0);
+  for (int i = threadIdx.x; i < nb * F; i += kThreads) s_ids[i] = ids[b0 * F + i];
+  for (int i = threadIdx.x; i < nb * Dn; i += kThreads) s_dense[i] = dense[b0 * Dn + i];
+  __syncthreads();
+
+  const int s = threadIdx.x / TPR;
+  const int r = threadIdx.x % TPR;
+  const bool sample_ok = s < nb;
+  const bool lane_ok = r * VEC < D;
+  const int64_t b = b0 + s;
+  const int N = F + Dn;
+
+  Vec<VEC> Ssum = vzero<VEC>();
+  Vec<VEC> Q = vzero<VEC>();
+  float first = 0.f;
+
+  if (sample_ok) {
+    const int64_t* my_ids = s_ids + (size_t)s * F;
+    float* feat_row = feat + (size_t)b * N * D + r * VEC;
+    for (int f0 = 0; f0 < F; f0 += kFieldUnroll) {
+      Vec<VEC> e[kFieldUnroll];
+#pragma unroll
+      for (int j = 0; j < kFieldUnroll; ++j) {
+        e[j] = vzero<VEC>();
+        const int f = f0 + j;
+        if (f < F) {
+          const int64_t id = my_ids[f];
+          const bool in_range = (uint64_t)id < (uint64_t)V;
+          const bool live = in_range && id != pad;
+          if (live && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * D + r * VEC);
+          if (live && (f & (TPR - 1)) == r) first += __ldg(W1 + id);
+          if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kFieldUnroll; ++j) {
+        const int f = f0 + j;
+        if (f < F) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            Ssum.v[k] += e[j].v[k];
+            Q.v[k] = fmaf(e[j].v[k], e[j].v[k], Q.v[k]);
+          }
+          if (lane_ok) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
+        }
+      }
+    }
+    const float* my_dense = s_dense + (size_t)s * Dn;
+    for (int j = 0; j < Dn; ++j) {
+      const float x = my_dense[j];
+      Vec<VEC> e = vzero<VEC>();
+      if (lane_ok) {
+        const Vec<VEC> w = ld_cached<VEC>(dense_w + (size_t)j * D + r * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) e.v[k] = x * w.v[k];
+        st_stream<VEC>(feat_row + (size_t)(F + j) * D, e);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        Ssum.v[k] += e.v[k];
+        Q.v[k] = fmaf(e.v[k], e.v[k], Q.v[k]);
+      }
+      if ((j & (TPR - 1)) == r) first = fmaf(x, __ldg(dense_w1 + j), first);
+    }
+  }
+
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) t += Ssum.v[k] * Ssum.v[k] - Q.v[k];
+  t = group_sum<TPR>(t);
+  first = group_sum<TPR>(first);
+  if (sample_ok) {
+    if (r == 0) {
+      y1[b] = first;
+      y2[b] = 0.5f * t;
+    }
+    if (S != nullptr && lane_ok) st_plain<VEC>(S + (size_t)b * D + r * VEC, Ssum);
+  }
+}
+
+static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids,
+                               const float* dense, const float* dense_w, const float* dense_w1,
+                               float* feat, float* y1, float* y2, float* S, int64_t B, int F,
+                               int Dn, int D, int64_t V, int64_t pad, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "embed_fm_fwd: unsupported D=%d", D);
+  if (rs.vec == 4)
+    B200_REQUIRE(aligned16(W) && aligned16(feat) && aligned16(dense_w) && (!S || aligned16(S)),
+                 "embed_fm_fwd: W/feat/dense_w/S must be 16-byte aligned for D%%4==0");
+  if (rs.vec == 2)
+    B200_REQUIRE(aligned8(W) && aligned8(feat) && aligned8(dense_w) && (!S || aligned8(S)),
+                 "embed_fm_fwd: W/feat/dense_w/S must be 8-byte aligned for D%%2==0");
+  if (B == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int SPB = FwdGeom<TPR>::kSamples;
+    const size_t smem = (size_t)SPB * F * sizeof(int64_t) + (size_t)SPB * Dn * sizeof(float);
+    B200_REQUIRE(smem <= 200 * 1024, "embed_fm_fwd: F=%d Dn=%d tile does not fit shared memory", F,
+                 Dn);
+    auto kern = embed_fm_fwd_kernel<VEC, TPR>;
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (B + SPB - 1) / SPB;
+    kern<<<(unsigned)grid, FwdGeom<TPR>::kThreads, smem, st>>>(W, W1, ids, dense, dense_w, dense_w1,
+                                                               feat, y1, y2, S, B, F, Dn, D, V, pad);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a: sparse part of the backward.  One group of TPR lanes per DISTINCT id (segment of the
+// sorted positions).  dfeat is never materialised for the sparse fields:
+//   dfeat[p] = gy2[b]*(S[b]-feat[p]) + dfeat_dnn[p]      (net.py:123-137 differentiated)
+// and summed in the fixed (stable-sort) order of the segment => deterministic.
+constexpr int kBwdThreads = 256;
+
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kBwdThreads)
+embed_fm_bwd_rows_kernel(const float* __restrict__ feat, const float* __restrict__ S,
+                         const float* __restrict__ dfeat_dnn, const float* __restrict__ gy1,
+                         const float* __restrict__ gy2, const int32_t* __restrict__ seg_offsets,
+                         const int32_t* __restrict__ sorted_pos,
+                         const int32_t* __restrict__ num_unique, float* __restrict__ dW_rows,
+                         float* __restrict__ dW1_rows, int F, int N, int D) {
+  const int U = num_unique[0];
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  const int groups_per_block = kBwdThreads / TPR;
+  for (int64_t u = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / TPR; u < U;
+       u += (int64_t)gridDim.x * groups_per_block) {
+    const int beg = seg_offsets[u];
+    const int end = seg_offsets[u + 1];
+    Vec<VEC> acc = vzero<VEC>();
+    float acc1 = 0.f;
+    for (int i = beg; i < end; ++i) {
+      const int p = sorted_pos[i];
+      const int b = p / F;
+      const int f = p - b * F;
+      const float g2 = __ldg(gy2 + b);
+      acc1 += __ldg(gy1 + b);
+      if (lane_ok) {
+        const size_t off = ((size_t)b * N + f) * D + r * VEC;
+        const Vec<VEC> fe = ld_row<VEC>(feat + off);
+        const Vec<VEC> sv = ld_cached<VEC>(S + (size_t)b * D + r * VEC);
+        Vec<VEC> dd = vzero<VEC>();
+        if (dfeat_dnn != nullptr) dd = ld_row<VEC>(dfeat_dnn + off);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] += fmaf(g2, sv.v[k] - fe.v[k], dd.v[k]);
+      }
+    }
+    if (lane_ok) st_plain<VEC>(dW_rows + (size_t)u * D + r * VEC, acc);
+    if (r == 0) dW1_rows[u] = acc1;
+  }
+}
+
+// K2b: dense-feature part: ddense_w[j,:] = sum_b dense[b,j]*dfeat[b,F+j,:],
+// ddense_w1[j] = sum_b gy1[b]*dense[b,j].  Persistent CTAs accumulate in registers over a
+// strided set of samples, reduce once, and write one partial per CTA; a second tiny kernel adds
+// the partials in a fixed order (deterministic, no float atomics).
+constexpr int kDenseChunk = 8;  // dense features held in registers at once (Dn=13 -> 2 passes)
+
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+embed_fm_bwd_dense_kernel(const float* __restrict__ feat, const float* __restrict__ S,
+                          const float* __restrict__ dfeat_dnn, const float* __restrict__ gy1,
+                          const float* __restrict__ gy2, const float* __restrict__ dense,
+                          float* __restrict__ partials /*[grid, Dn*D + Dn]*/, int64_t B, int F,
+                          int Dn, int D) {
+  constexpr int SPB = kBwdThreads / TPR;
+  constexpr int kWarps = kBwdThreads / 32;
+  __shared__ float s_red[kWarps][32 * VEC];
+  __shared__ float s_red1[kWarps];
+  const int s = threadIdx.x / TPR;
+  const int r = threadIdx.x % TPR;
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const bool lane_ok = r * VEC < D;
+  const int N = F + Dn;
+  float* my_partial = partials + (size_t)blockIdx.x * ((size_t)Dn * D + Dn);
+
+  for (int j0 = 0; j0 < Dn; j0 += kDenseChunk) {
+    Vec<VEC> acc[kDenseChunk];
+    float acc1[kDenseChunk];
+#pragma unroll
+    for (int j = 0; j < kDenseChunk; ++j) {
+      acc[j] = vzero<VEC>();
+      acc1[j] = 0.f;
+    }
+    for (int64_t b = (int64_t)blockIdx.x * SPB + s; b < B; b += (int64_t)gridDim.x * SPB) {
+      const float g2 = __ldg(gy2 + b);
+      const float g1 = __ldg(gy1 + b);
+      Vec<VEC> sv = vzero<VEC>();
+      if (lane_ok) sv = ld_cached<VEC>(S + (size_t)b * D + r * VEC);
+#pragma unroll
+      for (int j = 0; j < kDenseChunk; ++j) {
+        if (j0 + j < Dn) {
+          const float x = __ldg(dense + (size_t)b * Dn + j0 + j);
+          if (lane_ok) {
+            const size_t off = ((size_t)b * N + F + j0 + j) * D + r * VEC;
+            const Vec<VEC> fe = ld_row<VEC>(feat + off);
+            Vec<VEC> dd = vzero<VEC>();
+            if (dfeat_dnn != nullptr) dd = ld_row<VEC>(dfeat_dnn + off);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              acc[j].v[k] = fmaf(x, fmaf(g2, sv.v[k] - fe.v[k], dd.v[k]), acc[j].v[k]);
+          }
+          if (r == 0) acc1[j] = fmaf(g1, x, acc1[j]);
+        }
+      }
+    }
+    // reduce over the samples of the CTA, one dense feature at a time
+#pragma unroll
+    for (int j = 0; j < kDenseChunk; ++j) {
+      if (j0 + j < Dn) {  // uniform across the CTA
+        Vec<VEC> a = acc[j];
+        float a1 = acc1[j];
+#pragma unroll
+        for (int o = TPR; o < 32; o <<= 1) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a.v[k] += __shfl_xor_sync(0xffffffffu, a.v[k], o);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        if (lane < TPR) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s_red[warp][lane * VEC + k] = a.v[k];
+        }
+        if (lane == 0) s_red1[warp] = a1;
+        __syncthreads();
+        if (threadIdx.x < D) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) t += s_red[w][threadIdx.x];
+          my_partial[(size_t)(j0 + j) * D + threadIdx.x] = t;
+        }
+        if (threadIdx.x == 0) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) t += s_red1[w];
+          my_partial[(size_t)Dn * D + j0 + j] = t;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// out[k] = sum_g partials[g][k] in ascending g (deterministic).  `len` is small (Dn*D+Dn).
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int G, int len,
+                                       float* __restrict__ out0, int len0,
+                                       float* __restrict__ out1) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= len) return;
+  float t = 0.f;
+  for (int g = 0; g < G; ++g) t += partials[(size_t)g * len + k];
+  if (k < len0)
+    out0[k] = t;
+  else
+    out1[k - len0] = t;
+}
+
+static int bwd_dense_grid() { return sm_count() * 2; }
+
+static int launch_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_dnn,
+                               const float* gy1, const float* gy2, const float* dense,
+                               const int32_t* seg_offsets, const int32_t* sorted_pos,
+                               const int32_t* num_unique, float* dW_rows, float* dW1_rows,
+                               float* ddense_w, float* ddense_w1, int64_t B, int F, int Dn, int D,
+                               void* ws, size_t ws_bytes, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "embed_fm_bwd: unsupported D=%d", D);
+  const int align = rs.vec * 4;
+  auto ok = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) % align) == 0; };
+  B200_REQUIRE(ok(feat) && ok(S) && ok(dfeat_dnn) && ok(dW_rows),
+               "embed_fm_bwd: feat/S/dfeat_dnn/dW_rows must be %d-byte aligned", align);
+  B200_REQUIRE(B * F < (int64_t)INT32_MAX, "embed_fm_bwd: B*F must fit int32");
+  const int G = bwd_dense_grid();
+  const size_t need = (size_t)G * ((size_t)Dn * D + Dn) * sizeof(float);
+  if (Dn > 0 && ws_bytes < need) {
+    set_error("embed_fm_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return B200REC_ERR_WORKSPACE;
+  }
+  if (B == 0) {
+    if (Dn > 0) {
+      B200_CUDA(cudaMemsetAsync(ddense_w, 0, (size_t)Dn * D * sizeof(float), st));
+      B200_CUDA(cudaMemsetAsync(ddense_w1, 0, (size_t)Dn * sizeof(float), st));
+    }
+    return B200REC_OK;
+  }
+  const int N = F + Dn;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    const int64_t n = B * F;
+    const int gpb = kBwdThreads / TPR;
+    if (n > 0) {
+      const int64_t want = (n + gpb - 1) / gpb;
+      const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
+      embed_fm_bwd_rows_kernel<VEC, TPR><<<grid, kBwdThreads, 0, st>>>(
+          feat, S, dfeat_dnn, gy1, gy2, seg_offsets, sorted_pos, num_unique, dW_rows, dW1_rows, F,
+          N, D);
+    }
+    if (Dn > 0) {
+      embed_fm_bwd_dense_kernel<VEC, TPR><<<G, kBwdThreads, 0, st>>>(
+          feat, S, dfeat_dnn, gy1, gy2, dense, static_cast<float*>(ws), B, F, Dn, D);
+    }
+  });
+  B200_LAUNCH_CHECK();
+  if (Dn > 0) {
+    const int len = Dn * D + Dn;
+    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), G,
+                                                              len, ddense_w, Dn * D, ddense_w1);
+    B200_LAUNCH_CHECK();
+  }
+  return B200REC_OK;
+}
+
+}  // namespace b200rec

@@ -1,0 +1,267 @@
+// Plain embedding gather, segmented (deterministic) scatter-add, and the row-wise optimizers
+// that consume its SelectedRows-style output.
+//
+// Reference call sites: paddle.nn.Embedding in models/rank/wide_deep/net.py:47-53,90,
+// dcn_v2/net.py:45-54,95, din/net.py:33-82,141-147 (forward = lookup_table_v2, backward =
+// lookup_table_v2_grad with sparse=True -> SelectedRows); optimizers: Adam(lazy_mode=True)
+// models/rank/deepfm/static_model.py:101-103, SGD models/rank/din/dygraph_model.py:64-73,
+// SparseAdaGradSGDRule models/rank/slot_dnn/config_online.yaml:57-79.
+//
+// All kernels are HBM-bound: algorithmic bytes per looked-up row are 8 (id) + 2*4D.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200rec {
+
+constexpr int kGatherThreads = 256;
+constexpr int kGatherRowsPerGroup = 4;  // independent rows in flight per lane group
+
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(const float* __restrict__ W, const int64_t* __restrict__ ids,
+              float* __restrict__ out, int64_t n, int D, int64_t V, int64_t pad) {
+  constexpr int GPB = kGatherThreads / TPR;
+  const int g = threadIdx.x / TPR;
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  const int64_t base = ((int64_t)blockIdx.x * GPB + g) * kGatherRowsPerGroup;
+  Vec<VEC> e[kGatherRowsPerGroup];
+#pragma unroll
+  for (int j = 0; j < kGatherRowsPerGroup; ++j) {
+    e[j] = vzero<VEC>();
+    const int64_t i = base + j;
+    if (i < n) {
+      const int64_t id = __ldg(ids + i);
+      const bool in_range = (uint64_t)id < (uint64_t)V;
+      if (in_range && id != pad && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * D + r * VEC);
+      if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kGatherRowsPerGroup; ++j) {
+    const int64_t i = base + j;
+    if (i < n && lane_ok) st_stream<VEC>(out + (size_t)i * D + r * VEC, e[j]);
+  }
+}
+
+static int launch_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D,
+                         int64_t V, int64_t pad, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "gather: unsupported D=%d", D);
+  const int align = rs.vec * 4;
+  B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % align == 0 &&
+                   reinterpret_cast<uintptr_t>(out) % align == 0,
+               "gather: W/out must be %d-byte aligned", align);
+  if (n == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int rows_per_block = (kGatherThreads / TPR) * kGatherRowsPerGroup;
+    const int64_t grid = (n + rows_per_block - 1) / rows_per_block;
+    gather_kernel<VEC, TPR><<<(unsigned)grid, kGatherThreads, 0, st>>>(W, ids, out, n, D, V, pad);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+// rows[u,:] = sum over the segment of dOut[sorted_pos[i],:], fixed order.
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kGatherThreads)
+segment_reduce_kernel(const float* __restrict__ dOut, const int32_t* __restrict__ seg_offsets,
+                      const int32_t* __restrict__ sorted_pos,
+                      const int32_t* __restrict__ num_unique, float* __restrict__ rows, int D) {
+  constexpr int GPB = kGatherThreads / TPR;
+  const int U = num_unique[0];
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  for (int64_t u = (int64_t)blockIdx.x * GPB + threadIdx.x / TPR; u < U;
+       u += (int64_t)gridDim.x * GPB) {
+    const int beg = seg_offsets[u];
+    const int end = seg_offsets[u + 1];
+    Vec<VEC> acc = vzero<VEC>();
+    if (lane_ok) {
+      int i = beg;
+      for (; i + 1 < end; i += 2) {  // two rows in flight
+        const Vec<VEC> a = ld_row<VEC>(dOut + (size_t)sorted_pos[i] * D + r * VEC);
+        const Vec<VEC> c = ld_row<VEC>(dOut + (size_t)sorted_pos[i + 1] * D + r * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = (acc.v[k] + a.v[k]) + c.v[k];
+      }
+      if (i < end) {
+        const Vec<VEC> a = ld_row<VEC>(dOut + (size_t)sorted_pos[i] * D + r * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] += a.v[k];
+      }
+      st_plain<VEC>(rows + (size_t)u * D + r * VEC, acc);
+    }
+  }
+}
+
+static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
+                                 const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
+                                 int64_t n, int D, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "segment_reduce: unsupported D=%d", D);
+  const int align = rs.vec * 4;
+  B200_REQUIRE(reinterpret_cast<uintptr_t>(dOut) % align == 0 &&
+                   reinterpret_cast<uintptr_t>(rows) % align == 0,
+               "segment_reduce: dOut/rows must be %d-byte aligned", align);
+  if (n == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int GPB = kGatherThreads / TPR;
+    const int64_t want = (n + GPB - 1) / GPB;
+    const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
+    segment_reduce_kernel<VEC, TPR><<<grid, kGatherThreads, 0, st>>>(dOut, seg_offsets, sorted_pos,
+                                                                     num_unique, rows, D);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+// ---- row-wise update kernels ---------------------------------------------------------------
+// Common skeleton: one TPR-lane group per distinct row; Op::apply does the RMW of that row.
+struct RowsToDenseOp {
+  float* dW;
+  template <int VEC>
+  __device__ __forceinline__ void apply(size_t row_off, const Vec<VEC>& g, int) const {
+    Vec<VEC> w = ld_cached<VEC>(dW + row_off);  // plain load is fine: rows are distinct
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) w.v[k] += g.v[k];
+    st_plain<VEC>(dW + row_off, w);
+  }
+};
+
+struct SgdOp {
+  float* W;
+  float lr;
+  template <int VEC>
+  __device__ __forceinline__ void apply(size_t row_off, const Vec<VEC>& g, int) const {
+    Vec<VEC> w = *reinterpret_cast<const Vec<VEC>*>(W + row_off);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) w.v[k] = fmaf(-lr, g.v[k], w.v[k]);
+    st_plain<VEC>(W + row_off, w);
+  }
+};
+
+struct AdamOp {
+  float* W;
+  float* m;
+  float* v;
+  float beta1, beta2, lr_t, eps_t;  // lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps_t = eps*sqrt(1-b2^t)
+  template <int VEC>
+  __device__ __forceinline__ void apply(size_t row_off, const Vec<VEC>& g, int) const {
+    Vec<VEC> w = *reinterpret_cast<const Vec<VEC>*>(W + row_off);
+    Vec<VEC> mm = *reinterpret_cast<const Vec<VEC>*>(m + row_off);
+    Vec<VEC> vv = *reinterpret_cast<const Vec<VEC>*>(v + row_off);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      mm.v[k] = beta1 * mm.v[k] + (1.f - beta1) * g.v[k];
+      vv.v[k] = beta2 * vv.v[k] + (1.f - beta2) * g.v[k] * g.v[k];
+      w.v[k] -= lr_t * (mm.v[k] / (sqrtf(vv.v[k]) + eps_t));
+    }
+    st_plain<VEC>(W + row_off, w);
+    st_plain<VEC>(m + row_off, mm);
+    st_plain<VEC>(v + row_off, vv);
+  }
+};
+
+template <int VEC, int TPR, typename Op>
+__global__ void __launch_bounds__(kGatherThreads)
+row_update_kernel(const int64_t* __restrict__ unique_ids, const float* __restrict__ rows,
+                  const int32_t* __restrict__ num_unique, int D, int64_t V, Op op) {
+  constexpr int GPB = kGatherThreads / TPR;
+  const int U = num_unique[0];
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  for (int64_t u = (int64_t)blockIdx.x * GPB + threadIdx.x / TPR; u < U;
+       u += (int64_t)gridDim.x * GPB) {
+    const int64_t id = unique_ids[u];
+    if ((uint64_t)id >= (uint64_t)V || !lane_ok) continue;
+    const Vec<VEC> g = ld_row<VEC>(rows + (size_t)u * D + r * VEC);
+    op.template apply<VEC>((size_t)id * D + r * VEC, g, r);
+  }
+}
+
+// AdaGrad with ONE accumulator per row needs the row-mean of g^2 -> its own kernel.
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kGatherThreads)
+row_adagrad_kernel(float* __restrict__ W, float* __restrict__ g2sum,
+                   const int64_t* __restrict__ unique_ids, const float* __restrict__ rows,
+                   const int32_t* __restrict__ num_unique, int D, int64_t V, float lr, float g0,
+                   float lo, float hi) {
+  constexpr int GPB = kGatherThreads / TPR;
+  const int U = num_unique[0];
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  // whole warps iterate together so the group shuffles stay converged
+  const int64_t groups_total = (int64_t)gridDim.x * GPB;
+  const int64_t U_pad = ((int64_t)U + 32 / TPR - 1) / (32 / TPR) * (32 / TPR);
+  for (int64_t u = (int64_t)blockIdx.x * GPB + threadIdx.x / TPR; u < U_pad; u += groups_total) {
+    const bool live = u < U;
+    int64_t id = live ? unique_ids[u] : -1;
+    const bool ok = live && (uint64_t)id < (uint64_t)V && lane_ok;
+    Vec<VEC> g = vzero<VEC>();
+    if (ok) g = ld_row<VEC>(rows + (size_t)u * D + r * VEC);
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) sq = fmaf(g.v[k], g.v[k], sq);
+    sq = group_sum<TPR>(sq);
+    if (ok) {
+      const float acc = g2sum[id];
+      const float scale = sqrtf(g0 / (g0 + acc));
+      Vec<VEC> w = *reinterpret_cast<const Vec<VEC>*>(W + (size_t)id * D + r * VEC);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        w.v[k] -= lr * g.v[k] * scale;
+        w.v[k] = fminf(fmaxf(w.v[k], lo), hi);
+      }
+      st_plain<VEC>(W + (size_t)id * D + r * VEC, w);
+    }
+    __syncwarp();
+    if (ok && r == 0) g2sum[id] += sq / (float)D;
+  }
+}
+
+template <typename Op>
+static int launch_row_update(const char* what, const int64_t* unique_ids, const float* rows,
+                             const int32_t* num_unique, int64_t n, int D, int64_t V, Op op,
+                             const void* a0, const void* a1, const void* a2, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "%s: unsupported D=%d", what, D);
+  const int align = rs.vec * 4;
+  auto ok = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) % align) == 0; };
+  B200_REQUIRE(ok(rows) && ok(a0) && ok(a1) && ok(a2), "%s: buffers must be %d-byte aligned", what,
+               align);
+  if (n == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int GPB = kGatherThreads / TPR;
+    const int64_t want = (n + GPB - 1) / GPB;
+    const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
+    row_update_kernel<VEC, TPR, Op><<<grid, kGatherThreads, 0, st>>>(unique_ids, rows, num_unique,
+                                                                     D, V, op);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static int launch_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
+                          const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                          float g0, float lo, float hi, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "sparse_adagrad: unsupported D=%d", D);
+  const int align = rs.vec * 4;
+  B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % align == 0 &&
+                   reinterpret_cast<uintptr_t>(rows) % align == 0,
+               "sparse_adagrad: W/rows must be %d-byte aligned", align);
+  if (n == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int GPB = kGatherThreads / TPR;
+    const int64_t want = (n + GPB - 1) / GPB;
+    const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
+    row_adagrad_kernel<VEC, TPR><<<grid, kGatherThreads, 0, st>>>(W, g2sum, unique_ids, rows,
+                                                                  num_unique, D, V, lr, g0, lo, hi);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+}  // namespace b200rec

@@ -1,0 +1,67 @@
+"""Loss / metric helpers with Paddle's semantics (host-side plumbing, plain torch ops)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def log_loss(pred: torch.Tensor, label: torch.Tensor, epsilon: float = 1e-4) -> torch.Tensor:
+    """paddle.nn.functional.log_loss: -y*log(p+eps) - (1-y)*log(1-p+eps), eps=1e-4 by default
+    (called at models/rank/deepfm/dygraph_model.py:53-58)."""
+    return -label * torch.log(pred + epsilon) - (1.0 - label) * torch.log(1.0 - pred + epsilon)
+
+
+class Auc:
+    """paddle.metric.Auc("ROC", num_thresholds=4095): bucketed positive/negative histograms and a
+    trapezoid sweep.  Unlike the reference (`.numpy()` every step, dygraph_model.py:83-84) the
+    histograms stay on the device; only `accumulate()` synchronises."""
+
+    def __init__(self, curve: str = "ROC", num_thresholds: int = 4095):
+        self.num_thresholds = num_thresholds
+        self._pos = None
+        self._neg = None
+
+    def reset(self):
+        self._pos = None
+        self._neg = None
+
+    def update(self, preds, labels):
+        """preds: [B,2] (P(neg), P(pos)) or [B]/[B,1] P(pos); labels: [B,1] or [B]."""
+        if isinstance(preds, np.ndarray):
+            preds = torch.from_numpy(preds)
+        if isinstance(labels, np.ndarray):
+            labels = torch.from_numpy(labels)
+        p = preds[:, 1] if (preds.dim() == 2 and preds.shape[1] == 2) else preds.reshape(-1)
+        y = labels.reshape(-1).to(p.device)
+        nb = self.num_thresholds + 1
+        idx = (p.detach().float() * self.num_thresholds).to(torch.int64).clamp_(0, nb - 1)
+        pos_mask = y != 0
+        pos = torch.bincount(idx[pos_mask], minlength=nb)
+        neg = torch.bincount(idx[~pos_mask], minlength=nb)
+        if self._pos is None:
+            self._pos, self._neg = pos, neg
+        else:
+            self._pos += pos
+            self._neg += neg
+
+    def stats(self):
+        """(stat_pos, stat_neg) int64 tensors — what utils_single.py:160-206 all-reduces."""
+        return self._pos, self._neg
+
+    def accumulate(self) -> float:
+        if self._pos is None:
+            return 0.0
+        pos = self._pos.cpu().numpy().astype(np.float64)
+        neg = self._neg.cpu().numpy().astype(np.float64)
+        return auc_from_stats(pos, neg)
+
+
+def auc_from_stats(pos: np.ndarray, neg: np.ndarray) -> float:
+    tot_pos = tot_neg = 0.0
+    auc = 0.0
+    for idx in range(len(pos) - 1, -1, -1):
+        tot_pos_prev, tot_neg_prev = tot_pos, tot_neg
+        tot_pos += pos[idx]
+        tot_neg += neg[idx]
+        auc += abs(tot_neg - tot_neg_prev) * (tot_pos + tot_pos_prev) / 2.0
+    return auc / tot_pos / tot_neg if tot_pos > 0.0 and tot_neg > 0.0 else 0.0

@@ -1,0 +1,404 @@
+"""Torch-facing wrappers of the C ABI (include/b200rec.h).
+
+Two layers:
+  * `raw_*`  — one function per C entry point; takes CUDA tensors, allocates outputs/workspace
+               with torch's caching allocator (the "caller owns every buffer" side of the ABI) and
+               enqueues on torch's current stream.
+  * autograd.Function classes — what the net.py-shaped layers call.  The sparse-table gradients
+    are not materialised as dense [V,D] tensors: backward stores a `SelectedRows` (Paddle's name
+    for the rows/value pair that `Embedding(sparse=True)` produces) on the owning table object.
+
+There is deliberately no CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.B200RecError(
+            "%s must be a CUDA tensor: the b200rec hot path has no CPU fallback" % name)
+    if t.dtype != dtype:
+        raise _lib.B200RecError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- accounting -------------------------------------------------------------------------------
+# LAUNCHES counts OUR kernels (not CUB's, not torch's) enqueued through the C ABI; bench.py reports
+# it as `gpu_launches`.  KERNELS_PER_CALL is the static number of our kernels each entry point runs.
+LAUNCHES = 0
+KERNELS_PER_CALL = {
+    "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 3, "gather": 1, "segment_reduce": 1,
+    "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
+    "cross_v2_bwd": 2, "shard_bucketize": 2,
+}
+# When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
+EVENTS = None
+
+
+def _count(name: str) -> None:
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL[name]
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if EVENTS is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if EVENTS is not None:
+            self.end.record()
+            EVENTS.append((self.name, self.start, self.end))
+        return False
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
+    """A grow-only per-(device, tag) scratch buffer.  Safe because every consumer runs on the
+    current stream in program order."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class IdGroups:
+    """Output of b200rec_group_ids: positions grouped by distinct id."""
+    unique_ids: torch.Tensor   # int64 [n]   (first num[0] valid)
+    seg_offsets: torch.Tensor  # int32 [n+1]
+    sorted_pos: torch.Tensor   # int32 [n]
+    num: torch.Tensor          # int32 [2] on device: {#distinct, #kept}
+    n: int
+    height: int                # V
+
+
+@dataclass
+class SelectedRows:
+    """rows/value pair: gradient of a [height, D] table restricted to the touched rows.
+    Mirrors Paddle's SelectedRows (what paddle.nn.Embedding(sparse=True) hands the optimizer),
+    already merged (each row appears once)."""
+    rows: torch.Tensor    # int64 [n]  (first num[0] valid)
+    value: torch.Tensor   # f32 [n, D] (first num[0] valid; the rest is unspecified)
+    num: torch.Tensor     # int32 [2] device
+    height: int
+
+    def to_dense(self) -> torch.Tensor:
+        D = self.value.shape[1]
+        out = torch.zeros(self.height, D, dtype=torch.float32, device=self.value.device)
+        raw_rows_to_dense(self, out)
+        return out
+
+    def count(self) -> int:
+        return int(self.num[0].item())
+
+
+def raw_oob_count(reset: bool = True) -> int:
+    lib = _lib.load()
+    out = ctypes.c_uint64(0)
+    check(lib.b200rec_oob_count(ctypes.byref(out), int(reset), _stream()), "oob_count")
+    return int(out.value)
+
+
+def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, padding_idx: int, want_S: bool = True):
+    lib = _lib.load()
+    W = _req(W, torch.float32, "W")
+    W1 = _req(W1, torch.float32, "W1")
+    ids = _req(ids, torch.int64, "ids")
+    dense = _req(dense, torch.float32, "dense")
+    dense_w = _req(dense_w, torch.float32, "dense_w")
+    dense_w1 = _req(dense_w1, torch.float32, "dense_w1")
+    B, F = ids.shape
+    Dn = dense.shape[1] if dense.numel() or dense.dim() == 2 else 0
+    V, D = W.shape
+    assert W1.numel() == V and dense.shape[0] == B
+    assert dense_w.numel() == Dn * D and dense_w1.numel() == Dn
+    dev = W.device
+    feat = torch.empty(B, F + Dn, D, dtype=torch.float32, device=dev)
+    y1 = torch.empty(B, dtype=torch.float32, device=dev)
+    y2 = torch.empty(B, dtype=torch.float32, device=dev)
+    S = torch.empty(B, D, dtype=torch.float32, device=dev) if want_S else None
+    with _Timed("embed_fm_fwd"):
+        check(lib.b200rec_embed_fm_fwd(ptr(W), ptr(W1), ptr(ids), ptr(dense), ptr(dense_w),
+                                       ptr(dense_w1), ptr(feat), ptr(y1), ptr(y2), ptr(S), B, F, Dn,
+                                       D, V, int(padding_idx), _stream()), "embed_fm_fwd")
+    _count("embed_fm_fwd")
+    return feat, y1, y2, S
+
+
+def raw_group_ids(ids: torch.Tensor, V: int, padding_idx: int) -> IdGroups:
+    lib = _lib.load()
+    ids = _req(ids, torch.int64, "ids").reshape(-1)
+    n = ids.numel()
+    dev = ids.device
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_group_ids_workspace_bytes(n, V, ctypes.byref(nbytes)), "group_ids_ws")
+    ws = workspace(nbytes.value, dev, "group")
+    unique_ids = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    seg_offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    sorted_pos = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    num = torch.empty(2, dtype=torch.int32, device=dev)
+    check(lib.b200rec_group_ids(ptr(ids), n, V, int(padding_idx), ptr(unique_ids), ptr(seg_offsets),
+                                ptr(sorted_pos), ptr(num), ptr(ws), ws.numel(), _stream()),
+          "group_ids")
+    _count("group_ids")
+    return IdGroups(unique_ids, seg_offsets, sorted_pos, num, n, V)
+
+
+def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_pos, num, F: int):
+    """Returns (dW_rows [n,D], dW1_rows [n], ddense_w [Dn,D], ddense_w1 [Dn])."""
+    lib = _lib.load()
+    feat = _req(feat, torch.float32, "feat")
+    S = _req(S, torch.float32, "S")
+    if dfeat_dnn is not None:
+        dfeat_dnn = _req(dfeat_dnn, torch.float32, "dfeat_dnn")
+    gy1 = _req(gy1, torch.float32, "gy1").reshape(-1)
+    gy2 = _req(gy2, torch.float32, "gy2").reshape(-1)
+    dense = _req(dense, torch.float32, "dense")
+    B, N, D = feat.shape
+    Dn = N - F
+    n = B * F
+    dev = feat.device
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_embed_fm_bwd_workspace_bytes(B, F, Dn, D, ctypes.byref(nbytes)), "fm_bwd_ws")
+    ws = workspace(nbytes.value, dev, "fm_bwd")
+    dW_rows = torch.empty(max(n, 1), D, dtype=torch.float32, device=dev)
+    dW1_rows = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    ddense_w = torch.empty(Dn, D, dtype=torch.float32, device=dev)
+    ddense_w1 = torch.empty(Dn, dtype=torch.float32, device=dev)
+    check(lib.b200rec_embed_fm_bwd(ptr(feat), ptr(S), ptr(dfeat_dnn), ptr(gy1), ptr(gy2),
+                                   ptr(dense), ptr(seg_offsets), ptr(sorted_pos), ptr(num),
+                                   ptr(dW_rows), ptr(dW1_rows), ptr(ddense_w), ptr(ddense_w1), B, F,
+                                   Dn, D, ptr(ws), ws.numel(), _stream()), "embed_fm_bwd")
+    _count("embed_fm_bwd")
+    return dW_rows, dW1_rows, ddense_w, ddense_w1
+
+
+def raw_gather(W: torch.Tensor, ids: torch.Tensor, padding_idx: int) -> torch.Tensor:
+    lib = _lib.load()
+    W = _req(W, torch.float32, "W")
+    ids = _req(ids, torch.int64, "ids")
+    V, D = W.shape
+    n = ids.numel()
+    out = torch.empty(*ids.shape, D, dtype=torch.float32, device=W.device)
+    check(lib.b200rec_gather(ptr(W), ptr(ids), ptr(out), n, D, V, int(padding_idx), _stream()),
+          "gather")
+    _count("gather")
+    return out
+
+
+def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int) -> torch.Tensor:
+    lib = _lib.load()
+    dOut = _req(dOut, torch.float32, "dOut")
+    D = dOut.shape[-1]
+    rows = torch.empty(max(n, 1), D, dtype=torch.float32, device=dOut.device)
+    check(lib.b200rec_segment_reduce(ptr(dOut), ptr(groups_seg), ptr(groups_pos), ptr(num),
+                                     ptr(rows), n, D, _stream()), "segment_reduce")
+    _count("segment_reduce")
+    return rows
+
+
+def raw_rows_to_dense(sr: SelectedRows, dW: torch.Tensor) -> None:
+    lib = _lib.load()
+    dW = _req(dW, torch.float32, "dW")
+    n, D = sr.value.shape
+    check(lib.b200rec_rows_to_dense(ptr(sr.rows), ptr(sr.value), ptr(sr.num), ptr(dW), n, D,
+                                    sr.height, _stream()), "rows_to_dense")
+    _count("rows_to_dense")
+
+
+def raw_sparse_sgd(W: torch.Tensor, sr: SelectedRows, lr: float) -> None:
+    lib = _lib.load()
+    n, D = sr.value.shape
+    check(lib.b200rec_sparse_sgd(ptr(W), ptr(sr.rows), ptr(sr.value), ptr(sr.num), n, D, sr.height,
+                                 float(lr), _stream()), "sparse_sgd")
+    _count("sparse_sgd")
+
+
+def raw_sparse_adam(W, m, v, sr: SelectedRows, lr, beta1, beta2, eps, beta1_pow, beta2_pow) -> None:
+    lib = _lib.load()
+    n, D = sr.value.shape
+    check(lib.b200rec_sparse_adam(ptr(W), ptr(m), ptr(v), ptr(sr.rows), ptr(sr.value), ptr(sr.num),
+                                  n, D, sr.height, float(lr), float(beta1), float(beta2),
+                                  float(eps), float(beta1_pow), float(beta2_pow), _stream()),
+          "sparse_adam")
+    _count("sparse_adam")
+
+
+def raw_sparse_adagrad(W, g2sum, sr: SelectedRows, lr, initial_g2sum, lo, hi) -> None:
+    lib = _lib.load()
+    n, D = sr.value.shape
+    check(lib.b200rec_sparse_adagrad(ptr(W), ptr(g2sum), ptr(sr.rows), ptr(sr.value), ptr(sr.num),
+                                     n, D, sr.height, float(lr), float(initial_g2sum), float(lo),
+                                     float(hi), _stream()), "sparse_adagrad")
+    _count("sparse_adagrad")
+
+
+def raw_cross_v2_fwd(x0, xl, xw, bias) -> torch.Tensor:
+    lib = _lib.load()
+    x0 = _req(x0, torch.float32, "x0")
+    xl = _req(xl, torch.float32, "xl")
+    xw = _req(xw, torch.float32, "xw")
+    bias = _req(bias, torch.float32, "bias")
+    B, C = x0.shape
+    out = torch.empty_like(x0)
+    check(lib.b200rec_cross_v2_fwd(ptr(x0), ptr(xl), ptr(xw), ptr(bias), ptr(out), B, C, _stream()),
+          "cross_v2_fwd")
+    _count("cross_v2_fwd")
+    return out
+
+
+def raw_cross_v2_bwd(dout, x0, xw, bias):
+    """returns (dxw, dx0, dbias)."""
+    lib = _lib.load()
+    dout = _req(dout, torch.float32, "dout")
+    B, C = dout.shape
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_cross_bwd_workspace_bytes(B, C, ctypes.byref(nbytes)), "cross_ws")
+    ws = workspace(nbytes.value, dout.device, "cross")
+    dxw = torch.empty_like(dout)
+    dx0 = torch.empty_like(dout)
+    dbias = torch.empty(C, dtype=torch.float32, device=dout.device)
+    check(lib.b200rec_cross_v2_bwd(ptr(dout), ptr(x0), ptr(xw), ptr(bias), ptr(dxw), ptr(dx0),
+                                   ptr(dbias), B, C, ptr(ws), ws.numel(), _stream()), "cross_v2_bwd")
+    _count("cross_v2_bwd")
+    return dxw, dx0, dbias
+
+
+def raw_shard_bucketize(ids: torch.Tensor, world: int, V: int):
+    """Returns (send_ids [n], perm [n] i64, inv_perm [n] i32, counts [world] i64 device)."""
+    lib = _lib.load()
+    ids = _req(ids, torch.int64, "ids").reshape(-1)
+    n = ids.numel()
+    dev = ids.device
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_shard_bucketize_workspace_bytes(n, world, ctypes.byref(nbytes)), "shard_ws")
+    ws = workspace(nbytes.value, dev, "shard")
+    send_ids = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    perm = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    inv_perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    check(lib.b200rec_shard_bucketize(ptr(ids), n, world, V, ptr(send_ids), ptr(perm),
+                                      ptr(inv_perm), ptr(counts), ptr(ws), ws.numel(), _stream()),
+          "shard_bucketize")
+    _count("shard_bucketize")
+    return send_ids[:n], perm[:n], inv_perm[:n], counts
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd glue
+class _EmbedFM(torch.autograd.Function):
+    """FM.forward of models/rank/deepfm/net.py:105-139 as one kernel (+ one in backward).
+
+    `sink` is the object (an `EmbeddingTablePair`) that receives the two SelectedRows gradients.
+    """
+
+    @staticmethod
+    def forward(ctx, W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink):
+        D = W.shape[1]
+        feat, y1, y2, S = raw_embed_fm_fwd(W, W1, ids, dense, dense_w.reshape(-1, D),
+                                           dense_w1.reshape(-1), padding_idx)
+        ctx.save_for_backward(ids, dense, feat, S)
+        ctx.padding_idx = padding_idx
+        ctx.sink = sink
+        ctx.V = W.shape[0]
+        ctx.dense_w_shape = dense_w.shape
+        ctx.mark_non_differentiable(S)
+        return feat, y1.unsqueeze(1), y2.unsqueeze(1), S
+
+    @staticmethod
+    def backward(ctx, dfeat, dy1, dy2, _dS):
+        ids, dense, feat, S = ctx.saved_tensors
+        B, F = ids.shape
+        dev = feat.device
+        gy1 = dy1.reshape(-1).contiguous() if dy1 is not None else torch.zeros(B, device=dev)
+        gy2 = dy2.reshape(-1).contiguous() if dy2 is not None else torch.zeros(B, device=dev)
+        if dfeat is not None:
+            dfeat = dfeat.contiguous()
+        groups = ctx.sink.groups_for(ids, ctx.V, ctx.padding_idx)
+        dW_rows, dW1_rows, ddense_w, ddense_w1 = raw_embed_fm_bwd(
+            feat, S, dfeat, gy1, gy2, dense, groups.seg_offsets, groups.sorted_pos, groups.num, F)
+        ctx.sink.accept(SelectedRows(groups.unique_ids, dW_rows, groups.num, ctx.V),
+                        SelectedRows(groups.unique_ids, dW1_rows.unsqueeze(1), groups.num, ctx.V))
+        return (None, None, None, None, ddense_w.reshape(ctx.dense_w_shape), ddense_w1, None, None)
+
+
+class _Gather(torch.autograd.Function):
+    """paddle.nn.Embedding forward/backward (lookup_table_v2 / _grad, sparse=True)."""
+
+    @staticmethod
+    def forward(ctx, W, ids, padding_idx, sink, _hook):
+        out = raw_gather(W, ids, padding_idx)
+        ctx.save_for_backward(ids)
+        ctx.padding_idx = padding_idx
+        ctx.sink = sink
+        ctx.V = W.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        groups = raw_group_ids(ids, ctx.V, ctx.padding_idx)
+        rows = raw_segment_reduce(dout.reshape(-1, dout.shape[-1]), groups.seg_offsets,
+                                  groups.sorted_pos, groups.num, groups.n)
+        ctx.sink.accept(SelectedRows(groups.unique_ids, rows, groups.num, ctx.V))
+        return None, None, None, None, None
+
+
+class _CrossV2(torch.autograd.Function):
+    """One CrossNetV2 layer: X_{i+1} = X_i + X_0 * (X_i W + b)   (dcn_v2/net.py:222-226).
+    The GEMMs go through `mm` (the tensor-core library path chosen by paddlerec_b200.linear)."""
+
+    @staticmethod
+    def forward(ctx, x0, xl, W, bias, mm):
+        xw = mm(xl, W)
+        out = raw_cross_v2_fwd(x0, xl, xw, bias)
+        ctx.save_for_backward(x0, xl, xw, W, bias)
+        ctx.mm = mm
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x0, xl, xw, W, bias = ctx.saved_tensors
+        dout = dout.contiguous()
+        dxw, dx0, dbias = raw_cross_v2_bwd(dout, x0, xw, bias)
+        dxl = dout + ctx.mm(dxw, W.t())
+        dW = ctx.mm(xl.t(), dxw)
+        return dx0, dxl, dW, dbias, None
+
+
+def embed_fm(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink):
+    return _EmbedFM.apply(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink)
+
+
+def gather(W, ids, padding_idx, sink, hook):
+    return _Gather.apply(W, ids, padding_idx, sink, hook)
+
+
+def cross_v2(x0, xl, W, bias, mm):
+    return _CrossV2.apply(x0, xl, W, bias, mm)

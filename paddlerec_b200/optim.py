@@ -1,0 +1,191 @@
+"""Optimizers with paddle.optimizer's surface (`step()`, `clear_grad()`), where the embedding
+tables are updated row-wise from their SelectedRows gradients by the C-ABI kernels
+(b200rec_sparse_adam / _sgd / _adagrad) and the small dense parameters by torch's fused optimizers.
+
+Reference call sites: Adam  models/rank/deepfm/dygraph_model.py:61-65 (dygraph: non-lazy) and
+models/rank/deepfm/static_model.py:101-103 (lazy_mode=True); SGD + PiecewiseDecay
+models/rank/din/dygraph_model.py:64-73; ClipGradByGlobalNorm models/rank/dcn_v2/dygraph_model.py:81-88.
+Difference kept on purpose: only lazy (row-wise) table updates are implemented —
+non-lazy Adam would stream all V rows every step (77 GB at V=1e8, D=16).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Optional, Union
+
+import torch
+
+from . import ops
+
+
+class PiecewiseDecay:
+    """paddle.optimizer.lr.PiecewiseDecay(boundaries, values)."""
+
+    def __init__(self, boundaries, values):
+        assert len(values) == len(boundaries) + 1
+        self.boundaries, self.values = list(boundaries), list(values)
+        self.last_epoch = 0
+
+    def __call__(self) -> float:
+        for b, v in zip(self.boundaries, self.values):
+            if self.last_epoch < b:
+                return v
+        return self.values[-1]
+
+    def step(self):
+        self.last_epoch += 1
+
+
+class ClipGradByGlobalNorm:
+    def __init__(self, clip_norm: float):
+        self.clip_norm = float(clip_norm)
+
+
+def _is_sparse(p: torch.Tensor) -> bool:
+    return getattr(p, "is_sparse_table", False)
+
+
+def _valid_rows(sr: ops.SelectedRows) -> torch.Tensor:
+    n = sr.value.shape[0]
+    mask = torch.arange(n, device=sr.value.device) < sr.num[0]
+    return torch.where(mask.unsqueeze(1), sr.value, torch.zeros((), device=sr.value.device))
+
+
+class _Base:
+    def __init__(self, learning_rate, parameters: Iterable[torch.Tensor], grad_clip=None):
+        params = list(parameters)
+        self._sparse: List[torch.Tensor] = [p for p in params if _is_sparse(p)]
+        self._dense: List[torch.Tensor] = [p for p in params if not _is_sparse(p) and p.requires_grad]
+        self._lr = learning_rate
+        self._clip: Optional[ClipGradByGlobalNorm] = grad_clip
+        self.step_count = 0
+
+    def get_lr(self) -> float:
+        return float(self._lr()) if callable(self._lr) else float(self._lr)
+
+    def clear_grad(self) -> None:
+        for p in self._dense:
+            p.grad = None
+        for p in self._sparse:
+            p.grad_rows = None
+
+    zero_grad = clear_grad
+
+    def global_grad_norm(self) -> torch.Tensor:
+        sq = []
+        for p in self._dense:
+            if p.grad is not None:
+                sq.append(p.grad.float().square().sum())
+        for p in self._sparse:
+            sr = getattr(p, "grad_rows", None)
+            if sr is not None:
+                sq.append(_valid_rows(sr).square().sum())
+        return torch.stack(sq).sum().sqrt()
+
+    def _apply_clip(self) -> None:
+        if self._clip is None:
+            return
+        norm = self.global_grad_norm()
+        scale = self._clip.clip_norm / torch.clamp(norm, min=self._clip.clip_norm)
+        for p in self._dense:
+            if p.grad is not None:
+                p.grad.mul_(scale)
+        for p in self._sparse:
+            sr = getattr(p, "grad_rows", None)
+            if sr is not None:
+                sr.value.mul_(scale)
+
+
+class SGD(_Base):
+    def __init__(self, learning_rate, parameters, grad_clip=None):
+        super().__init__(learning_rate, parameters, grad_clip)
+        self._torch = torch.optim.SGD(self._dense, lr=self.get_lr()) if self._dense else None
+
+    @torch.no_grad()
+    def step(self) -> None:
+        self._apply_clip()
+        lr = self.get_lr()
+        if self._torch is not None:
+            for g in self._torch.param_groups:
+                g["lr"] = lr
+            self._torch.step()
+        for p in self._sparse:
+            sr = getattr(p, "grad_rows", None)
+            if sr is not None:
+                ops.raw_sparse_sgd(p.data, sr, lr)
+        self.step_count += 1
+        if hasattr(self._lr, "step"):
+            self._lr.step()
+
+
+class Adam(_Base):
+    """Adam with lazy (row-wise) updates of the sparse tables."""
+
+    def __init__(self, learning_rate=0.001, parameters=(), beta1=0.9, beta2=0.999, epsilon=1e-8,
+                 lazy_mode=True, grad_clip=None):
+        super().__init__(learning_rate, parameters, grad_clip)
+        if not lazy_mode and self._sparse:
+            raise NotImplementedError(
+                "non-lazy Adam over a sparse table is not supported (see module docstring)")
+        self.beta1, self.beta2, self.eps = beta1, beta2, epsilon
+        self._torch = (torch.optim.Adam(self._dense, lr=self.get_lr(), betas=(beta1, beta2),
+                                        eps=epsilon, fused=self._dense[0].is_cuda)
+                       if self._dense else None)
+        self._m = {}
+        self._v = {}
+
+    def moments(self, p):
+        k = id(p)
+        if k not in self._m:
+            self._m[k] = torch.zeros_like(p.data)
+            self._v[k] = torch.zeros_like(p.data)
+        return self._m[k], self._v[k]
+
+    @torch.no_grad()
+    def step(self) -> None:
+        self._apply_clip()
+        lr = self.get_lr()
+        self.step_count += 1
+        if self._torch is not None:
+            for g in self._torch.param_groups:
+                g["lr"] = lr
+            self._torch.step()
+        b1p = self.beta1 ** self.step_count
+        b2p = self.beta2 ** self.step_count
+        for p in self._sparse:
+            sr = getattr(p, "grad_rows", None)
+            if sr is not None:
+                m, v = self.moments(p)
+                ops.raw_sparse_adam(p.data, m, v, sr, lr, self.beta1, self.beta2, self.eps, b1p, b2p)
+        if hasattr(self._lr, "step"):
+            self._lr.step()
+
+
+class SparseAdaGrad(_Base):
+    """SparseAdaGradSGDRule of the PS/GPUBox path (models/rank/slot_dnn/config_online.yaml:57-79):
+    one g2sum accumulator per ROW; dense parameters fall back to Adam like the PS config does."""
+
+    def __init__(self, learning_rate=0.05, parameters=(), initial_g2sum=3.0,
+                 weight_bounds=(-10.0, 10.0), dense_learning_rate=0.001):
+        super().__init__(learning_rate, parameters, None)
+        self.g0 = initial_g2sum
+        self.lo, self.hi = weight_bounds
+        self._torch = (torch.optim.Adam(self._dense, lr=dense_learning_rate,
+                                        fused=self._dense[0].is_cuda) if self._dense else None)
+        self._g2 = {}
+
+    def g2sum(self, p):
+        k = id(p)
+        if k not in self._g2:
+            self._g2[k] = torch.zeros(p.shape[0], device=p.device)
+        return self._g2[k]
+
+    @torch.no_grad()
+    def step(self) -> None:
+        if self._torch is not None:
+            self._torch.step()
+        for p in self._sparse:
+            sr = getattr(p, "grad_rows", None)
+            if sr is not None:
+                ops.raw_sparse_adagrad(p.data, self.g2sum(p), sr, self.get_lr(), self.g0, self.lo,
+                                       self.hi)
+        self.step_count += 1

@@ -1,0 +1,218 @@
+"""Config loading and the dygraph training loop — the caller side of the hot path, shaped like the
+reference's tools/trainer.py:49-223 and tools/utils/utils_single.py (load_yaml :131-136,
+get_all_inters_from_yaml :57-86, create_data_loader :89-113, load_dy_model_class :116-120) so that
+`python tools/trainer.py -m <config.yaml> [-o key=value ...]` behaves the same way.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import importlib.util
+import logging
+import os
+import sys
+import time
+from typing import Dict, List
+
+import numpy as np
+import torch
+import yaml
+
+logging.basicConfig(format="%(asctime)s - %(levelname)s - %(message)s", level=logging.INFO)
+logger = logging.getLogger("paddlerec_b200")
+
+
+# ---- yaml -> flat dotted dict (utils_single.py:57-86,131-136) -----------------------------------
+def flatten_yaml(envs: dict, filters=("workspace", "runner", "hyper_parameters")) -> Dict[str, object]:
+    flat: Dict[str, object] = {}
+
+    def walk(prefix: List[str], node: dict):
+        for k, v in node.items():
+            if isinstance(v, dict):
+                walk(prefix + [k], v)
+            elif k in ("dataset", "phase", "runner") and isinstance(v, list):
+                for item in v:
+                    if item.get("name") is None:
+                        raise ValueError("name must be in dataset list. ", v)
+                    walk(prefix + [k, item["name"]], item)
+            else:
+                flat[".".join(prefix + [k])] = v
+
+    walk([], envs)
+    return {k: v for k, v in flat.items() if any(k.startswith(f) for f in filters)}
+
+
+def load_yaml(yaml_file: str) -> Dict[str, object]:
+    with open(yaml_file, "r") as fh:
+        envs = yaml.safe_load(fh)
+    return flatten_yaml(envs)
+
+
+def apply_overrides(config: dict, opts) -> None:
+    """`-o key=value`: typed by the existing value (trainer.py:55-65)."""
+    for parameter in opts or []:
+        parameter = parameter.strip()
+        key, _, value = parameter.partition("=")
+        if isinstance(config.get(key), bool):
+            config[key] = value in ("True", "true", "1")
+        elif isinstance(config.get(key), int):
+            config[key] = int(value)
+        elif isinstance(config.get(key), float):
+            config[key] = float(value)
+        elif isinstance(config.get(key), list):
+            config[key] = yaml.safe_load(value)
+        else:
+            config[key] = value
+
+
+# ---- plugin loading (utils_single.py:116-120) ---------------------------------------------------
+def _import_from_dir(abs_dir: str, module: str):
+    """Import <abs_dir>/<module>.py.  Our own model dirs are packages (relative imports); a foreign
+    plugin dir is imported the reference's way (sys.path + top-level name)."""
+    pkg_root = os.path.dirname(os.path.abspath(__file__))
+    abs_dir = os.path.abspath(abs_dir)
+    if abs_dir.startswith(pkg_root + os.sep):
+        rel = os.path.relpath(abs_dir, os.path.dirname(pkg_root)).replace(os.sep, ".")
+        return importlib.import_module(rel + "." + module)
+    if abs_dir not in sys.path:
+        sys.path.append(abs_dir)
+    return importlib.import_module(module)
+
+
+def load_dy_model_class(abs_dir: str):
+    return _import_from_dir(abs_dir, "dygraph_model").DygraphModel()
+
+
+def _collate(samples):
+    """Stack each slot: list of per-sample arrays -> list of [B, ...] tensors."""
+    return [torch.from_numpy(np.stack([s[i] for s in samples])) for i in range(len(samples[0]))]
+
+
+def create_data_loader(config, mode="train", rank=0, world_size=1):
+    if mode == "train":
+        data_dir = config.get("runner.train_data_dir")
+        batch_size = config.get("runner.train_batch_size")
+        reader_path = config.get("runner.train_reader_path", "reader")
+    else:
+        data_dir = config.get("runner.test_data_dir")
+        batch_size = config.get("runner.infer_batch_size")
+        reader_path = config.get("runner.infer_reader_path", "reader")
+    abs_dir = config["config_abs_dir"]
+    data_dir = os.path.join(abs_dir, data_dir)
+    file_list = [os.path.join(data_dir, x) for x in sorted(os.listdir(data_dir))]
+    reader = _import_from_dir(abs_dir, reader_path)
+    dataset = reader.RecDataset(file_list, config=config)
+    return torch.utils.data.DataLoader(dataset, batch_size=batch_size, drop_last=True,
+                                       collate_fn=_collate,
+                                       num_workers=int(config.get("runner.num_workers", 0)))
+
+
+# ---- checkpoint (save_load.py:25-46) ------------------------------------------------------------
+def save_model(net, optimizer, model_path, epoch_id, prefix="rec"):
+    path = os.path.join(model_path, str(epoch_id))
+    os.makedirs(path, exist_ok=True)
+    torch.save(net.state_dict(), os.path.join(path, prefix + ".pdparams"))
+    logger.info("Already save model in %s", path)
+
+
+def load_model(model_path, net, prefix="rec"):
+    state = torch.load(os.path.join(model_path, prefix + ".pdparams"), map_location="cuda")
+    net.load_state_dict(state)
+
+
+# ---- the loop (trainer.py:49-223) ---------------------------------------------------------------
+def parse_args(argv=None):
+    p = argparse.ArgumentParser("PaddleRec-shaped dygraph trainer on the b200rec engine")
+    p.add_argument("-m", "--config_yaml", type=str, required=True)
+    p.add_argument("-o", "--opt", nargs="*", type=str)
+    args = p.parse_args(argv)
+    args.abs_dir = os.path.dirname(os.path.abspath(args.config_yaml))
+    args.config_yaml = os.path.abspath(args.config_yaml)
+    return args
+
+
+def train(config: dict, max_steps=None, save=True):
+    """Returns a list of per-step python floats (loss) and the final metric values."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("paddlerec_b200 trains on a CUDA device only (no CPU fallback)")
+    dy_model_class = load_dy_model_class(config["config_abs_dir"])
+    seed = int(config.get("runner.seed", 12345))
+    torch.manual_seed(seed)
+    epochs = int(config.get("runner.epochs"))
+    print_interval = int(config.get("runner.print_interval", 10))
+    model_save_path = config.get("runner.model_save_path", "model_output")
+    model_init_path = config.get("runner.model_init_path", None)
+
+    dy_model = dy_model_class.create_model(config)
+    if model_init_path is not None:
+        load_model(model_init_path, dy_model)
+    optimizer = dy_model_class.create_optimizer(dy_model, config)
+    train_dataloader = create_data_loader(config, "train")
+
+    losses = []
+    metric_values = {}
+    step_num = 0
+    for epoch_id in range(int(config.get("last_epoch", -1)) + 1, epochs):
+        dy_model.train()
+        metric_list, metric_list_name = dy_model_class.create_metrics()
+        train_reader_cost = train_run_cost = 0.0
+        total_samples = 0
+        reader_start = time.time()
+        for batch_id, batch in enumerate(train_dataloader):
+            train_reader_cost += time.time() - reader_start
+            optimizer.clear_grad()
+            train_start = time.time()
+            batch_size = len(batch[0])
+            loss, metric_list, tensor_print_dict = dy_model_class.train_forward(
+                dy_model, metric_list, batch, config)
+            loss.backward()
+            optimizer.step()
+            total_samples += batch_size
+            if batch_id % print_interval == 0:
+                # the only host sync of the loop
+                metric_str = "".join("%s:%.6f, " % (n, m.accumulate())
+                                     for n, m in zip(metric_list_name, metric_list))
+                tensor_str = "".join("%s:%s," % (k, str(float(v))) for k, v in
+                                     (tensor_print_dict or {}).items())
+                train_run_cost += time.time() - train_start
+                logger.info(
+                    "epoch: %d, batch_id: %d, %s%s avg_reader_cost: %.5f sec, avg_batch_cost: %.5f "
+                    "sec, avg_samples: %.5f, ips: %.5f ins/s", epoch_id, batch_id, metric_str,
+                    tensor_str, train_reader_cost / print_interval,
+                    (train_reader_cost + train_run_cost) / print_interval,
+                    total_samples / print_interval,
+                    total_samples / (train_reader_cost + train_run_cost + 0.0001))
+                train_reader_cost = train_run_cost = 0.0
+                total_samples = 0
+            else:
+                train_run_cost += time.time() - train_start
+            losses.append(loss.detach())
+            reader_start = time.time()
+            step_num += 1
+            if max_steps is not None and step_num >= max_steps:
+                break
+        metric_values = {n: m.accumulate() for n, m in zip(metric_list_name, metric_list)}
+        logger.info("epoch: %d done, %s", epoch_id,
+                    ", ".join("%s: %.6f" % kv for kv in metric_values.items()))
+        if save:
+            save_model(dy_model, optimizer, os.path.join(config["config_abs_dir"], model_save_path)
+                       if not os.path.isabs(model_save_path) else model_save_path, epoch_id)
+        if max_steps is not None and step_num >= max_steps:
+            break
+    return [float(l) for l in losses], metric_values, dy_model
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    config = load_yaml(args.config_yaml)
+    config["yaml_path"] = args.config_yaml
+    config["config_abs_dir"] = args.abs_dir
+    apply_overrides(config, args.opt)
+    logger.info("**************common.configs**********")
+    for k in ("runner.use_gpu", "runner.train_batch_size", "runner.epochs", "runner.print_interval"):
+        logger.info("%s: %s", k, config.get(k))
+    train(config)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,269 @@
+"""Parity of every CUDA entry point (called through the C ABI via paddlerec_b200.ops.raw_*) against
+the CPU oracle on seeded inputs.  Tolerances: gathers are bit-exact; fp32 reductions are compared
+with a float64 oracle at 2e-6 relative to the tensor's max magnitude (fp32 rounding of <=39-term
+sums), optimizers at 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets
+from oracle import optim as ooptim
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from paddlerec_b200 import ops
+    return ops
+
+
+def make_fm_inputs(B, F, Dn, D, V, seed, pad_frac=0.05, zipf=False):
+    g = torch.Generator().manual_seed(seed)
+    if zipf:
+        r = torch.rand(B, F, generator=g, dtype=torch.float64)
+        ids = (V ** r).to(torch.int64).clamp_(1, V - 1)  # heavy duplication on small ids
+    else:
+        ids = torch.randint(1, V, (B, F), generator=g)
+    ids[torch.rand(B, F, generator=g) < pad_frac] = 0
+    if B > 1:
+        ids[1, :] = 0
+    dense = torch.rand(B, Dn, generator=g)
+    dense[torch.rand(B, Dn, generator=g) < 0.3] = 0
+    W = torch.randn(V, D, generator=g) * 0.1
+    W1 = torch.randn(V, 1, generator=g) * 0.1
+    dense_w = torch.randn(1, Dn, D, generator=g) * 0.1
+    dense_w1 = torch.randn(Dn, generator=g) * 0.1
+    return ids, dense, W, W1, dense_w, dense_w1
+
+
+def oracle_fm(ids, dense, W, W1, dense_w, dense_w1, dtype=torch.float64, pad=0):
+    p = {"fm.embedding.weight": W.to(dtype).clone().requires_grad_(True),
+         "fm.embedding_one.weight": W1.to(dtype).clone().requires_grad_(True),
+         "fm.dense_w": dense_w.to(dtype).clone().requires_grad_(True),
+         "fm.dense_w_one": dense_w1.to(dtype).clone().requires_grad_(True)}
+    if pad != 0:  # oracle helper hard-codes padding_idx=0 like the reference; remap for other pads
+        raise NotImplementedError
+    y1, y2, feat = nets.deepfm_fm(p, [ids[:, i:i + 1] for i in range(ids.shape[1])], dense.to(dtype))
+    return p, y1, y2, feat
+
+
+@pytest.mark.parametrize("D", [1, 4, 8, 9, 10, 16, 40, 64, 128])
+@pytest.mark.parametrize("B", [1, 7, 300])
+def test_embed_fm_fwd(D, B):
+    ops = _ops()
+    F, Dn, V = 26, 13, 1000
+    ids, dense, W, W1, dense_w, dense_w1 = make_fm_inputs(B, F, Dn, D, V, seed=100 + D + B)
+    _, y1, y2, feat = oracle_fm(ids, dense, W, W1, dense_w, dense_w1)
+    gfeat, gy1, gy2, gS = ops.raw_embed_fm_fwd(W.to(DEV), W1.to(DEV), ids.to(DEV), dense.to(DEV),
+                                                dense_w.reshape(Dn, D).to(DEV), dense_w1.to(DEV), 0)
+    # gathered rows: bit-exact copies; dense rows: one fp32 multiply, identical to fp32 oracle
+    f32 = torch.cat([W[ids] * (ids != 0).unsqueeze(-1), dense.unsqueeze(2) * dense_w], 1)
+    assert torch.equal(gfeat.cpu(), f32)
+    assert rel_err(gy1.cpu(), y1.reshape(-1)) < 2e-6
+    assert rel_err(gy2.cpu(), y2.reshape(-1)) < 2e-6
+    assert rel_err(gS.cpu(), feat.sum(1)) < 2e-6
+    assert ops.raw_oob_count() == 0
+
+
+def test_embed_fm_fwd_odd_fields_and_oob():
+    ops = _ops()
+    B, F, Dn, D, V = 33, 5, 3, 16, 50
+    ids, dense, W, W1, dense_w, dense_w1 = make_fm_inputs(B, F, Dn, D, V, seed=5)
+    ids[0, 0] = V + 7      # out of range -> treated as padding, counted
+    ids[2, 1] = -3
+    ops.raw_oob_count()
+    gfeat, gy1, gy2, _ = ops.raw_embed_fm_fwd(W.to(DEV), W1.to(DEV), ids.to(DEV), dense.to(DEV),
+                                               dense_w.reshape(Dn, D).to(DEV), dense_w1.to(DEV), 0)
+    ids_ok = ids.clone()
+    ids_ok[0, 0] = 0
+    ids_ok[2, 1] = 0
+    _, y1, y2, feat = oracle_fm(ids_ok, dense, W, W1, dense_w, dense_w1)
+    assert rel_err(gfeat.cpu(), feat) < 1e-7
+    assert rel_err(gy2.cpu(), y2.reshape(-1)) < 2e-6
+    assert ops.raw_oob_count() == 2
+
+
+def test_embed_fm_fwd_empty_batch():
+    ops = _ops()
+    W = torch.zeros(10, 16, device=DEV)
+    W1 = torch.zeros(10, 1, device=DEV)
+    feat, y1, y2, S = ops.raw_embed_fm_fwd(W, W1, torch.zeros(0, 26, dtype=torch.int64, device=DEV),
+                                           torch.zeros(0, 13, device=DEV),
+                                           torch.zeros(13, 16, device=DEV),
+                                           torch.zeros(13, device=DEV), 0)
+    assert feat.shape == (0, 39, 16) and y1.numel() == 0
+
+
+@pytest.mark.parametrize("V,n", [(50, 1), (1000, 5000), (100000000, 4096), (5_000_000_000, 3000)])
+def test_group_ids(V, n):
+    ops = _ops()
+    g = torch.Generator().manual_seed(V % 1000 + n)
+    ids = torch.randint(0, min(V, 2 ** 62), (n,), generator=g)
+    if n > 10:
+        ids[::7] = ids[3]          # many duplicates
+        ids[5] = 0                  # padding
+        ids[6] = V                  # out of range
+        ids[8] = -1
+    ops.raw_oob_count()
+    gr = ops.raw_group_ids(ids.to(DEV), V, 0)
+    U, kept = gr.num.cpu().tolist()
+    valid = (ids != 0) & (ids >= 0) & (ids < V)
+    uniq = torch.unique(ids[valid])
+    assert U == uniq.numel() and kept == int(valid.sum())
+    assert torch.equal(gr.unique_ids[:U].cpu(), uniq)
+    seg = gr.seg_offsets[:U + 1].cpu()
+    pos = gr.sorted_pos[:kept].cpu().long()
+    assert seg[0] == 0 and seg[-1] == kept
+    for u in range(min(U, 200)):
+        ps = pos[seg[u]:seg[u + 1]]
+        assert (ids[ps] == uniq[u]).all()
+        assert (ps[1:] > ps[:-1]).all()  # stable: ascending positions inside a segment
+    assert sorted(pos.tolist()) == torch.nonzero(valid).reshape(-1).tolist()
+
+
+def test_group_ids_all_padding_and_empty():
+    ops = _ops()
+    gr = ops.raw_group_ids(torch.zeros(17, dtype=torch.int64, device=DEV), 100, 0)
+    assert gr.num.cpu().tolist() == [0, 0]
+    gr = ops.raw_group_ids(torch.zeros(0, dtype=torch.int64, device=DEV), 100, 0)
+    assert gr.num.cpu().tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("D", [1, 4, 9, 10, 16, 40, 64, 128])
+@pytest.mark.parametrize("zipf", [False, True])
+def test_embed_fm_bwd(D, zipf):
+    ops = _ops()
+    B, F, Dn, V = 97, 26, 13, 400
+    ids, dense, W, W1, dense_w, dense_w1 = make_fm_inputs(B, F, Dn, D, V, seed=7 + D, zipf=zipf)
+    g = torch.Generator().manual_seed(D)
+    A = torch.randn(B, F + Dn, D, generator=g)
+    g1 = torch.randn(B, generator=g)
+    g2 = torch.randn(B, generator=g)
+    p, y1, y2, feat = oracle_fm(ids, dense, W, W1, dense_w, dense_w1)
+    L = (feat * A.double()).sum() + (y1.reshape(-1) * g1.double()).sum() + \
+        (y2.reshape(-1) * g2.double()).sum()
+    L.backward()
+    gfeat, _, _, gS = ops.raw_embed_fm_fwd(W.to(DEV), W1.to(DEV), ids.to(DEV), dense.to(DEV),
+                                           dense_w.reshape(Dn, D).to(DEV), dense_w1.to(DEV), 0)
+    gr = ops.raw_group_ids(ids.to(DEV), V, 0)
+    dW_rows, dW1_rows, ddw, ddw1 = ops.raw_embed_fm_bwd(gfeat, gS, A.to(DEV), g1.to(DEV),
+                                                        g2.to(DEV), dense.to(DEV), gr.seg_offsets,
+                                                        gr.sorted_pos, gr.num, F)
+    dW = ops.SelectedRows(gr.unique_ids, dW_rows, gr.num, V).to_dense().cpu()
+    dW1 = ops.SelectedRows(gr.unique_ids, dW1_rows.unsqueeze(1), gr.num, V).to_dense().cpu()
+    assert rel_err(dW, p["fm.embedding.weight"].grad) < 3e-6
+    assert rel_err(dW1, p["fm.embedding_one.weight"].grad) < 3e-6
+    assert rel_err(ddw.cpu(), p["fm.dense_w"].grad[0]) < 3e-6
+    assert rel_err(ddw1.cpu(), p["fm.dense_w_one"].grad) < 3e-6
+    assert not dW[0].any() and not dW1[0].any()      # padding row: no gradient
+    # deterministic: a second run is bit-identical
+    dW_rows2, dW1_rows2, ddw2, _ = ops.raw_embed_fm_bwd(gfeat, gS, A.to(DEV), g1.to(DEV),
+                                                        g2.to(DEV), dense.to(DEV), gr.seg_offsets,
+                                                        gr.sorted_pos, gr.num, F)
+    U = int(gr.num[0])
+    assert torch.equal(dW_rows[:U], dW_rows2[:U]) and torch.equal(ddw, ddw2)
+
+
+@pytest.mark.parametrize("D", [1, 2, 4, 9, 16, 64, 128])
+def test_gather_and_segment_reduce(D):
+    ops = _ops()
+    V, n = 300, 2000
+    g = torch.Generator().manual_seed(D)
+    W = torch.randn(V, D, generator=g)
+    ids = torch.randint(0, V, (n,), generator=g)
+    ids[::11] = 3
+    out = ops.raw_gather(W.to(DEV), ids.reshape(40, 50).to(DEV), 3)
+    ref = W[ids] * (ids != 3).unsqueeze(1)
+    assert torch.equal(out.cpu().reshape(n, D), ref)
+    out_nopad = ops.raw_gather(W.to(DEV), ids.to(DEV), -1)
+    assert torch.equal(out_nopad.cpu(), W[ids])
+    dOut = torch.randn(n, D, generator=g)
+    gr = ops.raw_group_ids(ids.to(DEV), V, 3)
+    rows = ops.raw_segment_reduce(dOut.to(DEV), gr.seg_offsets, gr.sorted_pos, gr.num, n)
+    dense = ops.SelectedRows(gr.unique_ids, rows, gr.num, V).to_dense().cpu()
+    uniq, merged = ooptim.merge_rows(ids.numpy(), dOut.numpy(), padding_idx=3)
+    ref_dense = np.zeros((V, D))
+    ref_dense[uniq] = merged
+    assert rel_err(dense, ref_dense) < 2e-6
+
+
+@pytest.mark.parametrize("D", [1, 9, 16, 64])
+def test_sparse_optimizers(D):
+    ops = _ops()
+    V, n = 500, 700
+    g = torch.Generator().manual_seed(3 * D)
+    W = torch.randn(V, D, generator=g)
+    ids = torch.randint(1, V, (n,), generator=g)
+    dOut = torch.randn(n, D, generator=g)
+    uniq, merged = ooptim.merge_rows(ids.numpy(), dOut.numpy())
+
+    def selected():
+        gr = ops.raw_group_ids(ids.to(DEV), V, -1)
+        rows = ops.raw_segment_reduce(dOut.to(DEV), gr.seg_offsets, gr.sorted_pos, gr.num, n)
+        return ops.SelectedRows(gr.unique_ids, rows, gr.num, V)
+
+    # SGD
+    Wd = W.to(DEV).clone()
+    ops.raw_sparse_sgd(Wd, selected(), 0.1)
+    assert rel_err(Wd.cpu(), ooptim.sgd(W.double().numpy(), uniq, merged, 0.1)) < 1e-6
+    # lazy Adam, two steps
+    Wd = W.to(DEV).clone()
+    m = torch.zeros_like(Wd)
+    v = torch.zeros_like(Wd)
+    Wr, mr, vr = W.double().numpy(), np.zeros((V, D)), np.zeros((V, D))
+    for t in (1, 2):
+        ops.raw_sparse_adam(Wd, m, v, selected(), 1e-3, 0.9, 0.999, 1e-8, 0.9 ** t, 0.999 ** t)
+        Wr, mr, vr = ooptim.adam_lazy(Wr, mr, vr, uniq, merged, 1e-3, 0.9, 0.999, 1e-8, t)
+    assert rel_err(Wd.cpu(), Wr) < 1e-6 and rel_err(m.cpu(), mr) < 1e-6 and rel_err(v.cpu(), vr) < 1e-6
+    untouched = np.setdiff1d(np.arange(V), uniq)
+    assert torch.equal(Wd.cpu()[untouched], W[untouched])   # lazy: other rows untouched
+    # row-wise AdaGrad
+    Wd = W.to(DEV).clone()
+    g2 = torch.zeros(V, device=DEV)
+    Wr, g2r = W.double().numpy(), np.zeros(V)
+    for _ in range(2):
+        ops.raw_sparse_adagrad(Wd, g2, selected(), 0.05, 3.0, -10.0, 10.0)
+        Wr, g2r = ooptim.adagrad_row(Wr, g2r, uniq, merged, 0.05, 3.0, -10.0, 10.0)
+    assert rel_err(Wd.cpu(), Wr) < 1e-6 and rel_err(g2.cpu(), g2r) < 1e-6
+
+
+@pytest.mark.parametrize("C", [156, 351, 1560])
+def test_cross_v2(C):
+    ops = _ops()
+    B = 77
+    g = torch.Generator().manual_seed(C)
+    x0, xl, xw, dout = (torch.randn(B, C, generator=g) for _ in range(4))
+    bias = torch.randn(C, generator=g)
+    out = ops.raw_cross_v2_fwd(x0.to(DEV), xl.to(DEV), xw.to(DEV), bias.to(DEV))
+    assert rel_err(out.cpu(), xl.double() + x0.double() * (xw.double() + bias.double())) < 1e-6
+    dxw, dx0, dbias = ops.raw_cross_v2_bwd(dout.to(DEV), x0.to(DEV), xw.to(DEV), bias.to(DEV))
+    assert rel_err(dxw.cpu(), dout.double() * x0.double()) < 1e-6
+    assert rel_err(dx0.cpu(), dout.double() * (xw.double() + bias.double())) < 1e-6
+    assert rel_err(dbias.cpu(), (dout.double() * x0.double()).sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_shard_bucketize(world):
+    ops = _ops()
+    V, n = 1000, 5000
+    g = torch.Generator().manual_seed(world)
+    ids = torch.randint(0, V, (n,), generator=g)
+    ids[10] = -5
+    ids[11] = V + 1
+    send, perm, inv, counts = ops.raw_shard_bucketize(ids.to(DEV), world, V)
+    send, perm, inv, counts = send.cpu(), perm.cpu(), inv.cpu().long(), counts.cpu()
+    valid = (ids >= 0) & (ids < V)
+    owner = torch.where(valid, ids % world, torch.zeros_like(ids))
+    assert counts.tolist() == [int((owner == r).sum()) for r in range(world)]
+    assert torch.equal(perm[inv], torch.arange(n))            # inverse permutations
+    assert (owner[inv][1:] >= owner[inv][:-1]).all()          # bucket order is owner-major
+    off = 0
+    for r in range(world):                                    # stable inside a bucket
+        seg = inv[off:off + int(counts[r])]
+        assert (seg[1:] > seg[:-1]).all()
+        off += int(counts[r])
+    local = torch.where(valid, ids // world, torch.full_like(ids, -1))
+    assert torch.equal(send, local[inv])
