@@ -65,7 +65,13 @@ def oracle_run(model, g, dtype=torch.float64):
     return pred.detach(), loss.detach(), grads
 
 
+def _np(x):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=np.float64)
+
+
 def rel_err(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a = _np(a)
+    b = _np(b)
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
