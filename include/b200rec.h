@@ -102,10 +102,13 @@ int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_d
 int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D, int64_t V,
                    int64_t padding_idx, void* stream);
 /* rows[u,:] = sum_{p in segment u} dOut[p,:]  — the SelectedRows merge of
- * lookup_table_v2_grad.  Deterministic (fixed order inside a segment). */
+ * lookup_table_v2_grad.  Deterministic (fixed order inside a segment); ids occurring more than
+ * 64 times are reduced by a whole CTA each (skew-proof). */
+int b200rec_segment_reduce_workspace_bytes(int64_t n, size_t* bytes_host);
 int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                            const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
-                           int64_t n, int D, void* stream);
+                           int64_t n, int D, void* workspace, size_t workspace_bytes,
+                           void* stream);
 /* dW[unique_ids[u],:] += rows[u,:] into a dense [V,D] gradient (small tables / tests). */
 int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const int32_t* num_unique,
                           float* dW, int64_t n, int D, int64_t V, void* stream);
@@ -113,19 +116,21 @@ int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const in
 /* ---- row-wise ("lazy") optimizers applied to the touched rows only -------- */
 /* W[id] -= lr * g */
 int b200rec_sparse_sgd(float* W, const int64_t* unique_ids, const float* rows,
-                       const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                       const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
                        void* stream);
 /* Adam(lazy_mode=True): m=b1*m+(1-b1)g; v=b2*v+(1-b2)g^2;
- * W -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps*sqrt(1-b2^t)); bias terms from the host. */
+ * W -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps*sqrt(1-b2^t)); bias terms from the host.
+ * Hyper-parameters are doubles: derived constants (1-b1, 1-b2, lr_t) are formed in double on the
+ * host and only then rounded to fp32 (1-0.999f would be off by 5e-5 relative). */
 int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
                         const float* rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
-                        float lr, float beta1, float beta2, float eps, float beta1_pow_t,
-                        float beta2_pow_t, void* stream);
+                        double lr, double beta1, double beta2, double eps, double beta1_pow_t,
+                        double beta2_pow_t, void* stream);
 /* SparseAdaGradSGDRule: one g2sum scalar per row.
  *   W -= lr * g * sqrt(g0/(g0+g2sum)); clamp to [lo,hi]; g2sum += mean_d(g^2). */
 int b200rec_sparse_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
-                           const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
-                           float initial_g2sum, float lo, float hi, void* stream);
+                           const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
+                           double initial_g2sum, double lo, double hi, void* stream);
 
 /* ---- K3: CrossNet fused epilogues (GEMM itself is a library GEMM) --------- */
 /* CrossNetV2 step, models/rank/dcn_v2/net.py:222-226, after xw = x_l @ W_l:

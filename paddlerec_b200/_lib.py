@@ -9,7 +9,7 @@ import ctypes
 import os
 import subprocess
 import sys
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER, c_uint64
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER, c_uint64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
@@ -78,13 +78,14 @@ _SIG = {
     "b200rec_embed_fm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
                                      c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200rec_gather": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int64, _P]),
-    "b200rec_segment_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "b200rec_segment_reduce_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "b200rec_segment_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "b200rec_rows_to_dense": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, _P]),
-    "b200rec_sparse_sgd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, c_float, _P]),
-    "b200rec_sparse_adam": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float,
-                                    c_float, c_float, c_float, c_float, c_float, _P]),
-    "b200rec_sparse_adagrad": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float,
-                                       c_float, c_float, c_float, _P]),
+    "b200rec_sparse_sgd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, c_double, _P]),
+    "b200rec_sparse_adam": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_double,
+                                    c_double, c_double, c_double, c_double, c_double, _P]),
+    "b200rec_sparse_adagrad": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_double,
+                                       c_double, c_double, c_double, _P]),
     "b200rec_cross_v2_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "b200rec_cross_bwd_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_cross_v2_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),

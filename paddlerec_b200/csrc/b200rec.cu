@@ -96,8 +96,8 @@ int b200rec_group_ids(const int64_t* ids, int64_t n, int64_t V, int64_t padding_
 
 int b200rec_embed_fm_bwd_workspace_bytes(int64_t B, int F, int Dn, int D, size_t* bytes_host) {
   NOT_NULL(bytes_host);
-  (void)B; (void)F;
-  *bytes_host = (size_t)bwd_dense_grid() * ((size_t)Dn * D + Dn) * sizeof(float) + 16;
+  *bytes_host = align_up((size_t)bwd_dense_grid() * ((size_t)Dn * D + Dn) * sizeof(float), 256) +
+                seg_workspace_bytes(B * F);
   return B200REC_OK;
 }
 
@@ -114,7 +114,8 @@ int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_d
       NOT_NULL(seg_offsets); NOT_NULL(sorted_pos); NOT_NULL(num_unique);
       NOT_NULL(dW_rows); NOT_NULL(dW1_rows);
     }
-    if (Dn > 0) { NOT_NULL(dense); NOT_NULL(ddense_w); NOT_NULL(ddense_w1); NOT_NULL(workspace); }
+    if (Dn > 0) { NOT_NULL(dense); NOT_NULL(ddense_w); NOT_NULL(ddense_w1); }
+    NOT_NULL(workspace);
   }
   return launch_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_pos,
                              num_unique, dW_rows, dW1_rows, ddense_w, ddense_w1, B, F, Dn, D,
@@ -128,12 +129,21 @@ int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, in
   return launch_gather(W, ids, out, n, D, V, padding_idx, ST(stream));
 }
 
+int b200rec_segment_reduce_workspace_bytes(int64_t n, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  B200_REQUIRE(n >= 0, "segment_reduce: bad sizes");
+  *bytes_host = seg_workspace_bytes(n);
+  return B200REC_OK;
+}
+
 int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                            const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
-                           int64_t n, int D, void* stream) {
+                           int64_t n, int D, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   B200_REQUIRE(n >= 0 && D > 0, "segment_reduce: bad sizes");
-  if (n > 0) { NOT_NULL(dOut); NOT_NULL(seg_offsets); NOT_NULL(sorted_pos); NOT_NULL(num_unique); NOT_NULL(rows); }
-  return launch_segment_reduce(dOut, seg_offsets, sorted_pos, num_unique, rows, n, D, ST(stream));
+  if (n > 0) { NOT_NULL(dOut); NOT_NULL(seg_offsets); NOT_NULL(sorted_pos); NOT_NULL(num_unique); NOT_NULL(rows); NOT_NULL(workspace); }
+  return launch_segment_reduce(dOut, seg_offsets, sorted_pos, num_unique, rows, n, D, workspace,
+                               workspace_bytes, ST(stream));
 }
 
 int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const int32_t* num_unique,
@@ -146,34 +156,35 @@ int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const in
 }
 
 int b200rec_sparse_sgd(float* W, const int64_t* unique_ids, const float* rows,
-                       const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
+                       const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
                        void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_sgd: bad sizes");
   if (n > 0) { NOT_NULL(W); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
-  SgdOp op{W, lr};
+  SgdOp op{W, (float)lr};
   return launch_row_update("sparse_sgd", unique_ids, rows, num_unique, n, D, V, op, W, nullptr,
                            nullptr, ST(stream));
 }
 
 int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
                         const float* rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
-                        float lr, float beta1, float beta2, float eps, float beta1_pow_t,
-                        float beta2_pow_t, void* stream) {
+                        double lr, double beta1, double beta2, double eps, double beta1_pow_t,
+                        double beta2_pow_t, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_adam: bad sizes");
   if (n > 0) { NOT_NULL(W); NOT_NULL(m); NOT_NULL(v); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
-  const double c2 = sqrt(1.0 - (double)beta2_pow_t);
-  AdamOp op{W, m, v, beta1, beta2, (float)((double)lr * c2 / (1.0 - (double)beta1_pow_t)),
-            (float)((double)eps * c2)};
+  const double c2 = sqrt(1.0 - beta2_pow_t);
+  AdamOp op{W, m, v, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+            (float)(lr * c2 / (1.0 - beta1_pow_t)), (float)(eps * c2)};
   return launch_row_update("sparse_adam", unique_ids, rows, num_unique, n, D, V, op, W, m, v,
                            ST(stream));
 }
 
 int b200rec_sparse_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
-                           const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
-                           float initial_g2sum, float lo, float hi, void* stream) {
+                           const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
+                           double initial_g2sum, double lo, double hi, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_adagrad: bad sizes");
   if (n > 0) { NOT_NULL(W); NOT_NULL(g2sum); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
-  return launch_adagrad(W, g2sum, unique_ids, rows, num_unique, n, D, V, lr, initial_g2sum, lo, hi,
+  return launch_adagrad(W, g2sum, unique_ids, rows, num_unique, n, D, V, (float)lr,
+                        (float)initial_g2sum, (float)lo, (float)hi,
                         ST(stream));
 }
 

@@ -15,6 +15,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "segreduce.cuh"
 
 namespace b200rec {
 
@@ -157,44 +158,31 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
 // and summed in the fixed (stable-sort) order of the segment => deterministic.
 constexpr int kBwdThreads = 256;
 
-template <int VEC, int TPR>
-__global__ void __launch_bounds__(kBwdThreads)
-embed_fm_bwd_rows_kernel(const float* __restrict__ feat, const float* __restrict__ S,
-                         const float* __restrict__ dfeat_dnn, const float* __restrict__ gy1,
-                         const float* __restrict__ gy2, const int32_t* __restrict__ seg_offsets,
-                         const int32_t* __restrict__ sorted_pos,
-                         const int32_t* __restrict__ num_unique, float* __restrict__ dW_rows,
-                         float* __restrict__ dW1_rows, int F, int N, int D) {
-  const int U = num_unique[0];
-  const int r = threadIdx.x % TPR;
-  const bool lane_ok = r * VEC < D;
-  const int groups_per_block = kBwdThreads / TPR;
-  for (int64_t u = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / TPR; u < U;
-       u += (int64_t)gridDim.x * groups_per_block) {
-    const int beg = seg_offsets[u];
-    const int end = seg_offsets[u + 1];
-    Vec<VEC> acc = vzero<VEC>();
-    float acc1 = 0.f;
-    for (int i = beg; i < end; ++i) {
-      const int p = sorted_pos[i];
-      const int b = p / F;
-      const int f = p - b * F;
-      const float g2 = __ldg(gy2 + b);
-      acc1 += __ldg(gy1 + b);
-      if (lane_ok) {
-        const size_t off = ((size_t)b * N + f) * D + r * VEC;
-        const Vec<VEC> fe = ld_row<VEC>(feat + off);
-        const Vec<VEC> sv = ld_cached<VEC>(S + (size_t)b * D + r * VEC);
-        Vec<VEC> dd = vzero<VEC>();
-        if (dfeat_dnn != nullptr) dd = ld_row<VEC>(dfeat_dnn + off);
+struct FmRowContrib {
+  const float* feat;
+  const float* S;
+  const float* dfeat_dnn;  // may be null
+  const float* gy1;
+  const float* gy2;
+  int F, N, D;
+  template <int VEC>
+  __device__ __forceinline__ void add(int p, int r, bool lane_ok, Vec<VEC>& acc,
+                                      float& acc1) const {
+    const int b = p / F;
+    const int f = p - b * F;
+    const float g2 = __ldg(gy2 + b);
+    acc1 += __ldg(gy1 + b);
+    if (lane_ok) {
+      const size_t off = ((size_t)b * N + f) * D + r * VEC;
+      const Vec<VEC> fe = ld_row<VEC>(feat + off);
+      const Vec<VEC> sv = ld_cached<VEC>(S + (size_t)b * D + r * VEC);
+      Vec<VEC> dd = vzero<VEC>();
+      if (dfeat_dnn != nullptr) dd = ld_row<VEC>(dfeat_dnn + off);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] += fmaf(g2, sv.v[k] - fe.v[k], dd.v[k]);
-      }
+      for (int k = 0; k < VEC; ++k) acc.v[k] += fmaf(g2, sv.v[k] - fe.v[k], dd.v[k]);
     }
-    if (lane_ok) st_plain<VEC>(dW_rows + (size_t)u * D + r * VEC, acc);
-    if (r == 0) dW1_rows[u] = acc1;
   }
-}
+};
 
 // K2b: dense-feature part: ddense_w[j,:] = sum_b dense[b,j]*dfeat[b,F+j,:],
 // ddense_w1[j] = sum_b gy1[b]*dense[b,j].  Persistent CTAs accumulate in registers over a
@@ -318,8 +306,9 @@ static int launch_embed_fm_bwd(const float* feat, const float* S, const float* d
                "embed_fm_bwd: feat/S/dfeat_dnn/dW_rows must be %d-byte aligned", align);
   B200_REQUIRE(B * F < (int64_t)INT32_MAX, "embed_fm_bwd: B*F must fit int32");
   const int G = bwd_dense_grid();
-  const size_t need = (size_t)G * ((size_t)Dn * D + Dn) * sizeof(float);
-  if (Dn > 0 && ws_bytes < need) {
+  const size_t dense_bytes = align_up((size_t)G * ((size_t)Dn * D + Dn) * sizeof(float), 256);
+  const size_t need = dense_bytes + seg_workspace_bytes(B * F);
+  if (ws_bytes < need) {
     set_error("embed_fm_bwd: workspace %zu < %zu bytes", ws_bytes, need);
     return B200REC_ERR_WORKSPACE;
   }
@@ -331,21 +320,22 @@ static int launch_embed_fm_bwd(const float* feat, const float* S, const float* d
     return B200REC_OK;
   }
   const int N = F + Dn;
+  int rc = B200REC_OK;
   B200_DISPATCH_ROW_SHAPE(rs, {
     const int64_t n = B * F;
-    const int gpb = kBwdThreads / TPR;
     if (n > 0) {
-      const int64_t want = (n + gpb - 1) / gpb;
-      const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
-      embed_fm_bwd_rows_kernel<VEC, TPR><<<grid, kBwdThreads, 0, st>>>(
-          feat, S, dfeat_dnn, gy1, gy2, seg_offsets, sorted_pos, num_unique, dW_rows, dW1_rows, F,
-          N, D);
+      FmRowContrib contrib{feat, S, dfeat_dnn, gy1, gy2, F, N, D};
+      rc = launch_seg_reduce<VEC, TPR, FmRowContrib>(seg_offsets, sorted_pos, num_unique, contrib,
+                                                     dW_rows, dW1_rows, n, D,
+                                                     static_cast<unsigned char*>(ws) + dense_bytes,
+                                                     st);
     }
-    if (Dn > 0) {
+    if (rc == B200REC_OK && Dn > 0) {
       embed_fm_bwd_dense_kernel<VEC, TPR><<<G, kBwdThreads, 0, st>>>(
           feat, S, dfeat_dnn, gy1, gy2, dense, static_cast<float*>(ws), B, F, Dn, D);
     }
   });
+  if (rc != B200REC_OK) return rc;
   B200_LAUNCH_CHECK();
   if (Dn > 0) {
     const int len = Dn * D + Dn;

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "segreduce.cuh"
 
 namespace b200rec {
 
@@ -63,42 +64,23 @@ static int launch_gather(const float* W, const int64_t* ids, float* out, int64_t
   return B200REC_OK;
 }
 
-// rows[u,:] = sum over the segment of dOut[sorted_pos[i],:], fixed order.
-template <int VEC, int TPR>
-__global__ void __launch_bounds__(kGatherThreads)
-segment_reduce_kernel(const float* __restrict__ dOut, const int32_t* __restrict__ seg_offsets,
-                      const int32_t* __restrict__ sorted_pos,
-                      const int32_t* __restrict__ num_unique, float* __restrict__ rows, int D) {
-  constexpr int GPB = kGatherThreads / TPR;
-  const int U = num_unique[0];
-  const int r = threadIdx.x % TPR;
-  const bool lane_ok = r * VEC < D;
-  for (int64_t u = (int64_t)blockIdx.x * GPB + threadIdx.x / TPR; u < U;
-       u += (int64_t)gridDim.x * GPB) {
-    const int beg = seg_offsets[u];
-    const int end = seg_offsets[u + 1];
-    Vec<VEC> acc = vzero<VEC>();
+// rows[u,:] = sum over the segment of dOut[sorted_pos[i],:], fixed order (segreduce.cuh).
+struct PlainRowContrib {
+  const float* dOut;
+  int D;
+  template <int VEC>
+  __device__ __forceinline__ void add(int p, int r, bool lane_ok, Vec<VEC>& acc, float&) const {
     if (lane_ok) {
-      int i = beg;
-      for (; i + 1 < end; i += 2) {  // two rows in flight
-        const Vec<VEC> a = ld_row<VEC>(dOut + (size_t)sorted_pos[i] * D + r * VEC);
-        const Vec<VEC> c = ld_row<VEC>(dOut + (size_t)sorted_pos[i + 1] * D + r * VEC);
+      const Vec<VEC> a = ld_row<VEC>(dOut + (size_t)p * D + r * VEC);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = (acc.v[k] + a.v[k]) + c.v[k];
-      }
-      if (i < end) {
-        const Vec<VEC> a = ld_row<VEC>(dOut + (size_t)sorted_pos[i] * D + r * VEC);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] += a.v[k];
-      }
-      st_plain<VEC>(rows + (size_t)u * D + r * VEC, acc);
+      for (int k = 0; k < VEC; ++k) acc.v[k] += a.v[k];
     }
   }
-}
+};
 
 static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                                  const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
-                                 int64_t n, int D, cudaStream_t st) {
+                                 int64_t n, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "segment_reduce: unsupported D=%d", D);
   const int align = rs.vec * 4;
@@ -106,15 +88,17 @@ static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                    reinterpret_cast<uintptr_t>(rows) % align == 0,
                "segment_reduce: dOut/rows must be %d-byte aligned", align);
   if (n == 0) return B200REC_OK;
+  if (ws_bytes < seg_workspace_bytes(n)) {
+    set_error("segment_reduce: workspace %zu < %zu bytes", ws_bytes, seg_workspace_bytes(n));
+    return B200REC_ERR_WORKSPACE;
+  }
+  int rc = B200REC_OK;
   B200_DISPATCH_ROW_SHAPE(rs, {
-    constexpr int GPB = kGatherThreads / TPR;
-    const int64_t want = (n + GPB - 1) / GPB;
-    const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
-    segment_reduce_kernel<VEC, TPR><<<grid, kGatherThreads, 0, st>>>(dOut, seg_offsets, sorted_pos,
-                                                                     num_unique, rows, D);
+    PlainRowContrib contrib{dOut, D};
+    rc = launch_seg_reduce<VEC, TPR, PlainRowContrib>(seg_offsets, sorted_pos, num_unique, contrib,
+                                                      rows, nullptr, n, D, ws, st);
   });
-  B200_LAUNCH_CHECK();
-  return B200REC_OK;
+  return rc;
 }
 
 // ---- row-wise update kernels ---------------------------------------------------------------
@@ -146,7 +130,8 @@ struct AdamOp {
   float* W;
   float* m;
   float* v;
-  float beta1, beta2, lr_t, eps_t;  // lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps_t = eps*sqrt(1-b2^t)
+  float beta1, beta2, omb1, omb2;  // omb = 1-beta, rounded from double
+  float lr_t, eps_t;  // lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps_t = eps*sqrt(1-b2^t)
   template <int VEC>
   __device__ __forceinline__ void apply(size_t row_off, const Vec<VEC>& g, int) const {
     Vec<VEC> w = *reinterpret_cast<const Vec<VEC>*>(W + row_off);
@@ -154,8 +139,8 @@ struct AdamOp {
     Vec<VEC> vv = *reinterpret_cast<const Vec<VEC>*>(v + row_off);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      mm.v[k] = beta1 * mm.v[k] + (1.f - beta1) * g.v[k];
-      vv.v[k] = beta2 * vv.v[k] + (1.f - beta2) * g.v[k] * g.v[k];
+      mm.v[k] = beta1 * mm.v[k] + omb1 * g.v[k];
+      vv.v[k] = beta2 * vv.v[k] + omb2 * g.v[k] * g.v[k];
       w.v[k] -= lr_t * (mm.v[k] / (sqrtf(vv.v[k]) + eps_t));
     }
     st_plain<VEC>(W + row_off, w);

@@ -62,8 +62,12 @@ def test_embed_fm_fwd(D, B):
     # gathered rows: bit-exact copies; dense rows: one fp32 multiply, identical to fp32 oracle
     f32 = torch.cat([W[ids] * (ids != 0).unsqueeze(-1), dense.unsqueeze(2) * dense_w], 1)
     assert torch.equal(gfeat.cpu(), f32)
-    assert rel_err(gy1.cpu(), y1.reshape(-1)) < 2e-6
-    assert rel_err(gy2.cpu(), y2.reshape(-1)) < 2e-6
+    # fp32 reductions: error bound is relative to the magnitude of the summed terms (a single
+    # sample's y2 = 0.5*sum(S^2 - Q) can cancel to ~0)
+    scale1 = float((W1[ids].abs().sum((1, 2)) + (dense * dense_w1).abs().sum(1)).max())
+    scale2 = float(0.5 * (feat.sum(1).square() + feat.square().sum(1)).sum(1).max())
+    assert float((gy1.cpu().double() - y1.reshape(-1)).abs().max()) <= 2e-6 * scale1 + 1e-12
+    assert float((gy2.cpu().double() - y2.reshape(-1)).abs().max()) <= 2e-6 * scale2 + 1e-12
     assert rel_err(gS.cpu(), feat.sum(1)) < 2e-6
     assert ops.raw_oob_count() == 0
 
