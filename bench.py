@@ -222,19 +222,21 @@ def run_b200(args, rank, world, local_rank):
     resident = [tuple(t.to(dev) for t in b) for b in host]
     label_f = [b[0].to(torch.float32) for b in resident]
 
+    scale = optimizer.scale_loss if hasattr(optimizer, "scale_loss") else (lambda x: x)
+
     def step_resident(i):
         label, ids, dense = resident[i % len(resident)]
         optimizer.clear_grad()
         pred = model(ids, dense)
         loss = dm.create_loss(pred, label_f[i % len(resident)])
-        loss.backward()
+        scale(loss).backward()
         optimizer.step()
         return loss
 
     def step_e2e(i):
         optimizer.clear_grad()
         loss, _, _ = dm.train_forward(model, None, host[i % len(host)], config)
-        loss.backward()
+        scale(loss).backward()
         optimizer.step()
         return loss.item()  # D2H read of the step's result
 

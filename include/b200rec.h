@@ -104,7 +104,7 @@ int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, in
 /* rows[u,:] = sum_{p in segment u} dOut[p,:]  — the SelectedRows merge of
  * lookup_table_v2_grad.  Deterministic (fixed order inside a segment); ids occurring more than
  * 64 times are reduced by a whole CTA each (skew-proof). */
-int b200rec_segment_reduce_workspace_bytes(int64_t n, size_t* bytes_host);
+int b200rec_segment_reduce_workspace_bytes(int64_t n, int D, size_t* bytes_host);
 int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                            const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
                            int64_t n, int D, void* workspace, size_t workspace_bytes,

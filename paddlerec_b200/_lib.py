@@ -78,7 +78,7 @@ _SIG = {
     "b200rec_embed_fm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
                                      c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200rec_gather": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int64, _P]),
-    "b200rec_segment_reduce_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "b200rec_segment_reduce_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_segment_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "b200rec_rows_to_dense": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, _P]),
     "b200rec_sparse_sgd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, c_double, _P]),

@@ -97,7 +97,7 @@ int b200rec_group_ids(const int64_t* ids, int64_t n, int64_t V, int64_t padding_
 int b200rec_embed_fm_bwd_workspace_bytes(int64_t B, int F, int Dn, int D, size_t* bytes_host) {
   NOT_NULL(bytes_host);
   *bytes_host = align_up((size_t)bwd_dense_grid() * ((size_t)Dn * D + Dn) * sizeof(float), 256) +
-                seg_workspace_bytes(B * F);
+                seg_workspace_bytes(B * F, D);
   return B200REC_OK;
 }
 
@@ -129,10 +129,10 @@ int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, in
   return launch_gather(W, ids, out, n, D, V, padding_idx, ST(stream));
 }
 
-int b200rec_segment_reduce_workspace_bytes(int64_t n, size_t* bytes_host) {
+int b200rec_segment_reduce_workspace_bytes(int64_t n, int D, size_t* bytes_host) {
   NOT_NULL(bytes_host);
   B200_REQUIRE(n >= 0, "segment_reduce: bad sizes");
-  *bytes_host = seg_workspace_bytes(n);
+  *bytes_host = seg_workspace_bytes(n, D);
   return B200REC_OK;
 }
 

@@ -307,7 +307,7 @@ static int launch_embed_fm_bwd(const float* feat, const float* S, const float* d
   B200_REQUIRE(B * F < (int64_t)INT32_MAX, "embed_fm_bwd: B*F must fit int32");
   const int G = bwd_dense_grid();
   const size_t dense_bytes = align_up((size_t)G * ((size_t)Dn * D + Dn) * sizeof(float), 256);
-  const size_t need = dense_bytes + seg_workspace_bytes(B * F);
+  const size_t need = dense_bytes + seg_workspace_bytes(B * F, D);
   if (ws_bytes < need) {
     set_error("embed_fm_bwd: workspace %zu < %zu bytes", ws_bytes, need);
     return B200REC_ERR_WORKSPACE;

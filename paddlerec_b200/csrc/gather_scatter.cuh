@@ -88,8 +88,8 @@ static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                    reinterpret_cast<uintptr_t>(rows) % align == 0,
                "segment_reduce: dOut/rows must be %d-byte aligned", align);
   if (n == 0) return B200REC_OK;
-  if (ws_bytes < seg_workspace_bytes(n)) {
-    set_error("segment_reduce: workspace %zu < %zu bytes", ws_bytes, seg_workspace_bytes(n));
+  if (ws_bytes < seg_workspace_bytes(n, D)) {
+    set_error("segment_reduce: workspace %zu < %zu bytes", ws_bytes, seg_workspace_bytes(n, D));
     return B200REC_ERR_WORKSPACE;
   }
   int rc = B200REC_OK;

@@ -1,10 +1,13 @@
 // Deterministic segmented reduction over positions grouped by id (the scatter-add half of every
-// embedding backward).  Two kernels share one "contribution" functor:
-//   light: one TPR-lane group per distinct id walks its (short) segment sequentially;
-//   hot:   ids that occur more than kHotThreshold times (skewed / Zipf traffic, DIN targets) are
-//          deferred to a list and reduced by a whole CTA each — strided partial sums, then a fixed
-//          shared-memory tree — so a popular id no longer serialises on one lane group.
-// Both orders are fixed by the stable sort => bit-reproducible results, no float atomics.
+// embedding backward).  Three kernels share one "contribution" functor:
+//   light:   one TPR-lane group per distinct id walks its (short) segment sequentially;
+//   hot:     ids that occur more than kHotThreshold times (skewed / Zipf traffic, DIN targets) are
+//            deferred: the light kernel reserves ceil(len/kHotChunk) work items per such id, and
+//            one CTA per item reduces its chunk (strided partial sums + a fixed shared-memory
+//            tree) into a partial row;
+//   combine: adds the partial rows of each hot id in chunk order.
+// All orders are fixed by the stable sort => bit-reproducible results, no float atomics, and a
+// single popular id no longer serialises on one lane group (or one CTA).
 #pragma once
 
 #include "common.cuh"
@@ -12,18 +15,23 @@
 namespace b200rec {
 
 constexpr int kSegThreads = 256;
-constexpr int kHotThreshold = 64;
+constexpr int kHotThreshold = 64;   // segments longer than this go to the hot path
+constexpr int kHotChunk = 2048;     // positions per hot work item (one CTA)
 
-// workspace: [0] hot counter (int32), [1..] hot list (segment indices)
-static inline size_t seg_workspace_bytes(int64_t n) {
-  return ((size_t)(n / kHotThreshold) + 8) * sizeof(int32_t);
+// workspace layout: int32 counter | int32 items[2*max_items] (segment, chunk) | float partials
+static inline size_t seg_max_items(int64_t n) { return (size_t)(n / kHotThreshold) + 1; }
+static inline size_t seg_workspace_bytes(int64_t n, int D) {
+  const size_t items = seg_max_items(n);
+  return align_up(16 + items * 2 * sizeof(int32_t), 256) + items * (size_t)(D + 1) * sizeof(float) +
+         256;
 }
 
 template <int VEC, int TPR, typename Contrib>
 __global__ void __launch_bounds__(kSegThreads)
 seg_light_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ sorted_pos,
                  const int32_t* __restrict__ num_unique, Contrib contrib, float* __restrict__ rows,
-                 float* __restrict__ rows1, int D, int32_t* __restrict__ hot) {
+                 float* __restrict__ rows1, int D, int32_t* __restrict__ hot_count,
+                 int32_t* __restrict__ hot_items) {
   constexpr int GPB = kSegThreads / TPR;
   const int U = num_unique[0];
   const int r = threadIdx.x % TPR;
@@ -33,7 +41,14 @@ seg_light_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restr
     const int beg = seg_offsets[u];
     const int end = seg_offsets[u + 1];
     if (end - beg > kHotThreshold) {
-      if (r == 0) hot[1 + atomicAdd(hot, 1)] = (int32_t)u;
+      if (r == 0) {
+        const int chunks = (end - beg + kHotChunk - 1) / kHotChunk;
+        const int first = atomicAdd(hot_count, chunks);
+        for (int c = 0; c < chunks; ++c) {
+          hot_items[2 * (first + c)] = (int32_t)u;
+          hot_items[2 * (first + c) + 1] = c | (c == 0 ? (chunks << 16) : 0);  // head knows #chunks
+        }
+      }
       continue;
     }
     Vec<VEC> acc = vzero<VEC>();
@@ -47,19 +62,20 @@ seg_light_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restr
 template <int VEC, int TPR, typename Contrib>
 __global__ void __launch_bounds__(kSegThreads)
 seg_hot_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ sorted_pos,
-               Contrib contrib, float* __restrict__ rows, float* __restrict__ rows1, int D,
-               const int32_t* __restrict__ hot) {
+               Contrib contrib, int D, const int32_t* __restrict__ hot_count,
+               const int32_t* __restrict__ hot_items, float* __restrict__ partials) {
   constexpr int GPB = kSegThreads / TPR;
   __shared__ float s_acc[GPB][TPR * VEC + 1];
   __shared__ float s_acc1[GPB];
-  const int n_hot = hot[0];
+  const int n_items = hot_count[0];
   const int g = threadIdx.x / TPR;
   const int r = threadIdx.x % TPR;
   const bool lane_ok = r * VEC < D;
-  for (int h = blockIdx.x; h < n_hot; h += gridDim.x) {
-    const int u = hot[1 + h];
-    const int beg = seg_offsets[u];
-    const int end = seg_offsets[u + 1];
+  for (int h = blockIdx.x; h < n_items; h += gridDim.x) {
+    const int u = hot_items[2 * h];
+    const int chunk = hot_items[2 * h + 1] & 0xffff;
+    const int beg = seg_offsets[u] + chunk * kHotChunk;
+    const int end = min(seg_offsets[u + 1], beg + kHotChunk);
     Vec<VEC> acc = vzero<VEC>();
     float acc1 = 0.f;
     for (int i = beg + g; i < end; i += GPB)
@@ -77,35 +93,65 @@ seg_hot_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restric
       __syncthreads();
     }
     if (g == 0) {
+      float* out = partials + (size_t)h * (D + 1);
       if (lane_ok) {
-        Vec<VEC> o;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o.v[k] = s_acc[0][r * VEC + k];
-        st_plain<VEC>(rows + (size_t)u * D + r * VEC, o);
+        for (int k = 0; k < VEC; ++k) out[r * VEC + k] = s_acc[0][r * VEC + k];
       }
-      if (rows1 != nullptr && r == 0) rows1[u] = s_acc1[0];
+      if (r == 0) out[D] = s_acc1[0];
     }
     __syncthreads();
   }
 }
 
-// Launches light + hot.  `ws` must hold seg_workspace_bytes(n).
+// one thread per (hot id, column): rows[u] = sum_c partials[first+c] in chunk order
+__global__ void seg_combine_kernel(const int32_t* __restrict__ hot_count,
+                                   const int32_t* __restrict__ hot_items,
+                                   const float* __restrict__ partials, float* __restrict__ rows,
+                                   float* __restrict__ rows1, int D) {
+  const int n_items = hot_count[0];
+  for (int h = blockIdx.x; h < n_items; h += gridDim.x) {
+    const int meta = hot_items[2 * h + 1];
+    if ((meta & 0xffff) != 0) continue;  // not a head item
+    const int chunks = meta >> 16;
+    const int u = hot_items[2 * h];
+    for (int d = threadIdx.x; d <= D; d += blockDim.x) {
+      float t = 0.f;
+      for (int c = 0; c < chunks; ++c) t += partials[(size_t)(h + c) * (D + 1) + d];
+      if (d < D)
+        rows[(size_t)u * D + d] = t;
+      else if (rows1 != nullptr)
+        rows1[u] = t;
+    }
+  }
+}
+
+// Launches light + hot + combine.  `ws` must hold seg_workspace_bytes(n, D).
+// A hot id is limited to 32767 chunks (6.7e7 positions) by the item encoding.
 template <int VEC, int TPR, typename Contrib>
 static int launch_seg_reduce(const int32_t* seg_offsets, const int32_t* sorted_pos,
                              const int32_t* num_unique, const Contrib& contrib, float* rows,
                              float* rows1, int64_t n, int D, void* ws, cudaStream_t st) {
-  int32_t* hot = static_cast<int32_t*>(ws);
-  B200_CUDA(cudaMemsetAsync(hot, 0, sizeof(int32_t), st));
+  B200_REQUIRE(n < (int64_t)32767 * kHotChunk, "segment reduce: n=%lld too large", (long long)n);
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  int32_t* hot_count = reinterpret_cast<int32_t*>(base);
+  int32_t* hot_items = reinterpret_cast<int32_t*>(base + 16);
+  const size_t items = seg_max_items(n);
+  float* partials = reinterpret_cast<float*>(
+      base + align_up(16 + items * 2 * sizeof(int32_t), 256));
+  B200_CUDA(cudaMemsetAsync(hot_count, 0, sizeof(int32_t), st));
   constexpr int GPB = kSegThreads / TPR;
   const int64_t want = (n + GPB - 1) / GPB;
   const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
   seg_light_kernel<VEC, TPR, Contrib><<<grid, kSegThreads, 0, st>>>(
-      seg_offsets, sorted_pos, num_unique, contrib, rows, rows1, D, hot);
+      seg_offsets, sorted_pos, num_unique, contrib, rows, rows1, D, hot_count, hot_items);
   B200_LAUNCH_CHECK();
   if (n > kHotThreshold) {
-    const unsigned hgrid = (unsigned)min((int64_t)(n / kHotThreshold), (int64_t)sm_count() * 8);
-    seg_hot_kernel<VEC, TPR, Contrib><<<hgrid, kSegThreads, 0, st>>>(seg_offsets, sorted_pos, contrib,
-                                                                    rows, rows1, D, hot);
+    const unsigned hgrid = (unsigned)min((int64_t)items, (int64_t)sm_count() * 8);
+    seg_hot_kernel<VEC, TPR, Contrib><<<hgrid, kSegThreads, 0, st>>>(
+        seg_offsets, sorted_pos, contrib, D, hot_count, hot_items, partials);
+    B200_LAUNCH_CHECK();
+    seg_combine_kernel<<<hgrid, 128, 0, st>>>(hot_count, hot_items, partials, rows, rows1, D);
     B200_LAUNCH_CHECK();
   }
   return B200REC_OK;

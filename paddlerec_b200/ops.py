@@ -40,7 +40,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 # it as `gpu_launches`.  KERNELS_PER_CALL is the static number of our kernels each entry point runs.
 LAUNCHES = 0
 KERNELS_PER_CALL = {
-    "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 4, "gather": 1, "segment_reduce": 2,
+    "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
     "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
     "cross_v2_bwd": 2, "shard_bucketize": 2,
 }
@@ -217,7 +217,7 @@ def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int) 
     D = dOut.shape[-1]
     rows = torch.empty(max(n, 1), D, dtype=torch.float32, device=dOut.device)
     nbytes = ctypes.c_size_t(0)
-    check(lib.b200rec_segment_reduce_workspace_bytes(n, ctypes.byref(nbytes)), "segment_reduce_ws")
+    check(lib.b200rec_segment_reduce_workspace_bytes(n, D, ctypes.byref(nbytes)), "segment_reduce_ws")
     ws = workspace(nbytes.value, dOut.device, "segred")
     check(lib.b200rec_segment_reduce(ptr(dOut), ptr(groups_seg), ptr(groups_pos), ptr(num),
                                      ptr(rows), n, D, ptr(ws), ws.numel(), _stream()),

@@ -1,0 +1,258 @@
+"""Row-cyclic sharding of the embedding tables over the GPUs of one box, with an NCCL all-to-all on
+the id -> owner and row -> requester exchanges.
+
+Behavioural spec in the reference: the PSGPU / HeterPS pull-push of the GPUBox trainer
+(tools/static_gpubox_trainer.py:152-159 builds the per-GPU HBM tables, :244-259 runs
+pull_sparse -> fwd/bwd -> push_sparse per batch; tools/run_gpubox.sh:7-45 launches it).  Here:
+
+    owner(id) = id mod world,  local_row(id) = id div world        (padding id 0 lives on rank 0)
+    forward   bucketize ids by owner  ->  all-to-all(counts)  ->  all-to-all(ids)
+              owner: b200rec_gather on its shard  ->  all-to-all(rows) back
+              requester: the SAME fused kernel as the single-GPU path (b200rec_embed_fm_fwd) over
+              the received rows, indexed by the bucket permutation
+    backward  requester: b200rec_embed_fm_bwd emits per-slot gradients in bucket order
+              all-to-all(grads) to the owners  ->  owner: group_ids + segment_reduce on local rows
+              -> SelectedRows on the local shard -> row-wise optimizer
+    dense     parameters are replicated; their gradients are all-reduced in one flat bucket.
+
+The collective plumbing is torch.distributed (NCCL on GPUs; gloo in the CPU unit tests, which
+inject a torch stand-in for the kernel set — the product default `ops` has no CPU path).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as tnn
+
+from . import nn as bnn
+from . import ops as _cuda_ops
+from . import optim
+
+
+def shard_rows(V: int, rank: int, world: int) -> int:
+    """Number of global ids with id % world == rank."""
+    return (V - rank + world - 1) // world if V > rank else 0
+
+
+@dataclass
+class ExchangePlan:
+    n: int
+    perm: torch.Tensor        # int64 [n]: slot of each position in bucket order
+    inv_perm: torch.Tensor    # int32 [n]
+    send_splits: List[int]    # ids sent to each rank
+    recv_splits: List[int]    # ids received from each rank
+    recv_ids: torch.Tensor    # int64 [m]: local rows requested from this rank (owner view)
+
+
+class ShardExchange:
+    """The all-to-all choreography; shared by every table that is looked up with the same ids."""
+
+    def __init__(self, V: int, rank: int, world: int, group=None, kernels=_cuda_ops):
+        self.V, self.rank, self.world, self.group, self.k = V, rank, world, group, kernels
+
+    def plan(self, ids: torch.Tensor) -> ExchangePlan:
+        ids = ids.reshape(-1)
+        n = ids.numel()
+        send_ids, perm, inv_perm, counts = self.k.raw_shard_bucketize(ids, self.world, self.V)
+        recv_counts = torch.empty_like(counts)
+        dist.all_to_all_single(recv_counts, counts, group=self.group)
+        both = torch.stack([counts, recv_counts]).cpu()      # the one host sync of the exchange
+        send_splits, recv_splits = both[0].tolist(), both[1].tolist()
+        recv_ids = torch.empty(sum(recv_splits), dtype=torch.int64, device=ids.device)
+        dist.all_to_all_single(recv_ids, send_ids, recv_splits, send_splits, group=self.group)
+        return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, recv_ids)
+
+    def pull(self, plan: ExchangePlan, shard: torch.Tensor, local_pad: int) -> torch.Tensor:
+        """Owner-side gather + rows back to the requesters: returns [n, D] in bucket order."""
+        rows_out = self.k.raw_gather(shard, plan.recv_ids, local_pad)
+        rows_in = torch.empty(plan.n, shard.shape[1], dtype=shard.dtype, device=shard.device)
+        dist.all_to_all_single(rows_in, rows_out, plan.send_splits, plan.recv_splits,
+                               group=self.group)
+        return rows_in
+
+    def push(self, plan: ExchangePlan, grads_bucket_order: torch.Tensor) -> torch.Tensor:
+        """Per-slot gradients [n, D] (bucket order) -> owners: returns [m, D] aligned with
+        plan.recv_ids."""
+        D = grads_bucket_order.shape[1]
+        out = torch.empty(plan.recv_ids.numel(), D, dtype=grads_bucket_order.dtype,
+                          device=grads_bucket_order.device)
+        dist.all_to_all_single(out, grads_bucket_order.contiguous(), plan.recv_splits,
+                               plan.send_splits, group=self.group)
+        return out
+
+    def owner_reduce(self, plan: ExchangePlan, grads: torch.Tensor, V_loc: int, local_pad: int):
+        """Merge the received gradients by local row -> SelectedRows on the local shard."""
+        groups = self.k.raw_group_ids(plan.recv_ids, max(V_loc, 1), local_pad)
+        rows = self.k.raw_segment_reduce(grads, groups.seg_offsets, groups.sorted_pos, groups.num,
+                                         groups.n)
+        return self.k.SelectedRows(groups.unique_ids, rows, groups.num, V_loc)
+
+
+class ShardedEmbedding(bnn.Embedding):
+    """The local shard ([ceil((V-rank)/world), D]) of a row-cyclically sharded table."""
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx, rank, world, init_std=None,
+                 init="truncated_normal", device=None):
+        local_pad = None
+        if padding_idx is not None and padding_idx % world == rank:
+            local_pad = padding_idx // world
+        super().__init__(shard_rows(num_embeddings, rank, world), embedding_dim, local_pad,
+                         init_std=init_std, init=init, device=device)
+        self.global_rows, self.rank, self.world = num_embeddings, rank, world
+
+    def forward(self, ids):
+        raise RuntimeError("a sharded table is looked up through ShardExchange")
+
+
+class _ShardedEmbedFM(torch.autograd.Function):
+    """DeepFM's FM block over sharded tables: exchange + the single-GPU fused kernels."""
+
+    @staticmethod
+    def forward(ctx, ids, dense, dense_w, dense_w1, fm):
+        k, ex = fm.k, fm.exchange
+        B, F = ids.shape
+        plan = ex.plan(ids)
+        rows = ex.pull(plan, fm.embedding.weight, fm.embedding.pad)
+        rows1 = ex.pull(plan, fm.embedding_one.weight, fm.embedding_one.pad)
+        D = rows.shape[1]
+        slot_ids = plan.perm.reshape(B, F)
+        feat, y1, y2, S = k.raw_embed_fm_fwd(rows, rows1, slot_ids, dense, dense_w.reshape(-1, D),
+                                             dense_w1.reshape(-1), -1)
+        ctx.save_for_backward(dense, feat, S)
+        ctx.plan, ctx.fm, ctx.F = plan, fm, F
+        ctx.dense_w_shape = dense_w.shape
+        return feat, y1.unsqueeze(1), y2.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, dfeat, dy1, dy2):
+        dense, feat, S = ctx.saved_tensors
+        fm, plan, F = ctx.fm, ctx.plan, ctx.F
+        k, ex = fm.k, fm.exchange
+        B = feat.shape[0]
+        dev = feat.device
+        gy1 = dy1.reshape(-1).contiguous() if dy1 is not None else torch.zeros(B, device=dev)
+        gy2 = dy2.reshape(-1).contiguous() if dy2 is not None else torch.zeros(B, device=dev)
+        if dfeat is not None:
+            dfeat = dfeat.contiguous()
+        n = plan.n
+        iota = torch.arange(n + 1, dtype=torch.int32, device=dev)
+        num = torch.tensor([n, n], dtype=torch.int32, device=dev)
+        # seg_offsets = iota, sorted_pos = inv_perm: row k of the output is the gradient of slot k
+        dW, dW1, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
+                                                          plan.inv_perm, num, F)
+        g = ex.push(plan, dW[:n])
+        g1 = ex.push(plan, dW1[:n].unsqueeze(1))
+        emb, emb1 = fm.embedding, fm.embedding_one
+        emb.accept(ex.owner_reduce(plan, g, emb.num_embeddings, emb.pad))
+        emb1.accept(ex.owner_reduce(plan, g1, emb1.num_embeddings, emb1.pad))
+        return None, None, ddense_w.reshape(ctx.dense_w_shape), ddense_w1, None
+
+
+class ShardedFM(tnn.Module):
+    """FM of models/rank/deepfm/net.py:52-139 with both tables sharded (same state_dict names;
+    `embedding*.weight` hold the LOCAL shard)."""
+
+    def __init__(self, sparse_feature_number, sparse_feature_dim, dense_feature_dim,
+                 sparse_num_field, rank, world, group=None, device="cuda", kernels=_cuda_ops):
+        super().__init__()
+        self.k = kernels
+        self.sparse_feature_number = sparse_feature_number
+        self.sparse_feature_dim = sparse_feature_dim
+        std = 0.1 / math.sqrt(float(sparse_feature_dim))
+        self.embedding_one = ShardedEmbedding(sparse_feature_number, 1, 0, rank, world,
+                                              init_std=std, device=device)
+        self.embedding = ShardedEmbedding(sparse_feature_number, sparse_feature_dim, 0, rank,
+                                          world, init_std=std, device=device)
+        self.dense_w_one = tnn.Parameter(torch.empty(dense_feature_dim, device=device))
+        self.dense_w = tnn.Parameter(
+            torch.empty(1, dense_feature_dim, sparse_feature_dim, device=device))
+        tnn.init.trunc_normal_(self.dense_w_one, 0.0, std, -2 * std, 2 * std)
+        tnn.init.trunc_normal_(self.dense_w, 0.0, std, -2 * std, 2 * std)
+        self.exchange = ShardExchange(sparse_feature_number, rank, world, group, kernels)
+
+    def forward(self, sparse_inputs, dense_inputs):
+        ids = (torch.cat(list(sparse_inputs), dim=1) if isinstance(sparse_inputs, (list, tuple))
+               else sparse_inputs)
+        feat, y1, y2 = _ShardedEmbedFM.apply(ids, dense_inputs, self.dense_w, self.dense_w_one, self)
+        return y1, y2, feat
+
+
+class ShardedDeepFMLayer(tnn.Module):
+    """DeepFMLayer (net.py:21-49) with sharded tables and a replicated tower."""
+
+    def __init__(self, sparse_feature_number, sparse_feature_dim, dense_feature_dim,
+                 sparse_num_field, layer_sizes, rank, world, group=None, device="cuda",
+                 kernels=_cuda_ops):
+        super().__init__()
+        from .rank.deepfm import net
+        self.fm = ShardedFM(sparse_feature_number, sparse_feature_dim, dense_feature_dim,
+                            sparse_num_field, rank, world, group, device, kernels)
+        self.dnn = net.DNN(sparse_feature_number, sparse_feature_dim, dense_feature_dim,
+                           dense_feature_dim + sparse_num_field, layer_sizes, device=device)
+        self.bias = tnn.Parameter(torch.zeros(1, device=device))
+        self.world, self.group = world, group
+        sync_dense_parameters(self, group)
+
+    def forward(self, sparse_inputs, dense_inputs):
+        y1, y2, feat = self.fm(sparse_inputs, dense_inputs)
+        return torch.sigmoid(y1 + y2 + self.dnn(feat))
+
+
+def dense_parameters(model: tnn.Module) -> List[torch.Tensor]:
+    return [p for p in model.parameters() if not getattr(p, "is_sparse_table", False)]
+
+
+@torch.no_grad()
+def sync_dense_parameters(model: tnn.Module, group=None) -> None:
+    """Replicas must start identical: broadcast rank 0's dense parameters."""
+    for p in dense_parameters(model):
+        dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                       group=group)
+
+
+class DistributedOptimizer:
+    """Wraps a paddlerec_b200.optim optimizer: all-reduces (SUM) the dense gradients in one flat
+    bucket before the step.  Callers scale the local loss by 1/world (`scale_loss`) so that the
+    summed dense gradients and the owner-summed table gradients both equal the gradient of the
+    global-batch mean loss — what fleet.distributed_model does at tools/trainer.py:113-118."""
+
+    def __init__(self, inner, model: tnn.Module, world: int, group=None):
+        self.inner, self.world, self.group = inner, world, group
+        self._dense = [p for p in dense_parameters(model) if p.requires_grad]
+
+    def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
+        return loss / self.world
+
+    def clear_grad(self):
+        self.inner.clear_grad()
+
+    def step(self):
+        grads = [p.grad for p in self._dense if p.grad is not None]
+        if grads and self.world > 1:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, group=self.group)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self.inner.step()
+
+
+def create_sharded_deepfm(config, device, rank, world, group=None, kernels=_cuda_ops):
+    return ShardedDeepFMLayer(
+        config.get("hyper_parameters.sparse_feature_number"),
+        config.get("hyper_parameters.sparse_feature_dim"),
+        config.get("hyper_parameters.dense_input_dim"),
+        config.get("hyper_parameters.sparse_inputs_slots") - 1,
+        config.get("hyper_parameters.fc_sizes"), rank, world, group, device, kernels)
+
+
+def create_optimizer(model, config, world=None, group=None):
+    lr = config.get("hyper_parameters.optimizer.learning_rate", 0.001)
+    inner = optim.Adam(learning_rate=lr, parameters=model.parameters(), lazy_mode=True)
+    world = world if world is not None else dist.get_world_size(group)
+    return DistributedOptimizer(inner, model, world, group)

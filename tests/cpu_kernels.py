@@ -1,0 +1,99 @@
+"""A torch (CPU) stand-in for the kernel set that paddlerec_b200.sharded takes by injection.
+TEST DOUBLE ONLY: it lets the world_size-2 gloo tests exercise the all-to-all choreography,
+split bookkeeping and gradient routing on a box without a GPU.  The product default is
+paddlerec_b200.ops (CUDA through the C ABI, no CPU path)."""
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class IdGroups:
+    unique_ids: torch.Tensor
+    seg_offsets: torch.Tensor
+    sorted_pos: torch.Tensor
+    num: torch.Tensor
+    n: int
+    height: int
+
+
+@dataclass
+class SelectedRows:
+    rows: torch.Tensor
+    value: torch.Tensor
+    num: torch.Tensor
+    height: int
+
+    def to_dense(self):
+        U = int(self.num[0])
+        out = torch.zeros(self.height, self.value.shape[1])
+        out[self.rows[:U]] += self.value[:U]
+        return out
+
+
+def raw_shard_bucketize(ids, world, V):
+    ids = ids.reshape(-1)
+    n = ids.numel()
+    valid = (ids >= 0) & (ids < V)
+    owner = torch.where(valid, ids % world, torch.zeros_like(ids))
+    inv_perm = torch.sort(owner, stable=True).indices
+    perm = torch.empty(n, dtype=torch.int64)
+    perm[inv_perm] = torch.arange(n)
+    local = torch.where(valid, ids // world, torch.full_like(ids, -1))
+    counts = torch.bincount(owner, minlength=world).to(torch.int64)
+    return local[inv_perm], perm, inv_perm.to(torch.int32), counts
+
+
+def raw_gather(W, ids, pad):
+    ok = (ids >= 0) & (ids < W.shape[0]) & (ids != pad)
+    return W[ids.clamp(0, max(W.shape[0] - 1, 0))] * ok.unsqueeze(-1).to(W.dtype)
+
+
+def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, pad, want_S=True):
+    e = raw_gather(W, ids, pad)
+    e1 = raw_gather(W1.reshape(-1, 1), ids, pad)
+    feat = torch.cat([e, dense.unsqueeze(2) * dense_w.unsqueeze(0)], 1)
+    y1 = e1.sum((1, 2)) + (dense * dense_w1).sum(1)
+    S = feat.sum(1)
+    y2 = 0.5 * (S.square() - feat.square().sum(1)).sum(1)
+    return feat, y1, y2, S
+
+
+def raw_group_ids(ids, V, pad):
+    ids = ids.reshape(-1)
+    n = ids.numel()
+    keep = (ids >= 0) & (ids < V) & (ids != pad)
+    key = torch.where(keep, ids, torch.full_like(ids, V))
+    order = torch.sort(key, stable=True).indices
+    kept = int(keep.sum())
+    uniq, cnt = torch.unique_consecutive(key[order][:kept], return_counts=True)
+    U = uniq.numel()
+    seg = torch.zeros(n + 1, dtype=torch.int32)
+    seg[1:U + 1] = torch.cumsum(cnt, 0).to(torch.int32)
+    unique_ids = torch.zeros(max(n, 1), dtype=torch.int64)
+    unique_ids[:U] = uniq
+    return IdGroups(unique_ids, seg, order.to(torch.int32), torch.tensor([U, kept], dtype=torch.int32),
+                    n, V)
+
+
+def raw_segment_reduce(dOut, seg, pos, num, n):
+    D = dOut.shape[-1]
+    rows = torch.zeros(max(n, 1), D)
+    for u in range(int(num[0])):
+        rows[u] = dOut[pos[seg[u]:seg[u + 1]].long()].sum(0)
+    return rows
+
+
+def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg, pos, num, F):
+    B, N, D = feat.shape
+    dfeat = gy2.reshape(B, 1, 1) * (S.unsqueeze(1) - feat)
+    if dfeat_dnn is not None:
+        dfeat = dfeat + dfeat_dnn
+    flat = dfeat[:, :F].reshape(B * F, D)
+    g1 = gy1.reshape(B, 1).expand(B, F).reshape(B * F, 1)
+    n = B * F
+    dW = raw_segment_reduce(flat, seg, pos, num, n)
+    dW1 = raw_segment_reduce(g1, seg, pos, num, n).reshape(-1)
+    ddense_w = (dense.unsqueeze(2) * dfeat[:, F:]).sum(0)
+    ddense_w1 = (gy1.reshape(B, 1) * dense).sum(0)
+    return dW, dW1, ddense_w, ddense_w1

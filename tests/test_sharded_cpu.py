@@ -1,0 +1,122 @@
+"""N>1 path on CPU: world_size=2 over gloo.  The sharded DeepFM (row-cyclic tables, all-to-all of
+ids/rows/grads, all-reduced dense grads) must reproduce the single-process oracle on the global
+batch: predictions, dense gradients, and each rank's shard of the table gradients."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import nets
+from tests import cpu_kernels
+
+V, D, Dn, F, FC, B = 53, 8, 13, 26, [16, 8], 12
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _full_problem():
+    g = torch.Generator().manual_seed(2468)
+    p = {"fm.embedding.weight": torch.randn(V, D, generator=g) * 0.1,
+         "fm.embedding_one.weight": torch.randn(V, 1, generator=g) * 0.1,
+         "fm.dense_w": torch.randn(1, Dn, D, generator=g) * 0.1,
+         "fm.dense_w_one": torch.randn(Dn, generator=g) * 0.1}
+    sizes = [(F + Dn) * D] + FC + [1]
+    for i in range(len(sizes) - 1):
+        p["dnn.linear_%d.weight" % i] = torch.randn(sizes[i], sizes[i + 1], generator=g) / sizes[i] ** 0.5
+        p["dnn.linear_%d.bias" % i] = torch.randn(sizes[i + 1], generator=g) * 0.01
+    p["fm.embedding.weight"][0] = 0
+    p["fm.embedding_one.weight"][0] = 0
+    ids = torch.randint(0, V, (B, F), generator=g)
+    ids[0, :3] = 0
+    ids[5, 2] = V + 3     # out-of-range id: zeros, no gradient
+    dense = torch.rand(B, Dn, generator=g)
+    label = (torch.rand(B, 1, generator=g) < 0.4).float()
+    return p, ids, dense, label
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import sharded
+        p, ids, dense, label = _full_problem()
+        torch.manual_seed(100 + rank)   # different init per rank: broadcast must fix the tower
+        model = sharded.ShardedDeepFMLayer(V, D, Dn, F, FC, rank, world, device="cpu",
+                                           kernels=cpu_kernels)
+        with torch.no_grad():
+            sd = model.state_dict()
+            for k, v in p.items():
+                if k in ("fm.embedding.weight", "fm.embedding_one.weight"):
+                    sd[k].copy_(v[rank::world])
+                else:
+                    sd[k].copy_(v)
+        per = B // world
+        sl = slice(rank * per, (rank + 1) * per)
+        pred = model(ids[sl], dense[sl])
+        loss = BF.log_loss(pred, label[sl]).mean()
+        opt = sharded.DistributedOptimizer(_NoStep(), model, world)
+        opt.scale_loss(loss).backward()
+        opt.step()   # all-reduce of the dense grads only
+        res = {"pred": pred.detach().numpy(),
+               "dW": model.fm.embedding.grad_rows.to_dense().numpy(),
+               "dW1": model.fm.embedding_one.grad_rows.to_dense().numpy()}
+        for k, v in model.named_parameters():
+            if v.grad is not None:
+                res["g:" + k] = v.grad.numpy()
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+class _NoStep:
+    def step(self):
+        pass
+
+    def clear_grad(self):
+        pass
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_deepfm_matches_oracle(world, tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    p, ids, dense, label = _full_problem()
+    pp = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    ids_ok = ids.clone()
+    ids_ok[ids_ok >= V] = 0
+    pred = nets.deepfm_forward(pp, [ids_ok[:, i:i + 1] for i in range(F)], dense.double(), len(FC))
+    loss = nets.log_loss(pred, label.double()).mean()
+    loss.backward()
+    per = B // world
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        np.testing.assert_allclose(r["pred"], pred.detach().numpy()[rank * per:(rank + 1) * per],
+                                   rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(r["dW"], pp["fm.embedding.weight"].grad.numpy()[rank::world],
+                                   rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(r["dW1"], pp["fm.embedding_one.weight"].grad.numpy()[rank::world],
+                                   rtol=2e-4, atol=1e-7)
+        for k in pp:
+            if k.startswith("fm.embedding"):
+                continue
+            np.testing.assert_allclose(r["g:" + k], pp[k].grad.numpy(), rtol=2e-4, atol=1e-7,
+                                       err_msg=k)
+
+
+def test_shard_rows_partition():
+    from paddlerec_b200.sharded import shard_rows
+    for V_ in (1, 7, 8, 9, 100000001):
+        for w in (1, 2, 4, 8):
+            assert sum(shard_rows(V_, r, w) for r in range(w)) == V_

@@ -1,0 +1,75 @@
+"""N>1 path on real GPUs (needs >= 2 visible devices; skipped otherwise): NCCL all-to-all + the CUDA
+kernels must reproduce the single-process oracle on the global batch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import nets
+from tests.test_sharded_cpu import B, D, Dn, F, FC, V, _free_port, _full_problem, _NoStep
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import sharded
+        dev = torch.device("cuda", rank)
+        p, ids, dense, label = _full_problem()
+        torch.manual_seed(100 + rank)
+        model = sharded.ShardedDeepFMLayer(V, D, Dn, F, FC, rank, world, device=dev)
+        with torch.no_grad():
+            sd = model.state_dict()
+            for k, v in p.items():
+                sd[k].copy_(v[rank::world] if k.startswith("fm.embedding") else v)
+        per = B // world
+        sl = slice(rank * per, (rank + 1) * per)
+        pred = model(ids[sl].to(dev), dense[sl].to(dev))
+        loss = BF.log_loss(pred, label[sl].to(dev)).mean()
+        opt = sharded.DistributedOptimizer(_NoStep(), model, world)
+        opt.scale_loss(loss).backward()
+        opt.step()
+        res = {"pred": pred.detach().cpu().numpy(),
+               "dW": model.fm.embedding.grad_rows.to_dense().cpu().numpy(),
+               "dW1": model.fm.embedding_one.grad_rows.to_dense().cpu().numpy()}
+        for k, v in model.named_parameters():
+            if v.grad is not None:
+                res["g:" + k] = v.grad.cpu().numpy()
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_deepfm_nccl(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    p, ids, dense, label = _full_problem()
+    pp = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    ids_ok = ids.clone()
+    ids_ok[ids_ok >= V] = 0
+    pred = nets.deepfm_forward(pp, [ids_ok[:, i:i + 1] for i in range(F)], dense.double(), len(FC))
+    nets.log_loss(pred, label.double()).mean().backward()
+    per = B // world
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        np.testing.assert_allclose(r["pred"], pred.detach().numpy()[rank * per:(rank + 1) * per],
+                                   rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(r["dW"], pp["fm.embedding.weight"].grad.numpy()[rank::world],
+                                   rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(r["dW1"], pp["fm.embedding_one.weight"].grad.numpy()[rank::world],
+                                   rtol=1e-4, atol=1e-7)
+        for k in pp:
+            if not k.startswith("fm.embedding"):
+                np.testing.assert_allclose(r["g:" + k], pp[k].grad.numpy(), rtol=1e-4, atol=1e-7,
+                                           err_msg=k)
