@@ -144,6 +144,25 @@ int b200rec_cross_v2_bwd(const float* dout, const float* x0, const float* xw, co
                          float* dxw, float* dx0, float* dbias, int64_t B, int C,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- tower epilogues (bf16 hi/lo split operands for the tensor-core GEMMs) -- */
+/* The MLP tower (DNN.forward, models/rank/deepfm/net.py:169-174) runs its GEMMs on the bf16 tensor
+ * cores as a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32 accumulate).  These fuse everything
+ * between two GEMMs into one pass.  bf16 buffers are passed as void*.
+ *   split:          out[m,0:K] = hi(f(x[m,:])), out[m,K:2K] = lo(...),  f = (+bias) then (ReLU)
+ *   relu_bwd_split: dz = dy * (act_hi > 0) (act may be NULL: no mask); dz_out = [hi|lo];
+ *                   dbias[n] = sum_m dz[m,n]   (deterministic)
+ *   prep_weight:    W[K,N] -> W2r[2K,N]=[hi;hi], W2c[K,2N]=[hi|hi], Wlo[K,N]
+ *   fold_dw:        dW = Mx[0:K,0:N] + Mx[0:K,N:2N] + Mx[K:2K,0:N],  Mx = [a_hi|a_lo]^T [dz_hi|dz_lo] */
+int b200rec_tower_split(const float* x, const float* bias, int relu, void* out_bf16, int64_t M,
+                        int K, void* stream);
+int b200rec_tower_bwd_workspace_bytes(int64_t M, int N, size_t* bytes_host);
+int b200rec_tower_relu_bwd_split(const float* dy, const void* act_bf16, void* dz_bf16,
+                                 float* dbias, int64_t M, int N, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int b200rec_tower_prep_weight(const float* W, void* W2r_bf16, void* W2c_bf16, void* Wlo_bf16,
+                              int K, int N, void* stream);
+int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream);
+
 /* ---- K5: row-cyclic sharding helpers (owner = id mod world) --------------- */
 /* Stable bucketing of n ids by owner rank (bucket order = owner-major, original order inside).
  *   send_ids[k]   local row (id div world) of the k-th id in bucket order; -1 if out of range

@@ -10,6 +10,7 @@
 #include "gather_scatter.cuh"
 #include "cross.cuh"
 #include "shard.cuh"
+#include "tower.cuh"
 #include "din_attn.cuh"
 
 namespace b200rec {
@@ -225,6 +226,48 @@ int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V,
   if (n > 0) { NOT_NULL(ids); NOT_NULL(send_ids); NOT_NULL(perm); NOT_NULL(inv_perm); NOT_NULL(workspace); }
   return launch_shard_bucketize(ids, n, world, V, send_ids, perm, inv_perm, counts, workspace,
                                 workspace_bytes, ST(stream));
+}
+
+int b200rec_tower_split(const float* x, const float* bias, int relu, void* out_bf16, int64_t M,
+                        int K, void* stream) {
+  if (M > 0) { NOT_NULL(x); NOT_NULL(out_bf16); }
+  return launch_tower_split(x, bias, relu, out_bf16, M, K, ST(stream));
+}
+
+int b200rec_tower_bwd_workspace_bytes(int64_t M, int N, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  *bytes_host = (size_t)tower_row_slices(M) * (size_t)N * sizeof(float) + 16;
+  return B200REC_OK;
+}
+
+int b200rec_tower_relu_bwd_split(const float* dy, const void* act_bf16, void* dz_bf16,
+                                 float* dbias, int64_t M, int N, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  NOT_NULL(dbias);
+  if (M > 0) { NOT_NULL(dy); NOT_NULL(dz_bf16); NOT_NULL(workspace); }
+  return launch_tower_relu_bwd_split(dy, act_bf16, dz_bf16, dbias, M, N, workspace,
+                                     workspace_bytes, ST(stream));
+}
+
+int b200rec_tower_prep_weight(const float* W, void* W2r_bf16, void* W2c_bf16, void* Wlo_bf16,
+                              int K, int N, void* stream) {
+  B200_REQUIRE(K > 0 && N > 0, "tower_prep_weight: bad sizes");
+  NOT_NULL(W); NOT_NULL(W2r_bf16); NOT_NULL(W2c_bf16); NOT_NULL(Wlo_bf16);
+  const int64_t total = (int64_t)K * N;
+  tower_prep_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(
+      W, static_cast<__nv_bfloat16*>(W2r_bf16), static_cast<__nv_bfloat16*>(W2c_bf16),
+      static_cast<__nv_bfloat16*>(Wlo_bf16), K, N);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream) {
+  B200_REQUIRE(K > 0 && N > 0, "tower_fold_dw: bad sizes");
+  NOT_NULL(Mx); NOT_NULL(dW);
+  const int64_t total = (int64_t)K * N;
+  tower_fold_dw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(Mx, dW, K, N);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
 }
 
 #include "din_attn_api.inc"

@@ -1,0 +1,193 @@
+// Tower epilogues: the elementwise halves of the dense MLP tower when its GEMMs run on the bf16
+// tensor cores with a hi/lo split of the fp32 operands ("bf16x3": a*b ~ a_hi*b_hi + a_lo*b_hi +
+// a_hi*b_lo, exact products accumulated in fp32, ~2^-16 relative error — meets the 1e-4 bar that
+// plain TF32 misses).
+//
+// Reference: DNN.forward models/rank/deepfm/net.py:169-174 (Linear -> ReLU chain) and its autograd.
+// The GEMMs themselves are library calls (cuBLASLt through torch.mm(out_dtype=fp32)); what the
+// reference spreads over bias-add / ReLU / cast kernels is one streaming pass per layer here:
+//   forward : y(fp32) --(+bias, ReLU, split)--> [hi | lo] bf16, directly the next GEMM's A operand
+//   backward: dy(fp32) --(ReLU mask from the saved hi half, split, bias column-sum)--> [hi | lo]
+//   weights : W(fp32) --> the three bf16 operand layouts the forward/backward GEMMs consume
+// All HBM-bound: 8 B/element forward, 10 B/element backward.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200rec {
+
+constexpr int kTowerThreads = 256;
+
+__device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+struct alignas(8) Bf16x4 {
+  __nv_bfloat16 v[4];
+};
+
+// out[m, k] = hi(f(x[m,k])), out[m, K+k] = lo(...), f = optional (+bias[k]) then optional ReLU.
+template <int VEC>
+__global__ void __launch_bounds__(kTowerThreads)
+tower_split_kernel(const float* __restrict__ x, const float* __restrict__ bias, int relu,
+                   __nv_bfloat16* __restrict__ out, int64_t M, int K) {
+  const int chunks = K / VEC;
+  const int64_t total = M * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * kTowerThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kTowerThreads) {
+    const int64_t m = i / chunks;
+    const int k = (int)(i - m * chunks) * VEC;
+    Vec<VEC> a = ld_row<VEC>(x + (size_t)m * K + k);
+    if (bias != nullptr) {
+      const Vec<VEC> b = ld_cached<VEC>(bias + k);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a.v[j] += b.v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a.v[j] = fmaxf(a.v[j], 0.f);
+    }
+    __nv_bfloat16* row = out + (size_t)m * 2 * K;
+    if (VEC == 4) {
+      Bf16x4 hi, lo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split1(a.v[j], hi.v[j], lo.v[j]);
+      *reinterpret_cast<Bf16x4*>(row + k) = hi;
+      *reinterpret_cast<Bf16x4*>(row + K + k) = lo;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) split1(a.v[j], row[k + j], row[K + k + j]);
+    }
+  }
+}
+
+// dz = dy * (act_hi > 0) (mask skipped if act == nullptr); dz_out = [hi | lo]; partial column sums
+// of dz per row-slice (thread owns its columns => register accumulation, fixed order).
+template <int VEC>
+__global__ void __launch_bounds__(kTowerThreads)
+tower_relu_bwd_split_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ act,
+                            __nv_bfloat16* __restrict__ dz, float* __restrict__ partials,
+                            int64_t M, int N) {
+  const int chunks = N / VEC;
+  const int chunk = blockIdx.x * kTowerThreads + threadIdx.x;
+  if (chunk >= chunks) return;
+  const int c = chunk * VEC;
+  Vec<VEC> acc = vzero<VEC>();
+  for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
+    Vec<VEC> g = ld_row<VEC>(dy + (size_t)m * N + c);
+    if (act != nullptr) {
+      const __nv_bfloat16* a = act + (size_t)m * 2 * N + c;
+      if (VEC == 4) {
+        const Bf16x4 h = *reinterpret_cast<const Bf16x4*>(a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (!(__bfloat162float(h.v[j]) > 0.f)) g.v[j] = 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (!(__bfloat162float(a[j]) > 0.f)) g.v[j] = 0.f;
+      }
+    }
+    __nv_bfloat16* row = dz + (size_t)m * 2 * N;
+    if (VEC == 4) {
+      Bf16x4 hi, lo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split1(g.v[j], hi.v[j], lo.v[j]);
+      *reinterpret_cast<Bf16x4*>(row + c) = hi;
+      *reinterpret_cast<Bf16x4*>(row + N + c) = lo;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) split1(g.v[j], row[c + j], row[N + c + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc.v[j] += g.v[j];
+  }
+  st_plain<VEC>(partials + (size_t)blockIdx.y * N + c, acc);
+}
+
+// W fp32 [K,N] -> W2r bf16 [2K,N] = [hi; hi],  W2c bf16 [K,2N] = [hi | hi],  Wlo bf16 [K,N]
+__global__ void tower_prep_weight_kernel(const float* __restrict__ W,
+                                         __nv_bfloat16* __restrict__ W2r,
+                                         __nv_bfloat16* __restrict__ W2c,
+                                         __nv_bfloat16* __restrict__ Wlo, int K, int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)K * N) return;
+  const int k = (int)(i / N);
+  const int n = (int)(i - (int64_t)k * N);
+  __nv_bfloat16 hi, lo;
+  split1(W[i], hi, lo);
+  W2r[i] = hi;
+  W2r[(int64_t)K * N + i] = hi;
+  W2c[(int64_t)k * 2 * N + n] = hi;
+  W2c[(int64_t)k * 2 * N + N + n] = hi;
+  Wlo[i] = lo;
+}
+
+// dW[k,n] = Mx[k,n] + Mx[k,N+n] + Mx[K+k,n]   with Mx = [a_hi|a_lo]^T @ [dz_hi|dz_lo]  ([2K,2N])
+__global__ void tower_fold_dw_kernel(const float* __restrict__ Mx, float* __restrict__ dW, int K,
+                                     int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)K * N) return;
+  const int k = (int)(i / N);
+  const int n = (int)(i - (int64_t)k * N);
+  const size_t r0 = (size_t)k * 2 * N, r1 = (size_t)(K + k) * 2 * N;
+  dW[i] = (Mx[r0 + n] + Mx[r0 + N + n]) + Mx[r1 + n];
+}
+
+constexpr int kTowerRowSlices = 148 * 2;
+static int tower_row_slices(int64_t M) {
+  return (int)min((int64_t)kTowerRowSlices, M > 0 ? M : (int64_t)1);
+}
+
+static int launch_tower_split(const float* x, const float* bias, int relu, void* out, int64_t M,
+                              int K, cudaStream_t st) {
+  B200_REQUIRE(K > 0 && M >= 0, "tower_split: bad sizes");
+  if (M == 0) return B200REC_OK;
+  const bool v4 = (K % 4 == 0) && aligned16(x) && aligned8(out) && (!bias || aligned16(bias));
+  const int64_t total = M * (v4 ? K / 4 : K);
+  const unsigned grid =
+      (unsigned)min((total + kTowerThreads - 1) / kTowerThreads, (int64_t)sm_count() * 16);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (v4)
+    tower_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(x, bias, relu, o, M, K);
+  else
+    tower_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(x, bias, relu, o, M, K);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static int launch_tower_relu_bwd_split(const float* dy, const void* act, void* dz, float* dbias,
+                                       int64_t M, int N, void* ws, size_t ws_bytes,
+                                       cudaStream_t st) {
+  B200_REQUIRE(N > 0 && M >= 0, "tower_relu_bwd_split: bad sizes");
+  const int slices = tower_row_slices(M);
+  const size_t need = (size_t)slices * N * sizeof(float);
+  if (ws_bytes < need) {
+    set_error("tower_relu_bwd_split: workspace %zu < %zu bytes", ws_bytes, need);
+    return B200REC_ERR_WORKSPACE;
+  }
+  if (M == 0) {
+    B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
+    return B200REC_OK;
+  }
+  const bool v4 = (N % 4 == 0) && aligned16(dy) && aligned8(dz) && (!act || aligned8(act)) &&
+                  aligned16(ws);
+  const int chunks = v4 ? N / 4 : N;
+  dim3 grid((chunks + kTowerThreads - 1) / kTowerThreads, slices);
+  float* partials = static_cast<float*>(ws);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(act);
+  __nv_bfloat16* z = static_cast<__nv_bfloat16*>(dz);
+  if (v4)
+    tower_relu_bwd_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(dy, a, z, partials, M, N);
+  else
+    tower_relu_bwd_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(dy, a, z, partials, M, N);
+  B200_LAUNCH_CHECK();
+  reduce_partials_kernel<<<(N + 127) / 128, 128, 0, st>>>(partials, slices, N, dbias, N, nullptr);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+}  // namespace b200rec

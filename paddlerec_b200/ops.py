@@ -42,7 +42,8 @@ LAUNCHES = 0
 KERNELS_PER_CALL = {
     "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
     "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
-    "cross_v2_bwd": 2, "shard_bucketize": 2,
+    "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
+    "tower_prep_weight": 1, "tower_fold_dw": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
 EVENTS = None
@@ -311,6 +312,57 @@ def raw_shard_bucketize(ids: torch.Tensor, world: int, V: int):
           "shard_bucketize")
     _count("shard_bucketize")
     return send_ids[:n], perm[:n], inv_perm[:n], counts
+
+
+def raw_tower_split(x: torch.Tensor, bias, relu: bool) -> torch.Tensor:
+    """fp32 [M,K] -> bf16 [M,2K] = [hi | lo] of relu?(x + bias?)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    M, K = x.shape
+    out = torch.empty(M, 2 * K, dtype=torch.bfloat16, device=x.device)
+    check(lib.b200rec_tower_split(ptr(x), ptr(bias), int(relu), ptr(out), M, K, _stream()),
+          "tower_split")
+    _count("tower_split")
+    return out
+
+
+def raw_tower_relu_bwd_split(dy: torch.Tensor, act):
+    """Returns (dz bf16 [M,2N], dbias [N])."""
+    lib = _lib.load()
+    dy = _req(dy, torch.float32, "dy")
+    M, N = dy.shape
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_tower_bwd_workspace_bytes(M, N, ctypes.byref(nbytes)), "tower_ws")
+    ws = workspace(nbytes.value, dy.device, "tower")
+    dz = torch.empty(M, 2 * N, dtype=torch.bfloat16, device=dy.device)
+    dbias = torch.empty(N, dtype=torch.float32, device=dy.device)
+    check(lib.b200rec_tower_relu_bwd_split(ptr(dy), ptr(act), ptr(dz), ptr(dbias), M, N, ptr(ws),
+                                           ws.numel(), _stream()), "tower_relu_bwd_split")
+    _count("tower_relu_bwd_split")
+    return dz, dbias
+
+
+def raw_tower_prep_weight(W: torch.Tensor):
+    """W fp32 [K,N] -> (W2r bf16 [2K,N], W2c bf16 [K,2N], Wlo bf16 [K,N])."""
+    lib = _lib.load()
+    W = _req(W, torch.float32, "W")
+    K, N = W.shape
+    W2r = torch.empty(2 * K, N, dtype=torch.bfloat16, device=W.device)
+    W2c = torch.empty(K, 2 * N, dtype=torch.bfloat16, device=W.device)
+    Wlo = torch.empty(K, N, dtype=torch.bfloat16, device=W.device)
+    check(lib.b200rec_tower_prep_weight(ptr(W), ptr(W2r), ptr(W2c), ptr(Wlo), K, N, _stream()),
+          "tower_prep_weight")
+    _count("tower_prep_weight")
+    return W2r, W2c, Wlo
+
+
+def raw_tower_fold_dw(Mx: torch.Tensor, K: int, N: int) -> torch.Tensor:
+    lib = _lib.load()
+    Mx = _req(Mx, torch.float32, "Mx")
+    dW = torch.empty(K, N, dtype=torch.float32, device=Mx.device)
+    check(lib.b200rec_tower_fold_dw(ptr(Mx), ptr(dW), K, N, _stream()), "tower_fold_dw")
+    _count("tower_fold_dw")
+    return dW
 
 
 # ------------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ import torch.nn as tnn
 
 from ... import nn as bnn
 from ... import ops
+from ... import tower
 
 
 class DeepFMLayer(tnn.Module):
@@ -94,6 +95,10 @@ class DNN(tnn.Module):
 
     def forward(self, feat_embeddings):
         y_dnn = feat_embeddings.reshape(-1, self.num_field * self.sparse_feature_dim)
+        if bnn.get_matmul_precision() == "bf16x3" and y_dnn.is_cuda:
+            # one autograd node: tensor-core GEMMs + fused bias/ReLU/split epilogues (tower.py)
+            linears = [m for m in self._mlp_layers if isinstance(m, bnn.Linear)]
+            return tower.mlp(y_dnn, [m.weight for m in linears], [m.bias for m in linears])
         for layer in self._mlp_layers:
             y_dnn = layer(y_dnn)
         return y_dnn

@@ -1,0 +1,90 @@
+"""The dense MLP tower (Linear -> ReLU chain of models/rank/deepfm/net.py:142-174, also
+wide_deep/net.py:55-71 and the DIN / DCN-V2 MLPs) as ONE autograd node in 'bf16x3' precision.
+
+Tensor cores are reserved for exactly this part of the path (BASELINE north star).  Each fp32 GEMM
+a@b is evaluated as a_hi@b_hi + a_lo@b_hi + a_hi@b_lo with bf16 operands and fp32 accumulation
+(cuBLASLt via torch.mm(out_dtype=float32)); everything between two GEMMs — bias, ReLU, the hi/lo
+split, the ReLU mask and bias column-sum in backward — is one hand-written streaming kernel per
+layer (csrc/tower.cuh).  Activations are kept ONLY in their split bf16 form (what the backward GEMM
+consumes), never as fp32.
+
+    forward, layer i :  y = [a_hi|a_lo] @ [W_hi;W_hi]  (+)= a_hi @ W_lo         2 GEMMs
+                        a_next = split(relu(y + b))                            1 kernel
+    backward, layer i:  dz = split(dy * mask), db = colsum(dz)                 1 kernel
+                        dW = fold([a_hi|a_lo]^T @ [dz_hi|dz_lo])               1 GEMM + 1 kernel
+                        dx = [dz_hi|dz_lo] @ [W_hi|W_hi]^T (+)= dz_hi @ W_lo^T   2 GEMMs
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+
+
+class _TowerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_layers, last_act, *params):
+        Ws, bs = params[:n_layers], params[n_layers:]
+        a = ops.raw_tower_split(x, None, False)             # [M, 2K0] bf16
+        acts, preps = [a], []
+        y = None
+        for i in range(n_layers):
+            W = Ws[i]
+            K, N = W.shape
+            W2r, W2c, Wlo = ops.raw_tower_prep_weight(W)
+            preps.append((W2c, Wlo))
+            y = torch.mm(a, W2r, out_dtype=F32)
+            torch.addmm(y, a[:, :K], Wlo, out_dtype=F32, out=y)
+            relu = (i < n_layers - 1) or last_act
+            if i < n_layers - 1:
+                a = ops.raw_tower_split(y, bs[i], relu)
+                acts.append(a)
+            else:
+                if relu:
+                    a = ops.raw_tower_split(y, bs[i], True)   # keep the mask source
+                    acts.append(a)
+                    y = torch.relu_(y.add_(bs[i])) if bs[i] is not None else torch.relu_(y)
+                elif bs[i] is not None:
+                    y = y.add_(bs[i])
+        ctx.n_layers, ctx.last_act = n_layers, last_act
+        ctx.acts, ctx.preps = acts, preps
+        ctx.shapes = [tuple(W.shape) for W in Ws]
+        ctx.has_bias = [b is not None for b in bs]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n = ctx.n_layers
+        acts, preps = ctx.acts, ctx.preps
+        dy = dy.contiguous()
+        dWs, dbs = [None] * n, [None] * n
+        for i in range(n - 1, -1, -1):
+            K, N = ctx.shapes[i]
+            masked = (i < n - 1) or ctx.last_act
+            mask_src = acts[i + 1] if masked else None
+            dz, db = ops.raw_tower_relu_bwd_split(dy, mask_src)      # [M, 2N] bf16
+            a = acts[i]                                              # [M, 2K] bf16
+            Mx = torch.mm(a.t(), dz, out_dtype=F32)                  # [2K, 2N]
+            dWs[i] = ops.raw_tower_fold_dw(Mx, K, N)
+            dbs[i] = db if ctx.has_bias[i] else None
+            if i > 0 or ctx.needs_input_grad[0]:
+                W2c, Wlo = preps[i]
+                dx = torch.mm(dz, W2c.t(), out_dtype=F32)            # [M, K]
+                torch.addmm(dx, dz[:, :N], Wlo.t(), out_dtype=F32, out=dx)
+                dy = dx
+        dx0 = dy if ctx.needs_input_grad[0] else None
+        ctx.acts = ctx.preps = None
+        return (dx0, None, None, *dWs, *dbs)
+
+
+def mlp(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+        last_act: bool = False) -> torch.Tensor:
+    """relu(...relu(x@W0+b0)...)@W_last+b_last  (ReLU after the last layer iff last_act)."""
+    lead = x.shape[:-1]
+    y = _TowerFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), len(weights), last_act, *weights,
+                       *biases)
+    return y.reshape(*lead, y.shape[-1])

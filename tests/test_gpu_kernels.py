@@ -271,3 +271,68 @@ def test_shard_bucketize(world):
         off += int(counts[r])
     local = torch.where(valid, ids // world, torch.full_like(ids, -1))
     assert torch.equal(send, local[inv])
+
+
+@pytest.mark.parametrize("K,N", [(624, 400), (351, 7), (400, 1)])
+def test_tower_epilogues(K, N):
+    ops = _ops()
+    M = 333
+    g = torch.Generator().manual_seed(K + N)
+    x = torch.randn(M, K, generator=g)
+    bias = torch.randn(K, generator=g)
+    out = ops.raw_tower_split(x.to(DEV), bias.to(DEV), True).cpu().float()
+    ref = torch.relu(x + bias)
+    hi = ref.to(torch.bfloat16)
+    lo = (ref - hi.float()).to(torch.bfloat16)
+    assert torch.equal(out[:, :K], hi.float()) and torch.equal(out[:, K:], lo.float())
+    assert rel_err(out[:, :K] + out[:, K:], ref) < 2 ** -15
+    out2 = ops.raw_tower_split(x.to(DEV), None, False).cpu().float()
+    assert rel_err(out2[:, :K] + out2[:, K:], x) < 2 ** -15
+    # backward epilogue
+    dy = torch.randn(M, K, generator=g)
+    dz, db = ops.raw_tower_relu_bwd_split(dy.to(DEV), ops.raw_tower_split(x.to(DEV), bias.to(DEV), True))
+    dz = dz.cpu().float()
+    dz_ref = dy * (hi.float() > 0)
+    assert rel_err(dz[:, :K] + dz[:, K:], dz_ref) < 2 ** -15
+    assert rel_err(db.cpu(), dz_ref.double().sum(0)) < 2e-6
+    dz2, db2 = ops.raw_tower_relu_bwd_split(dy.to(DEV), None)
+    assert rel_err(db2.cpu(), dy.double().sum(0)) < 2e-6
+    # weight operand layouts + dW folding
+    W = torch.randn(K, N, generator=g)
+    W2r, W2c, Wlo = (t.cpu().float() for t in ops.raw_tower_prep_weight(W.to(DEV)))
+    whi = W.to(torch.bfloat16).float()
+    assert torch.equal(W2r[:K], whi) and torch.equal(W2r[K:], whi)
+    assert torch.equal(W2c[:, :N], whi) and torch.equal(W2c[:, N:], whi)
+    assert torch.equal(Wlo, (W - whi).to(torch.bfloat16).float())
+    Mx = torch.randn(2 * K, 2 * N, generator=g)
+    dW = ops.raw_tower_fold_dw(Mx.to(DEV), K, N).cpu()
+    assert rel_err(dW, Mx[:K, :N] + Mx[:K, N:] + Mx[K:, :N]) < 1e-6
+
+
+@pytest.mark.parametrize("last_act", [False, True])
+def test_tower_mlp_matches_fp64(last_act):
+    from paddlerec_b200 import tower
+    g = torch.Generator().manual_seed(11)
+    M, sizes = 257, [624, 400, 400, 1]
+    x = torch.randn(M, sizes[0], generator=g)
+    Ws = [torch.randn(sizes[i], sizes[i + 1], generator=g) / sizes[i] ** 0.5 for i in range(3)]
+    bs = [torch.randn(sizes[i + 1], generator=g) * 0.1 for i in range(3)]
+    xd = x.double().requires_grad_(True)
+    Wd = [w.double().requires_grad_(True) for w in Ws]
+    bd = [b.double().requires_grad_(True) for b in bs]
+    h = xd
+    for i in range(3):
+        h = h @ Wd[i] + bd[i]
+        if i < 2 or last_act:
+            h = torch.relu(h)
+    gy = torch.randn(M, 1, generator=g)
+    (h * gy.double()).sum().backward()
+    xc = x.to(DEV).requires_grad_(True)
+    Wc = [w.to(DEV).requires_grad_(True) for w in Ws]
+    bc = [b.to(DEV).requires_grad_(True) for b in bs]
+    y = tower.mlp(xc, Wc, bc, last_act=last_act)
+    (y * gy.to(DEV)).sum().backward()
+    assert rel_err(y, h) < 1e-4
+    assert rel_err(xc.grad, xd.grad) < 1e-4
+    for a, b in zip(Wc + bc, Wd + bd):
+        assert rel_err(a.grad, b.grad) < 1e-4
