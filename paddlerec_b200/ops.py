@@ -448,6 +448,10 @@ class _CrossV2(torch.autograd.Function):
         return dx0, dxl, dW, dbias, None
 
 
+# K4 (DIN attention pooling) is wired in by din_attention_fwd once the kernel is in the library.
+HAVE_DIN_ATTN = False
+
+
 def embed_fm(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink):
     return _EmbedFM.apply(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink)
 

@@ -71,3 +71,94 @@ def test_deepfm_golden(name, precision, as_list):
         check(g, pred, loss, grads_of(layer))
     finally:
         bnn.set_matmul_precision("fp32")
+
+
+def _criteo_inputs(g):
+    ids = torch.tensor(g["in"]["ids"], device="cuda")
+    dense = torch.tensor(g["in"]["dense"], dtype=torch.float32, device="cuda")
+    label = torch.tensor(g["in"]["label"], dtype=torch.float32, device="cuda")
+    return ids, dense, label
+
+
+@pytest.mark.parametrize("name,mix,stacked", [("dcn_v2_v2_stacked", False, True),
+                                              ("dcn_v2_mix_parallel", True, False)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_dcn_v2_golden(name, mix, stacked, precision):
+    from paddlerec_b200 import functional as BF
+    from paddlerec_b200 import nn as bnn
+    from paddlerec_b200.rank.dcn_v2 import net
+    g = load_golden(name)
+    V, D = g["param"]["embedding.weight"].shape
+    fc = [g["param"]["DNN_.linear_%d.weight" % i].shape[1] for i in range(2)]
+    bnn.set_matmul_precision(precision)
+    try:
+        layer = net.DCN_V2Layer(V, D, 13, 26, fc, 2, stacked, mix, 6, 4)
+        load_state(layer, g)
+        layer.eval()      # parity is defined without dropout
+        ids, dense, label = _criteo_inputs(g)
+        pred = layer([ids[:, i:i + 1] for i in range(26)], dense)
+        loss = BF.log_loss(pred, label).mean()
+        loss.backward()
+        check(g, pred, loss, grads_of(layer))
+    finally:
+        bnn.set_matmul_precision("fp32")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_wide_deep_golden(precision):
+    from paddlerec_b200 import functional as BF
+    from paddlerec_b200 import nn as bnn
+    from paddlerec_b200.rank.wide_deep import net
+    g = load_golden("wide_deep")
+    V, D = g["param"]["embedding.weight"].shape
+    fc = [g["param"]["linear_%d.weight" % i].shape[1] for i in range(2)]
+    bnn.set_matmul_precision(precision)
+    try:
+        layer = load_state(net.WideDeepLayer(V, D, 13, 26, fc), g)
+        ids, dense, label = _criteo_inputs(g)
+        pred = layer([ids[:, i:i + 1] for i in range(26)], dense)
+        loss = BF.log_loss(pred, label).mean()
+        loss.backward()
+        check(g, pred, loss, grads_of(layer))
+        # id 0 is a real row here (no padding_idx): it must receive gradient
+        assert np.abs(grads_of(layer)["embedding.weight"][0]).max() > 0
+    finally:
+        bnn.set_matmul_precision("fp32")
+
+
+@pytest.mark.parametrize("tiled", [True, False])
+def test_din_golden(tiled):
+    import torch.nn.functional as F
+
+    from paddlerec_b200.rank.din import net
+    g = load_golden("din")
+    item_count, e2 = g["param"]["hist_item_emb_attr.weight"].shape
+    cat_count = g["param"]["hist_cat_emb_attr.weight"].shape[0]
+    layer = net.DINLayer(e2, e2, "sigmoid", False, False, item_count, cat_count,
+                         faithful_frozen_attention=False, tiled_target_seq=tiled)
+    remap = {k: k.replace("att.", "attention.") for k in g["param"]}
+    g2 = dict(g)
+    g2["param"] = {remap[k]: v for k, v in g["param"].items()}
+    g2["grad"] = {remap[k]: v for k, v in g["grad"].items()}
+    load_state(layer, g2)
+    i = g["in"]
+    dev = "cuda"
+    L = i["hist_item"].shape[1]
+    ti = torch.tensor(i["target_item"], device=dev)
+    tc = torch.tensor(i["target_cat"], device=dev)
+    label = torch.tensor(i["label"], dtype=torch.float32, device=dev)
+    logit = layer(torch.tensor(i["hist_item"], device=dev), torch.tensor(i["hist_cat"], device=dev),
+                  ti, tc, label, torch.tensor(i["mask"], device=dev),
+                  ti.unsqueeze(1).repeat(1, L), tc.unsqueeze(1).repeat(1, L))
+    loss = F.binary_cross_entropy_with_logits(logit, label)
+    loss.backward()
+    check(g2, logit, loss, grads_of(layer))
+
+
+def test_din_faithful_frozen_attention_default():
+    """by default the attention-unit linears are NOT trainable (the reference loses
+    them from parameters() through a sub-layer name collision)."""
+    from paddlerec_b200.rank.din import net
+    layer = net.DINLayer(8, 8, "sigmoid", False, False, 50, 11)
+    assert all(not p.requires_grad for p in layer.attention.parameters())
+    assert layer.linear_0.weight.requires_grad
