@@ -67,45 +67,84 @@ tower_split_kernel(const float* __restrict__ x, const float* __restrict__ bias, 
 // dz = dy * (act_hi > 0) (mask skipped if act == nullptr); dz_out = [hi | lo]; partial column sums
 // of dz per row-slice (thread owns its columns => register accumulation, fixed order).
 template <int VEC>
+__device__ __forceinline__ void relu_bwd_split_row(Vec<VEC>& g, const __nv_bfloat16* a,
+                                                   __nv_bfloat16* row, int N, int c) {
+  if (a != nullptr) {
+    if (VEC == 4) {
+      const Bf16x4 h = *reinterpret_cast<const Bf16x4*>(a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!(__bfloat162float(h.v[j]) > 0.f)) g.v[j] = 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (!(__bfloat162float(a[j]) > 0.f)) g.v[j] = 0.f;
+    }
+  }
+  if (VEC == 4) {
+    Bf16x4 hi, lo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split1(g.v[j], hi.v[j], lo.v[j]);
+    *reinterpret_cast<Bf16x4*>(row + c) = hi;
+    *reinterpret_cast<Bf16x4*>(row + N + c) = lo;
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) split1(g.v[j], row[c + j], row[N + c + j]);
+  }
+}
+
+// blockDim = (TX column chunks, TY rows); a thread owns its columns and walks rows
+// blockIdx.y*TY + ty, stepping gridDim.y*TY, four rows in flight.
+constexpr int kBwdUnroll = 4;
+
+template <int VEC>
 __global__ void __launch_bounds__(kTowerThreads)
 tower_relu_bwd_split_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ act,
                             __nv_bfloat16* __restrict__ dz, float* __restrict__ partials,
                             int64_t M, int N) {
   const int chunks = N / VEC;
-  const int chunk = blockIdx.x * kTowerThreads + threadIdx.x;
-  if (chunk >= chunks) return;
+  const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = chunk * VEC;
+  const bool col_ok = chunk < chunks;
+  const int64_t row_step = (int64_t)gridDim.y * blockDim.y;
   Vec<VEC> acc = vzero<VEC>();
-  for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
-    Vec<VEC> g = ld_row<VEC>(dy + (size_t)m * N + c);
-    if (act != nullptr) {
-      const __nv_bfloat16* a = act + (size_t)m * 2 * N + c;
-      if (VEC == 4) {
-        const Bf16x4 h = *reinterpret_cast<const Bf16x4*>(a);
+  if (col_ok) {
+    int64_t m = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; m + (kBwdUnroll - 1) * row_step < M; m += kBwdUnroll * row_step) {
+      Vec<VEC> g[kBwdUnroll];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (!(__bfloat162float(h.v[j]) > 0.f)) g.v[j] = 0.f;
-      } else {
+      for (int u = 0; u < kBwdUnroll; ++u)
+        g[u] = ld_row<VEC>(dy + (size_t)(m + u * row_step) * N + c);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
-          if (!(__bfloat162float(a[j]) > 0.f)) g.v[j] = 0.f;
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const int64_t mm = m + u * row_step;
+        relu_bwd_split_row<VEC>(g[u], act ? act + (size_t)mm * 2 * N + c : nullptr,
+                                dz + (size_t)mm * 2 * N, N, c);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc.v[j] += g[u].v[j];
       }
     }
-    __nv_bfloat16* row = dz + (size_t)m * 2 * N;
-    if (VEC == 4) {
-      Bf16x4 hi, lo;
+    for (; m < M; m += row_step) {
+      Vec<VEC> g = ld_row<VEC>(dy + (size_t)m * N + c);
+      relu_bwd_split_row<VEC>(g, act ? act + (size_t)m * 2 * N + c : nullptr,
+                              dz + (size_t)m * 2 * N, N, c);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split1(g.v[j], hi.v[j], lo.v[j]);
-      *reinterpret_cast<Bf16x4*>(row + c) = hi;
-      *reinterpret_cast<Bf16x4*>(row + N + c) = lo;
-    } else {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) split1(g.v[j], row[c + j], row[N + c + j]);
+      for (int j = 0; j < VEC; ++j) acc.v[j] += g.v[j];
     }
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) acc.v[j] += g.v[j];
   }
-  st_plain<VEC>(partials + (size_t)blockIdx.y * N + c, acc);
+  // reduce the TY row-threads of the block in shared memory (fixed order), one partial per block
+  __shared__ float s_part[kTowerThreads * 4];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j)
+    s_part[(threadIdx.y * blockDim.x + threadIdx.x) * VEC + j] = acc.v[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && col_ok) {
+    Vec<VEC> t = vzero<VEC>();
+    for (int y = 0; y < (int)blockDim.y; ++y)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) t.v[j] += s_part[(y * blockDim.x + threadIdx.x) * VEC + j];
+    st_plain<VEC>(partials + (size_t)blockIdx.y * N + c, t);
+  }
 }
 
 // W fp32 [K,N] -> W2r bf16 [2K,N] = [hi; hi],  W2c bf16 [K,2N] = [hi | hi],  Wlo bf16 [K,N]
@@ -137,7 +176,7 @@ __global__ void tower_fold_dw_kernel(const float* __restrict__ Mx, float* __rest
   dW[i] = (Mx[r0 + n] + Mx[r0 + N + n]) + Mx[r1 + n];
 }
 
-constexpr int kTowerRowSlices = 148 * 2;
+constexpr int kTowerRowSlices = 148 * 4;
 static int tower_row_slices(int64_t M) {
   return (int)min((int64_t)kTowerRowSlices, M > 0 ? M : (int64_t)1);
 }
@@ -176,14 +215,19 @@ static int launch_tower_relu_bwd_split(const float* dy, const void* act, void* d
   const bool v4 = (N % 4 == 0) && aligned16(dy) && aligned8(dz) && (!act || aligned8(act)) &&
                   aligned16(ws);
   const int chunks = v4 ? N / 4 : N;
-  dim3 grid((chunks + kTowerThreads - 1) / kTowerThreads, slices);
+  // TX = column chunks per block (power of two <= 256), TY = rows per block
+  int tx = 32;
+  while (tx < chunks && tx < kTowerThreads) tx <<= 1;
+  const int ty = kTowerThreads / tx;
+  dim3 block(tx, ty);
+  dim3 grid((chunks + tx - 1) / tx, slices);
   float* partials = static_cast<float*>(ws);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(act);
   __nv_bfloat16* z = static_cast<__nv_bfloat16*>(dz);
   if (v4)
-    tower_relu_bwd_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(dy, a, z, partials, M, N);
+    tower_relu_bwd_split_kernel<4><<<grid, block, 0, st>>>(dy, a, z, partials, M, N);
   else
-    tower_relu_bwd_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(dy, a, z, partials, M, N);
+    tower_relu_bwd_split_kernel<1><<<grid, block, 0, st>>>(dy, a, z, partials, M, N);
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<(N + 127) / 128, 128, 0, st>>>(partials, slices, N, dbias, N, nullptr);
   B200_LAUNCH_CHECK();

@@ -42,8 +42,8 @@ def check(g, pred, loss, grads, tol=TOL):
     assert abs(float(loss) - float(g["out"]["loss"])) < tol * max(1.0, abs(float(g["out"]["loss"])))
     for k, ref in g["grad"].items():
         assert k in grads, k
-        if np.abs(ref).max() == 0:
-            assert np.abs(grads[k]).max() == 0, k
+        if np.abs(ref).max() < 1e-10:   # mathematically zero (e.g. softmax shift invariance)
+            assert np.abs(grads[k]).max() < 1e-7, k
         else:
             assert rel_err(grads[k], ref) < tol, (k, rel_err(grads[k], ref))
 

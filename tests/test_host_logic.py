@@ -1,0 +1,107 @@
+"""Host-side logic that needs no GPU: yaml flattening / overrides (utils_single.py:57-86,
+trainer.py:55-65), the Criteo and DIN readers, AUC, LR schedule, the oracle's optimizer rules."""
+import os
+
+import numpy as np
+import torch
+
+from paddlerec_b200 import functional as BF
+from paddlerec_b200 import optim, runner
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "paddlerec_b200")
+
+
+def test_yaml_flatten_and_overrides():
+    cfg = runner.load_yaml(os.path.join(PKG, "rank", "deepfm", "config.yaml"))
+    assert cfg["runner.train_batch_size"] == 2 and cfg["runner.epochs"] == 3
+    assert cfg["hyper_parameters.sparse_feature_number"] == 1000001
+    assert cfg["hyper_parameters.sparse_feature_dim"] == 9
+    assert cfg["hyper_parameters.optimizer.learning_rate"] == 0.001
+    assert cfg["hyper_parameters.fc_sizes"] == [512, 256, 128, 32]
+    runner.apply_overrides(cfg, ["runner.train_batch_size=8", "runner.use_gpu=False",
+                                 "hyper_parameters.optimizer.learning_rate=0.01",
+                                 "hyper_parameters.fc_sizes=[8,4]", "runner.model_save_path=xx"])
+    assert cfg["runner.train_batch_size"] == 8 and cfg["runner.use_gpu"] is False
+    assert cfg["hyper_parameters.optimizer.learning_rate"] == 0.01
+    assert cfg["hyper_parameters.fc_sizes"] == [8, 4] and cfg["runner.model_save_path"] == "xx"
+
+
+def test_named_list_flattening():
+    flat = runner.flatten_yaml({"runner": [{"name": "a", "x": 1}], "hyper_parameters": {"y": {"z": 2}}})
+    assert flat == {"runner.a.name": "a", "runner.a.x": 1, "hyper_parameters.y.z": 2}
+
+
+def test_criteo_reader_contract():
+    from paddlerec_b200.rank.deepfm import criteo_reader
+    d = os.path.join(PKG, "rank", "deepfm", "data", "sample_data", "train")
+    ds = criteo_reader.RecDataset([os.path.join(d, f) for f in os.listdir(d)], config={})
+    samples = list(ds)
+    assert len(samples) == 80
+    s = samples[0]
+    assert len(s) == 28 and all(a.dtype == np.int64 and a.shape == (1,) for a in s[:27])
+    assert s[27].dtype == np.float32 and s[27].shape == (13,)
+    assert any((np.concatenate(x[1:27]) == 0).any() for x in samples)   # padding id present
+    # missing slot -> padding id 0
+    out = ds.parse_line("click:1 dense_feature:0.5 3:77")
+    assert out[0][0] == 1 and out[3][0] == 77 and out[1][0] == 0 and out[27].shape == (1,)
+    loader_cfg = {"runner.train_data_dir": "data/sample_data/train", "runner.train_batch_size": 2,
+                  "runner.train_reader_path": "criteo_reader",
+                  "config_abs_dir": os.path.join(PKG, "rank", "deepfm")}
+    batch = next(iter(runner.create_data_loader(loader_cfg)))
+    assert len(batch) == 28 and batch[1].shape == (2, 1) and batch[27].shape == (2, 13)
+
+
+def test_din_reader_contract(tmp_path):
+    from paddlerec_b200.rank.din import reader
+    p = tmp_path / "d.txt"
+    p.write_text("1 2 3;4 5 6;7;8;1\n9;10;11;12;0\n3 4;5 6;7;8;1\n1 1 1 1;2 2 2 2;5;6;0\n")
+    ds = reader.RecDataset([str(p)], {"runner.train_batch_size": 2})
+    out = list(ds)
+    assert len(out) == 4
+    lens = [int((s[5] == 0).sum()) for s in out]
+    assert lens == sorted(lens)                                  # sorted by history length
+    s = out[1]
+    L = s[0].shape[0]
+    assert s[5].shape == (L, 1) and s[5].dtype == np.int64
+    assert (s[6] == s[2]).all() and s[6].shape == (L,)           # target id tiled L times
+    first = out[0]
+    assert first[0].tolist() == [9, 0] and first[5].reshape(-1).tolist() == [0, int(-1e9)]
+
+
+def test_auc_matches_sklearn():
+    from sklearn.metrics import roc_auc_score
+    g = torch.Generator().manual_seed(0)
+    y = (torch.rand(5000, generator=g) < 0.3).long()
+    p = (torch.rand(5000, generator=g) * 0.6 + 0.3 * y).clamp(0, 1)
+    m = BF.Auc()
+    m.update(torch.stack([1 - p, p], 1)[:2500], y[:2500].reshape(-1, 1))
+    m.update(p[2500:].reshape(-1, 1), y[2500:])
+    assert abs(m.accumulate() - roc_auc_score(y.numpy(), p.numpy())) < 2e-3   # 4095 buckets
+    assert BF.Auc().accumulate() == 0.0
+
+
+def test_piecewise_decay():
+    lr = optim.PiecewiseDecay([3], [0.85, 0.2])
+    vals = []
+    for _ in range(5):
+        vals.append(lr())
+        lr.step()
+    assert vals == [0.85, 0.85, 0.85, 0.2, 0.2]
+
+
+def test_oracle_optimizer_rules_against_torch():
+    from oracle import optim as oo
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn(20, 4, generator=g, dtype=torch.float64)
+    grad = torch.randn(20, 4, generator=g, dtype=torch.float64)
+    p = W.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=1e-2)
+    Wr, m, v = W.numpy(), np.zeros((20, 4)), np.zeros((20, 4))
+    for t in (1, 2, 3):
+        p.grad = grad.clone()
+        opt.step()
+        Wr, m, v = oo.adam_lazy(Wr, m, v, np.arange(20), grad.numpy(), 1e-2, 0.9, 0.999, 1e-8, t)
+    np.testing.assert_allclose(Wr, p.detach().numpy(), rtol=1e-10, atol=1e-12)
+    ids = np.array([3, 5, 3, 0, 5, 5])
+    u, merged = oo.merge_rows(ids, np.ones((6, 2)), padding_idx=0)
+    assert u.tolist() == [3, 5] and merged[:, 0].tolist() == [2.0, 3.0]
