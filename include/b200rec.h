@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200REC_ABI_VERSION 1
+#define B200REC_ABI_VERSION 2
 
 #define B200REC_OK 0
 #define B200REC_ERR_INVALID (-1)   /* bad argument (shape, alignment, NULL) */
@@ -63,11 +63,17 @@ int b200rec_oob_count(uint64_t* count_host, int reset, void* stream);
  *   y1[b] = sum_f W1[ids[b,f]] + sum_j dense[b,j]*dense_w1[j]
  *   S[b,:] = sum_n feat[b,n,:] ;  y2[b] = 0.5 * sum_d ( S[b,d]^2 - sum_n feat[b,n,d]^2 )
  * feat:[B,F+Dn,D]  y1,y2:[B]  S:[B,D] (saved for backward; may be NULL).
- * padding_idx < 0 means "no padding row".  D must be <=128 (D%4==0), <=64 (D%2==0) or <=32. */
-int b200rec_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids, const float* dense,
-                         const float* dense_w, const float* dense_w1, float* feat, float* y1,
-                         float* y2, float* S, int64_t B, int F, int Dn, int D, int64_t V,
-                         int64_t padding_idx, void* stream);
+ * padding_idx < 0 means "no padding row".  D must be <=128 (D%4==0), <=64 (D%2==0) or <=32.
+ * Row strides (in floats): row i of the second-order table starts at W + i*ldw, its first-order
+ * weight is W1[i*ldw1].  Two separate tables: ldw=D, ldw1=1.  The B200-native FUSED layout keeps
+ * both in one 128-byte slot [D emb | w1 | pad] (ldw = ldw1 = 32, W1 = W + D): a random 64-byte
+ * row and a random 4-byte scalar each cost a full 128-byte DRAM access on this part
+ * (profiles/r1_gather_variants_microbench.txt), so the slot halves the random traffic. */
+int b200rec_embed_fm_fwd(const float* W, int64_t ldw, const float* W1, int64_t ldw1,
+                         const int64_t* ids, const float* dense, const float* dense_w,
+                         const float* dense_w1, float* feat, float* y1, float* y2, float* S,
+                         int64_t B, int F, int Dn, int D, int64_t V, int64_t padding_idx,
+                         void* stream);
 
 /* ---- grouping of ids (sort + run-length) shared by every backward -------- */
 /* Stable-sorts the n ids, dropping padding / out-of-range ones, and produces
@@ -87,20 +93,24 @@ int b200rec_group_ids(const int64_t* ids, int64_t n, int64_t V, int64_t padding_
  *   dW_rows[u,:] = sum_{p in segment u} dfeat[p]        dW1_rows[u] = sum_{p in seg u} gy1[b(p)]
  *   ddense_w[j,:] = sum_b dense[b,j]*dfeat[b,F+j,:]     ddense_w1[j] = sum_b gy1[b]*dense[b,j]
  * dW_rows:[n,D], dW1_rows:[n] with n=B*F; only the first num_unique[0] rows are written
- * (a SelectedRows{rows=unique_ids, value=dW_rows} in Paddle terms).  Deterministic. */
+ * (a SelectedRows{rows=unique_ids, value=dW_rows} in Paddle terms).  Deterministic.
+ * Output strides: dW_rows[u*ld_dw + d], dW1_rows[u*ld_dw1]; separate buffers: ld_dw=D, ld_dw1=1,
+ * dw1_zero_pad=0.  Fused gradient rows [D | g1 | 0-pad]: dW1_rows = dW_rows + D, ld_dw = ld_dw1 =
+ * D+1+pad, dw1_zero_pad = pad (those floats are written as zeros). */
 int b200rec_embed_fm_bwd_workspace_bytes(int64_t B, int F, int Dn, int D, size_t* bytes_host);
 int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_dnn,
                          const float* gy1, const float* gy2, const float* dense,
                          const int32_t* seg_offsets, const int32_t* sorted_pos,
-                         const int32_t* num_unique, float* dW_rows, float* dW1_rows,
-                         float* ddense_w, float* ddense_w1, int64_t B, int F, int Dn, int D,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         const int32_t* num_unique, float* dW_rows, int64_t ld_dw,
+                         float* dW1_rows, int64_t ld_dw1, int dw1_zero_pad, float* ddense_w,
+                         float* ddense_w1, int64_t B, int F, int Dn, int D, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- plain gather / segmented scatter-add (W&D, DCN-V2, DIN lookups) ------ */
 /* out[i,:] = W[ids[i],:]  (zeros if ids[i]==padding_idx).  Replaces paddle.nn.Embedding
  * forward (lookup_table_v2), e.g. models/rank/wide_deep/net.py:90, dcn_v2/net.py:95. */
-int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D, int64_t V,
-                   int64_t padding_idx, void* stream);
+int b200rec_gather(const float* W, int64_t ldw, const int64_t* ids, float* out, int64_t n, int D,
+                   int64_t V, int64_t padding_idx, void* stream);
 /* rows[u,:] = sum_{p in segment u} dOut[p,:]  — the SelectedRows merge of
  * lookup_table_v2_grad.  Deterministic (fixed order inside a segment); ids occurring more than
  * 64 times are reduced by a whole CTA each (skew-proof). */
@@ -110,26 +120,30 @@ int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                            int64_t n, int D, void* workspace, size_t workspace_bytes,
                            void* stream);
 /* dW[unique_ids[u],:] += rows[u,:] into a dense [V,D] gradient (small tables / tests). */
-int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const int32_t* num_unique,
-                          float* dW, int64_t n, int D, int64_t V, void* stream);
+int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, int64_t ld_rows,
+                          const int32_t* num_unique, float* dW, int64_t ld_dw, int64_t n, int D,
+                          int64_t V, void* stream);
 
 /* ---- row-wise ("lazy") optimizers applied to the touched rows only -------- */
+/* W (and m, v) rows start at i*ldw, gradient rows at u*ld_rows; D columns are updated. */
 /* W[id] -= lr * g */
-int b200rec_sparse_sgd(float* W, const int64_t* unique_ids, const float* rows,
-                       const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
-                       void* stream);
+int b200rec_sparse_sgd(float* W, int64_t ldw, const int64_t* unique_ids, const float* rows,
+                       int64_t ld_rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
+                       double lr, void* stream);
 /* Adam(lazy_mode=True): m=b1*m+(1-b1)g; v=b2*v+(1-b2)g^2;
  * W -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps*sqrt(1-b2^t)); bias terms from the host.
  * Hyper-parameters are doubles: derived constants (1-b1, 1-b2, lr_t) are formed in double on the
  * host and only then rounded to fp32 (1-0.999f would be off by 5e-5 relative). */
-int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
-                        const float* rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
+int b200rec_sparse_adam(float* W, float* m, float* v, int64_t ldw, const int64_t* unique_ids,
+                        const float* rows, int64_t ld_rows, const int32_t* num_unique, int64_t n,
+                        int D, int64_t V,
                         double lr, double beta1, double beta2, double eps, double beta1_pow_t,
                         double beta2_pow_t, void* stream);
 /* SparseAdaGradSGDRule: one g2sum scalar per row.
  *   W -= lr * g * sqrt(g0/(g0+g2sum)); clamp to [lo,hi]; g2sum += mean_d(g^2). */
-int b200rec_sparse_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
-                           const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
+int b200rec_sparse_adagrad(float* W, float* g2sum, int64_t ldw, const int64_t* unique_ids,
+                           const float* rows, int64_t ld_rows, const int32_t* num_unique, int64_t n,
+                           int D, int64_t V, double lr,
                            double initial_g2sum, double lo, double hi, void* stream);
 
 /* ---- K3: CrossNet fused epilogues (GEMM itself is a library GEMM) --------- */

@@ -64,28 +64,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+ABI_VERSION = 2
 _P = c_void_p
 _SIG = {
     "b200rec_abi_version": (c_int, []),
     "b200rec_last_error": (c_char_p, []),
     "b200rec_oob_count": (c_int, [POINTER(c_uint64), c_int, _P]),
-    "b200rec_embed_fm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
-                                     c_int, c_int64, c_int64, _P]),
+    "b200rec_embed_fm_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P,
+                                     c_int64, c_int, c_int, c_int, c_int64, c_int64, _P]),
     "b200rec_group_ids_workspace_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
     "b200rec_group_ids": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200rec_embed_fm_bwd_workspace_bytes": (c_int, [c_int64, c_int, c_int, c_int,
                                                      POINTER(c_size_t)]),
-    "b200rec_embed_fm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
-                                     c_int, c_int, c_int, _P, c_size_t, _P]),
-    "b200rec_gather": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int64, _P]),
+    "b200rec_embed_fm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64,
+                                     c_int, _P, _P, c_int64, c_int, c_int, c_int, _P, c_size_t,
+                                     _P]),
+    "b200rec_gather": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int64, c_int64, _P]),
     "b200rec_segment_reduce_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_segment_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
-    "b200rec_rows_to_dense": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, _P]),
-    "b200rec_sparse_sgd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, c_double, _P]),
-    "b200rec_sparse_adam": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_double,
-                                    c_double, c_double, c_double, c_double, c_double, _P]),
-    "b200rec_sparse_adagrad": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_double,
-                                       c_double, c_double, c_double, _P]),
+    "b200rec_rows_to_dense": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int64,
+                                      _P]),
+    "b200rec_sparse_sgd": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int, c_int64,
+                                   c_double, _P]),
+    "b200rec_sparse_adam": (c_int, [_P, _P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int,
+                                    c_int64, c_double, c_double, c_double, c_double, c_double,
+                                    c_double, _P]),
+    "b200rec_sparse_adagrad": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int,
+                                       c_int64, c_double, c_double, c_double, c_double, _P]),
     "b200rec_cross_v2_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "b200rec_cross_bwd_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_cross_v2_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
@@ -131,8 +136,8 @@ def load() -> ctypes.CDLL:
         fn.restype = res
         fn.argtypes = args
     got = lib.b200rec_abi_version()
-    if got != 1:
-        raise B200RecError("libb200rec ABI version %d, expected 1" % got)
+    if got != ABI_VERSION:
+        raise B200RecError("libb200rec ABI version %d, expected %d" % (got, ABI_VERSION))
     _lib = lib
     return lib
 

@@ -63,10 +63,11 @@ int b200rec_oob_count(uint64_t* count_host, int reset, void* stream) {
   return B200REC_OK;
 }
 
-int b200rec_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids, const float* dense,
-                         const float* dense_w, const float* dense_w1, float* feat, float* y1,
-                         float* y2, float* S, int64_t B, int F, int Dn, int D, int64_t V,
-                         int64_t padding_idx, void* stream) {
+int b200rec_embed_fm_fwd(const float* W, int64_t ldw, const float* W1, int64_t ldw1,
+                         const int64_t* ids, const float* dense, const float* dense_w,
+                         const float* dense_w1, float* feat, float* y1, float* y2, float* S,
+                         int64_t B, int F, int Dn, int D, int64_t V, int64_t padding_idx,
+                         void* stream) {
   B200_REQUIRE(B >= 0 && F >= 0 && Dn >= 0 && D > 0 && V > 0, "embed_fm_fwd: bad sizes");
   if (B > 0) {
     NOT_NULL(W); NOT_NULL(W1); NOT_NULL(feat); NOT_NULL(y1); NOT_NULL(y2);
@@ -74,7 +75,7 @@ int b200rec_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids, co
     if (Dn > 0) { NOT_NULL(dense); NOT_NULL(dense_w); NOT_NULL(dense_w1); }
   }
   return launch_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, feat, y1, y2, S, B, F, Dn, D, V,
-                             padding_idx, ST(stream));
+                             padding_idx, ldw, ldw1, ST(stream));
 }
 
 int b200rec_group_ids_workspace_bytes(int64_t n, int64_t V, size_t* bytes_host) {
@@ -105,9 +106,10 @@ int b200rec_embed_fm_bwd_workspace_bytes(int64_t B, int F, int Dn, int D, size_t
 int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_dnn,
                          const float* gy1, const float* gy2, const float* dense,
                          const int32_t* seg_offsets, const int32_t* sorted_pos,
-                         const int32_t* num_unique, float* dW_rows, float* dW1_rows,
-                         float* ddense_w, float* ddense_w1, int64_t B, int F, int Dn, int D,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         const int32_t* num_unique, float* dW_rows, int64_t ld_dw,
+                         float* dW1_rows, int64_t ld_dw1, int dw1_zero_pad, float* ddense_w,
+                         float* ddense_w1, int64_t B, int F, int Dn, int D, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   B200_REQUIRE(B >= 0 && F >= 0 && Dn >= 0 && D > 0, "embed_fm_bwd: bad sizes");
   if (B > 0) {
     NOT_NULL(feat); NOT_NULL(S); NOT_NULL(gy1); NOT_NULL(gy2);
@@ -119,15 +121,16 @@ int b200rec_embed_fm_bwd(const float* feat, const float* S, const float* dfeat_d
     NOT_NULL(workspace);
   }
   return launch_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_pos,
-                             num_unique, dW_rows, dW1_rows, ddense_w, ddense_w1, B, F, Dn, D,
-                             workspace, workspace_bytes, ST(stream));
+                             num_unique, dW_rows, dW1_rows, SegOut{ld_dw, ld_dw1, dw1_zero_pad},
+                             ddense_w, ddense_w1, B, F, Dn, D, workspace, workspace_bytes,
+                             ST(stream));
 }
 
-int b200rec_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D, int64_t V,
-                   int64_t padding_idx, void* stream) {
+int b200rec_gather(const float* W, int64_t ldw, const int64_t* ids, float* out, int64_t n, int D,
+                   int64_t V, int64_t padding_idx, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "gather: bad sizes");
   if (n > 0) { NOT_NULL(W); NOT_NULL(ids); NOT_NULL(out); }
-  return launch_gather(W, ids, out, n, D, V, padding_idx, ST(stream));
+  return launch_gather(W, ids, out, n, D, V, padding_idx, ldw, ST(stream));
 }
 
 int b200rec_segment_reduce_workspace_bytes(int64_t n, int D, size_t* bytes_host) {
@@ -147,27 +150,29 @@ int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
                                workspace_bytes, ST(stream));
 }
 
-int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, const int32_t* num_unique,
-                          float* dW, int64_t n, int D, int64_t V, void* stream) {
+int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, int64_t ld_rows,
+                          const int32_t* num_unique, float* dW, int64_t ld_dw, int64_t n, int D,
+                          int64_t V, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "rows_to_dense: bad sizes");
   if (n > 0) { NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); NOT_NULL(dW); }
   RowsToDenseOp op{dW};
-  return launch_row_update("rows_to_dense", unique_ids, rows, num_unique, n, D, V, op, dW, nullptr,
-                           nullptr, ST(stream));
+  return launch_row_update("rows_to_dense", unique_ids, rows, num_unique, n, D, V, ld_dw, ld_rows,
+                           op, dW, nullptr, nullptr, ST(stream));
 }
 
-int b200rec_sparse_sgd(float* W, const int64_t* unique_ids, const float* rows,
-                       const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
-                       void* stream) {
+int b200rec_sparse_sgd(float* W, int64_t ldw, const int64_t* unique_ids, const float* rows,
+                       int64_t ld_rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
+                       double lr, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_sgd: bad sizes");
   if (n > 0) { NOT_NULL(W); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
   SgdOp op{W, (float)lr};
-  return launch_row_update("sparse_sgd", unique_ids, rows, num_unique, n, D, V, op, W, nullptr,
-                           nullptr, ST(stream));
+  return launch_row_update("sparse_sgd", unique_ids, rows, num_unique, n, D, V, ldw, ld_rows, op,
+                           W, nullptr, nullptr, ST(stream));
 }
 
-int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
-                        const float* rows, const int32_t* num_unique, int64_t n, int D, int64_t V,
+int b200rec_sparse_adam(float* W, float* m, float* v, int64_t ldw, const int64_t* unique_ids,
+                        const float* rows, int64_t ld_rows, const int32_t* num_unique, int64_t n,
+                        int D, int64_t V,
                         double lr, double beta1, double beta2, double eps, double beta1_pow_t,
                         double beta2_pow_t, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_adam: bad sizes");
@@ -175,16 +180,17 @@ int b200rec_sparse_adam(float* W, float* m, float* v, const int64_t* unique_ids,
   const double c2 = sqrt(1.0 - beta2_pow_t);
   AdamOp op{W, m, v, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
             (float)(lr * c2 / (1.0 - beta1_pow_t)), (float)(eps * c2)};
-  return launch_row_update("sparse_adam", unique_ids, rows, num_unique, n, D, V, op, W, m, v,
-                           ST(stream));
+  return launch_row_update("sparse_adam", unique_ids, rows, num_unique, n, D, V, ldw, ld_rows, op,
+                           W, m, v, ST(stream));
 }
 
-int b200rec_sparse_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
-                           const int32_t* num_unique, int64_t n, int D, int64_t V, double lr,
+int b200rec_sparse_adagrad(float* W, float* g2sum, int64_t ldw, const int64_t* unique_ids,
+                           const float* rows, int64_t ld_rows, const int32_t* num_unique, int64_t n,
+                           int D, int64_t V, double lr,
                            double initial_g2sum, double lo, double hi, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0 && V > 0, "sparse_adagrad: bad sizes");
   if (n > 0) { NOT_NULL(W); NOT_NULL(g2sum); NOT_NULL(unique_ids); NOT_NULL(rows); NOT_NULL(num_unique); }
-  return launch_adagrad(W, g2sum, unique_ids, rows, num_unique, n, D, V, (float)lr,
+  return launch_adagrad(W, g2sum, unique_ids, rows, num_unique, n, D, V, ldw, ld_rows, (float)lr,
                         (float)initial_g2sum, (float)lo, (float)hi,
                         ST(stream));
 }

@@ -34,7 +34,7 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
                     const float* __restrict__ dense_w, const float* __restrict__ dense_w1,
                     float* __restrict__ feat, float* __restrict__ y1, float* __restrict__ y2,
                     float* __restrict__ S, int64_t B, int F, int Dn, int D, int64_t V,
-                    int64_t pad) {
+                    int64_t pad, int64_t ldw, int64_t ldw1) {
   constexpr int kThreads = FwdGeom<TPR>::kThreads;
   constexpr int SPB = FwdGeom<TPR>::kSamples;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,8 +71,8 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
           const int64_t id = my_ids[f];
           const bool in_range = (uint64_t)id < (uint64_t)V;
           const bool live = in_range && id != pad;
-          if (live && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * D + r * VEC);
-          if (live && (f & (TPR - 1)) == r) first += __ldg(W1 + id);
+          if (live && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * ldw + r * VEC);
+          if (live && (f & (TPR - 1)) == r) first += __ldg(W1 + (size_t)id * ldw1);
           if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
         }
       }
@@ -125,9 +125,12 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
 static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids,
                                const float* dense, const float* dense_w, const float* dense_w1,
                                float* feat, float* y1, float* y2, float* S, int64_t B, int F,
-                               int Dn, int D, int64_t V, int64_t pad, cudaStream_t st) {
+                               int Dn, int D, int64_t V, int64_t pad, int64_t ldw, int64_t ldw1,
+                               cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "embed_fm_fwd: unsupported D=%d", D);
+  B200_REQUIRE(ldw >= D && ldw1 >= 1 && ldw % rs.vec == 0,
+               "embed_fm_fwd: bad row strides ldw=%lld ldw1=%lld", (long long)ldw, (long long)ldw1);
   if (rs.vec == 4)
     B200_REQUIRE(aligned16(W) && aligned16(feat) && aligned16(dense_w) && (!S || aligned16(S)),
                  "embed_fm_fwd: W/feat/dense_w/S must be 16-byte aligned for D%%4==0");
@@ -145,7 +148,8 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
       B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (B + SPB - 1) / SPB;
     kern<<<(unsigned)grid, FwdGeom<TPR>::kThreads, smem, st>>>(W, W1, ids, dense, dense_w, dense_w1,
-                                                               feat, y1, y2, S, B, F, Dn, D, V, pad);
+                                                               feat, y1, y2, S, B, F, Dn, D, V, pad, ldw,
+                                                               ldw1);
   });
   B200_LAUNCH_CHECK();
   return B200REC_OK;
@@ -296,14 +300,16 @@ static int launch_embed_fm_bwd(const float* feat, const float* S, const float* d
                                const float* gy1, const float* gy2, const float* dense,
                                const int32_t* seg_offsets, const int32_t* sorted_pos,
                                const int32_t* num_unique, float* dW_rows, float* dW1_rows,
-                               float* ddense_w, float* ddense_w1, int64_t B, int F, int Dn, int D,
-                               void* ws, size_t ws_bytes, cudaStream_t st) {
+                               SegOut so, float* ddense_w, float* ddense_w1, int64_t B, int F,
+                               int Dn, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "embed_fm_bwd: unsupported D=%d", D);
   const int align = rs.vec * 4;
   auto ok = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) % align) == 0; };
   B200_REQUIRE(ok(feat) && ok(S) && ok(dfeat_dnn) && ok(dW_rows),
                "embed_fm_bwd: feat/S/dfeat_dnn/dW_rows must be %d-byte aligned", align);
+  B200_REQUIRE(so.ld_rows >= D && so.ld_rows % rs.vec == 0 && so.ld_rows1 >= 1 && so.zero_pad >= 0,
+               "embed_fm_bwd: bad output strides");
   B200_REQUIRE(B * F < (int64_t)INT32_MAX, "embed_fm_bwd: B*F must fit int32");
   const int G = bwd_dense_grid();
   const size_t dense_bytes = align_up((size_t)G * ((size_t)Dn * D + Dn) * sizeof(float), 256);
@@ -326,7 +332,7 @@ static int launch_embed_fm_bwd(const float* feat, const float* S, const float* d
     if (n > 0) {
       FmRowContrib contrib{feat, S, dfeat_dnn, gy1, gy2, F, N, D};
       rc = launch_seg_reduce<VEC, TPR, FmRowContrib>(seg_offsets, sorted_pos, num_unique, contrib,
-                                                     dW_rows, dW1_rows, n, D,
+                                                     dW_rows, dW1_rows, so, n, D,
                                                      static_cast<unsigned char*>(ws) + dense_bytes,
                                                      st);
     }

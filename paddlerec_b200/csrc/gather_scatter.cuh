@@ -21,7 +21,7 @@ constexpr int kGatherRowsPerGroup = 4;  // independent rows in flight per lane g
 template <int VEC, int TPR>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_kernel(const float* __restrict__ W, const int64_t* __restrict__ ids,
-              float* __restrict__ out, int64_t n, int D, int64_t V, int64_t pad) {
+              float* __restrict__ out, int64_t n, int D, int64_t V, int64_t pad, int64_t ldw) {
   constexpr int GPB = kGatherThreads / TPR;
   const int g = threadIdx.x / TPR;
   const int r = threadIdx.x % TPR;
@@ -35,7 +35,7 @@ gather_kernel(const float* __restrict__ W, const int64_t* __restrict__ ids,
     if (i < n) {
       const int64_t id = __ldg(ids + i);
       const bool in_range = (uint64_t)id < (uint64_t)V;
-      if (in_range && id != pad && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * D + r * VEC);
+      if (in_range && id != pad && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * ldw + r * VEC);
       if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
     }
   }
@@ -47,9 +47,10 @@ gather_kernel(const float* __restrict__ W, const int64_t* __restrict__ ids,
 }
 
 static int launch_gather(const float* W, const int64_t* ids, float* out, int64_t n, int D,
-                         int64_t V, int64_t pad, cudaStream_t st) {
+                         int64_t V, int64_t pad, int64_t ldw, cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "gather: unsupported D=%d", D);
+  B200_REQUIRE(ldw >= D && ldw % rs.vec == 0, "gather: bad row stride %lld", (long long)ldw);
   const int align = rs.vec * 4;
   B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % align == 0 &&
                    reinterpret_cast<uintptr_t>(out) % align == 0,
@@ -58,7 +59,8 @@ static int launch_gather(const float* W, const int64_t* ids, float* out, int64_t
   B200_DISPATCH_ROW_SHAPE(rs, {
     constexpr int rows_per_block = (kGatherThreads / TPR) * kGatherRowsPerGroup;
     const int64_t grid = (n + rows_per_block - 1) / rows_per_block;
-    gather_kernel<VEC, TPR><<<(unsigned)grid, kGatherThreads, 0, st>>>(W, ids, out, n, D, V, pad);
+    gather_kernel<VEC, TPR><<<(unsigned)grid, kGatherThreads, 0, st>>>(W, ids, out, n, D, V, pad,
+                                                                       ldw);
   });
   B200_LAUNCH_CHECK();
   return B200REC_OK;
@@ -96,7 +98,8 @@ static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
   B200_DISPATCH_ROW_SHAPE(rs, {
     PlainRowContrib contrib{dOut, D};
     rc = launch_seg_reduce<VEC, TPR, PlainRowContrib>(seg_offsets, sorted_pos, num_unique, contrib,
-                                                      rows, nullptr, n, D, ws, st);
+                                                      rows, nullptr, SegOut{D, 1, 0}, n, D, ws,
+                                                      st);
   });
   return rc;
 }
@@ -152,7 +155,8 @@ struct AdamOp {
 template <int VEC, int TPR, typename Op>
 __global__ void __launch_bounds__(kGatherThreads)
 row_update_kernel(const int64_t* __restrict__ unique_ids, const float* __restrict__ rows,
-                  const int32_t* __restrict__ num_unique, int D, int64_t V, Op op) {
+                  const int32_t* __restrict__ num_unique, int D, int64_t V, int64_t ldw,
+                  int64_t ld_rows, Op op) {
   constexpr int GPB = kGatherThreads / TPR;
   const int U = num_unique[0];
   const int r = threadIdx.x % TPR;
@@ -161,8 +165,8 @@ row_update_kernel(const int64_t* __restrict__ unique_ids, const float* __restric
        u += (int64_t)gridDim.x * GPB) {
     const int64_t id = unique_ids[u];
     if ((uint64_t)id >= (uint64_t)V || !lane_ok) continue;
-    const Vec<VEC> g = ld_row<VEC>(rows + (size_t)u * D + r * VEC);
-    op.template apply<VEC>((size_t)id * D + r * VEC, g, r);
+    const Vec<VEC> g = ld_row<VEC>(rows + (size_t)u * ld_rows + r * VEC);
+    op.template apply<VEC>((size_t)id * ldw + r * VEC, g, r);
   }
 }
 
@@ -171,8 +175,8 @@ template <int VEC, int TPR>
 __global__ void __launch_bounds__(kGatherThreads)
 row_adagrad_kernel(float* __restrict__ W, float* __restrict__ g2sum,
                    const int64_t* __restrict__ unique_ids, const float* __restrict__ rows,
-                   const int32_t* __restrict__ num_unique, int D, int64_t V, float lr, float g0,
-                   float lo, float hi) {
+                   const int32_t* __restrict__ num_unique, int D, int64_t V, int64_t ldw,
+                   int64_t ld_rows, float lr, float g0, float lo, float hi) {
   constexpr int GPB = kGatherThreads / TPR;
   const int U = num_unique[0];
   const int r = threadIdx.x % TPR;
@@ -185,7 +189,7 @@ row_adagrad_kernel(float* __restrict__ W, float* __restrict__ g2sum,
     int64_t id = live ? unique_ids[u] : -1;
     const bool ok = live && (uint64_t)id < (uint64_t)V && lane_ok;
     Vec<VEC> g = vzero<VEC>();
-    if (ok) g = ld_row<VEC>(rows + (size_t)u * D + r * VEC);
+    if (ok) g = ld_row<VEC>(rows + (size_t)u * ld_rows + r * VEC);
     float sq = 0.f;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) sq = fmaf(g.v[k], g.v[k], sq);
@@ -193,13 +197,13 @@ row_adagrad_kernel(float* __restrict__ W, float* __restrict__ g2sum,
     if (ok) {
       const float acc = g2sum[id];
       const float scale = sqrtf(g0 / (g0 + acc));
-      Vec<VEC> w = *reinterpret_cast<const Vec<VEC>*>(W + (size_t)id * D + r * VEC);
+      Vec<VEC> w = *reinterpret_cast<const Vec<VEC>*>(W + (size_t)id * ldw + r * VEC);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         w.v[k] -= lr * g.v[k] * scale;
         w.v[k] = fminf(fmaxf(w.v[k], lo), hi);
       }
-      st_plain<VEC>(W + (size_t)id * D + r * VEC, w);
+      st_plain<VEC>(W + (size_t)id * ldw + r * VEC, w);
     }
     __syncwarp();
     if (ok && r == 0) g2sum[id] += sq / (float)D;
@@ -208,10 +212,13 @@ row_adagrad_kernel(float* __restrict__ W, float* __restrict__ g2sum,
 
 template <typename Op>
 static int launch_row_update(const char* what, const int64_t* unique_ids, const float* rows,
-                             const int32_t* num_unique, int64_t n, int D, int64_t V, Op op,
-                             const void* a0, const void* a1, const void* a2, cudaStream_t st) {
+                             const int32_t* num_unique, int64_t n, int D, int64_t V, int64_t ldw,
+                             int64_t ld_rows, Op op, const void* a0, const void* a1,
+                             const void* a2, cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "%s: unsupported D=%d", what, D);
+  B200_REQUIRE(ldw >= D && ld_rows >= D && ldw % rs.vec == 0 && ld_rows % rs.vec == 0,
+               "%s: bad row strides", what);
   const int align = rs.vec * 4;
   auto ok = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) % align) == 0; };
   B200_REQUIRE(ok(rows) && ok(a0) && ok(a1) && ok(a2), "%s: buffers must be %d-byte aligned", what,
@@ -222,17 +229,20 @@ static int launch_row_update(const char* what, const int64_t* unique_ids, const 
     const int64_t want = (n + GPB - 1) / GPB;
     const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
     row_update_kernel<VEC, TPR, Op><<<grid, kGatherThreads, 0, st>>>(unique_ids, rows, num_unique,
-                                                                     D, V, op);
+                                                                     D, V, ldw, ld_rows, op);
   });
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }
 
 static int launch_adagrad(float* W, float* g2sum, const int64_t* unique_ids, const float* rows,
-                          const int32_t* num_unique, int64_t n, int D, int64_t V, float lr,
-                          float g0, float lo, float hi, cudaStream_t st) {
+                          const int32_t* num_unique, int64_t n, int D, int64_t V, int64_t ldw,
+                          int64_t ld_rows, float lr, float g0, float lo, float hi,
+                          cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "sparse_adagrad: unsupported D=%d", D);
+  B200_REQUIRE(ldw >= D && ld_rows >= D && ldw % rs.vec == 0 && ld_rows % rs.vec == 0,
+               "sparse_adagrad: bad row strides");
   const int align = rs.vec * 4;
   B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % align == 0 &&
                    reinterpret_cast<uintptr_t>(rows) % align == 0,
@@ -242,8 +252,8 @@ static int launch_adagrad(float* W, float* g2sum, const int64_t* unique_ids, con
     constexpr int GPB = kGatherThreads / TPR;
     const int64_t want = (n + GPB - 1) / GPB;
     const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
-    row_adagrad_kernel<VEC, TPR><<<grid, kGatherThreads, 0, st>>>(W, g2sum, unique_ids, rows,
-                                                                  num_unique, D, V, lr, g0, lo, hi);
+    row_adagrad_kernel<VEC, TPR><<<grid, kGatherThreads, 0, st>>>(
+        W, g2sum, unique_ids, rows, num_unique, D, V, ldw, ld_rows, lr, g0, lo, hi);
   });
   B200_LAUNCH_CHECK();
   return B200REC_OK;

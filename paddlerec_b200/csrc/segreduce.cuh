@@ -15,6 +15,14 @@
 namespace b200rec {
 
 constexpr int kSegThreads = 256;
+
+// Output geometry: rows[u*ld_rows + d]; rows1[u*ld_rows1] (+ zero_pad zeroed floats after it, used
+// when rows1 is the tail of a fused [emb | w1 | pad] gradient row).
+struct SegOut {
+  int64_t ld_rows;
+  int64_t ld_rows1;
+  int zero_pad;
+};
 constexpr int kHotThreshold = 64;   // segments longer than this go to the hot path
 constexpr int kHotChunk = 2048;     // positions per hot work item (one CTA)
 
@@ -30,7 +38,7 @@ template <int VEC, int TPR, typename Contrib>
 __global__ void __launch_bounds__(kSegThreads)
 seg_light_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ sorted_pos,
                  const int32_t* __restrict__ num_unique, Contrib contrib, float* __restrict__ rows,
-                 float* __restrict__ rows1, int D, int32_t* __restrict__ hot_count,
+                 float* __restrict__ rows1, int D, SegOut so, int32_t* __restrict__ hot_count,
                  int32_t* __restrict__ hot_items) {
   constexpr int GPB = kSegThreads / TPR;
   const int U = num_unique[0];
@@ -54,8 +62,12 @@ seg_light_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restr
     Vec<VEC> acc = vzero<VEC>();
     float acc1 = 0.f;
     for (int i = beg; i < end; ++i) contrib.template add<VEC>(sorted_pos[i], r, lane_ok, acc, acc1);
-    if (lane_ok) st_plain<VEC>(rows + (size_t)u * D + r * VEC, acc);
-    if (rows1 != nullptr && r == 0) rows1[u] = acc1;
+    if (lane_ok) st_plain<VEC>(rows + (size_t)u * so.ld_rows + r * VEC, acc);
+    if (rows1 != nullptr && r == 0) {
+      float* p1 = rows1 + (size_t)u * so.ld_rows1;
+      p1[0] = acc1;
+      for (int j = 1; j <= so.zero_pad; ++j) p1[j] = 0.f;
+    }
   }
 }
 
@@ -108,7 +120,7 @@ seg_hot_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restric
 __global__ void seg_combine_kernel(const int32_t* __restrict__ hot_count,
                                    const int32_t* __restrict__ hot_items,
                                    const float* __restrict__ partials, float* __restrict__ rows,
-                                   float* __restrict__ rows1, int D) {
+                                   float* __restrict__ rows1, int D, SegOut so) {
   const int n_items = hot_count[0];
   for (int h = blockIdx.x; h < n_items; h += gridDim.x) {
     const int meta = hot_items[2 * h + 1];
@@ -118,10 +130,13 @@ __global__ void seg_combine_kernel(const int32_t* __restrict__ hot_count,
     for (int d = threadIdx.x; d <= D; d += blockDim.x) {
       float t = 0.f;
       for (int c = 0; c < chunks; ++c) t += partials[(size_t)(h + c) * (D + 1) + d];
-      if (d < D)
-        rows[(size_t)u * D + d] = t;
-      else if (rows1 != nullptr)
-        rows1[u] = t;
+      if (d < D) {
+        rows[(size_t)u * so.ld_rows + d] = t;
+      } else if (rows1 != nullptr) {
+        float* p1 = rows1 + (size_t)u * so.ld_rows1;
+        p1[0] = t;
+        for (int j = 1; j <= so.zero_pad; ++j) p1[j] = 0.f;
+      }
     }
   }
 }
@@ -131,7 +146,8 @@ __global__ void seg_combine_kernel(const int32_t* __restrict__ hot_count,
 template <int VEC, int TPR, typename Contrib>
 static int launch_seg_reduce(const int32_t* seg_offsets, const int32_t* sorted_pos,
                              const int32_t* num_unique, const Contrib& contrib, float* rows,
-                             float* rows1, int64_t n, int D, void* ws, cudaStream_t st) {
+                             float* rows1, SegOut so, int64_t n, int D, void* ws,
+                             cudaStream_t st) {
   B200_REQUIRE(n < (int64_t)32767 * kHotChunk, "segment reduce: n=%lld too large", (long long)n);
   unsigned char* base = static_cast<unsigned char*>(ws);
   int32_t* hot_count = reinterpret_cast<int32_t*>(base);
@@ -144,14 +160,14 @@ static int launch_seg_reduce(const int32_t* seg_offsets, const int32_t* sorted_p
   const int64_t want = (n + GPB - 1) / GPB;
   const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
   seg_light_kernel<VEC, TPR, Contrib><<<grid, kSegThreads, 0, st>>>(
-      seg_offsets, sorted_pos, num_unique, contrib, rows, rows1, D, hot_count, hot_items);
+      seg_offsets, sorted_pos, num_unique, contrib, rows, rows1, D, so, hot_count, hot_items);
   B200_LAUNCH_CHECK();
   if (n > kHotThreshold) {
     const unsigned hgrid = (unsigned)min((int64_t)items, (int64_t)sm_count() * 8);
     seg_hot_kernel<VEC, TPR, Contrib><<<hgrid, kSegThreads, 0, st>>>(
         seg_offsets, sorted_pos, contrib, D, hot_count, hot_items, partials);
     B200_LAUNCH_CHECK();
-    seg_combine_kernel<<<hgrid, 128, 0, st>>>(hot_count, hot_items, partials, rows, rows1, D);
+    seg_combine_kernel<<<hgrid, 128, 0, st>>>(hot_count, hot_items, partials, rows, rows1, D, so);
     B200_LAUNCH_CHECK();
   }
   return B200REC_OK;

@@ -187,6 +187,121 @@ class Embedding(tnn.Module):
         return out
 
 
+class FusedTable(tnn.Module):
+    """B200-native layout for a pair of tables that are always looked up with the same ids (DeepFM's
+    second-order [V,D] and first-order [V,1], models/rank/deepfm/net.py:66-86): ONE array of
+    128-byte slots `[D emb | w1 | pad]`.
+
+    Why: on B200 a random 64-byte row costs a full 128-byte DRAM access and so does a random 4-byte
+    scalar (profiles/r1_gather_variants_microbench.txt), so the reference's two-table layout moves
+    256 B per looked-up id for 68 useful bytes; the slot moves 128 B.  Same for the optimizer.
+
+    state_dict() still exposes the reference's two keys (`embedding.weight` [V,D] and
+    `embedding_one.weight` [V,1], as views of the slot array) and loads from them, so checkpoints
+    stay interchangeable.  The gradient is one SelectedRows of width D+1 (+pad) on `weight`."""
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx=None, init_std=None, device=None,
+                 names=("embedding.weight", "embedding_one.weight"), attr="_fused"):
+        super().__init__()
+        D = embedding_dim
+        self.num_embeddings, self.embedding_dim = num_embeddings, D
+        self.slot, self.grad_cols = ops.fused_slot(D), ops.fused_grad_cols(D)
+        self.padding_idx = padding_idx
+        self._names, self._attr = names, attr
+        w = torch.zeros(num_embeddings, self.slot, device=device)
+        std = init_std or 1.0
+        if num_embeddings > 0:
+            tnn.init.trunc_normal_(w[:, :D + 1], 0.0, std, -2.0 * std, 2.0 * std)
+            if padding_idx is not None:
+                w[padding_idx].zero_()
+        self.weight = tnn.Parameter(w, requires_grad=False)
+        self._tag()
+
+    def _tag(self):
+        self.weight.is_sparse_table = True
+        self.weight.fused_D = self.embedding_dim
+        self.weight.fused_names = self._names
+        if not hasattr(self.weight, "grad_rows"):
+            self.weight.grad_rows = None
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._tag()
+        return out
+
+    @property
+    def pad(self) -> int:
+        return -1 if self.padding_idx is None else int(self.padding_idx)
+
+    def views(self):
+        w = self.weight.detach()
+        D = self.embedding_dim
+        return w[:, :D], w[:, D:D + 1]
+
+    # ---- gradient sink protocol used by ops._EmbedFM -----------------------------------------
+    def groups_for(self, ids, V, pad):
+        return ops.raw_group_ids(ids, V, pad)
+
+    def accept_fused(self, sr: ops.SelectedRows) -> None:
+        if self.weight.grad_rows is not None:
+            raise RuntimeError("FusedTable used twice in one step (clear_grad between steps)")
+        sr.ncols = self.grad_cols
+        self.weight.grad_rows = sr
+
+    @property
+    def grad_rows(self):
+        return self.weight.grad_rows
+
+    def grad_dense(self):
+        """(dW [V,D], dW1 [V,1]) as dense tensors (tests / small tables)."""
+        D = self.embedding_dim
+        if self.weight.grad_rows is None:
+            z = torch.zeros(self.num_embeddings, D + 1, device=self.weight.device)
+        else:
+            z = self.weight.grad_rows.to_dense()
+        return z[:, :D], z[:, D:D + 1]
+
+    # ---- reference-compatible checkpoint keys -------------------------------------------------
+    def _parent_prefix(self, prefix: str) -> str:
+        return prefix[:-(len(self._attr) + 1)]
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        e, e1 = self.views()
+        parent = self._parent_prefix(prefix)
+        destination[parent + self._names[0]] = e
+        destination[parent + self._names[1]] = e1
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        pass  # the owning module routes the reference-named keys here (load_views)
+
+    def load_views(self, state_dict, parent_prefix, strict, missing_keys):
+        """Copy `<parent>embedding.weight` / `<parent>embedding_one.weight` into the slot array and
+        return the state_dict without those keys (torch only hands a child the keys under ITS
+        prefix, so the parent module calls this from its own _load_from_state_dict)."""
+        e, e1 = self.views()
+        rest = dict(state_dict)
+        for name, view in ((self._names[0], e), (self._names[1], e1)):
+            key = parent_prefix + name
+            if key in rest:
+                with torch.no_grad():
+                    view.copy_(rest.pop(key).reshape(view.shape))
+            elif strict:
+                missing_keys.append(key)
+        return rest
+
+
+class FusedTableOwner(tnn.Module):
+    """Mixin for a module that holds a FusedTable in `self._fused` (may be absent)."""
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                              unexpected_keys, error_msgs):
+        fused = self._modules.get("_fused")
+        if fused is not None:
+            state_dict = fused.load_views(state_dict, prefix, strict, missing_keys)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
+                                      unexpected_keys, error_msgs)
+
+
 class EmbeddingPair:
     """Grad sink for the fused DeepFM kernel, which reads TWO tables ([V,1] and [V,D]) with the
     same ids: one grouping pass serves both SelectedRows."""

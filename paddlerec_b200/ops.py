@@ -104,13 +104,17 @@ class SelectedRows:
     Mirrors Paddle's SelectedRows (what paddle.nn.Embedding(sparse=True) hands the optimizer),
     already merged (each row appears once)."""
     rows: torch.Tensor    # int64 [n]  (first num[0] valid)
-    value: torch.Tensor   # f32 [n, D] (first num[0] valid; the rest is unspecified)
+    value: torch.Tensor   # f32 [n, ld] (first num[0] rows valid; the rest is unspecified)
     num: torch.Tensor     # int32 [2] device
     height: int
+    ncols: Optional[int] = None   # gradient columns (<= ld); None = all of value's columns
+
+    @property
+    def cols(self) -> int:
+        return self.value.shape[1] if self.ncols is None else self.ncols
 
     def to_dense(self) -> torch.Tensor:
-        D = self.value.shape[1]
-        out = torch.zeros(self.height, D, dtype=torch.float32, device=self.value.device)
+        out = torch.zeros(self.height, self.cols, dtype=torch.float32, device=self.value.device)
         raw_rows_to_dense(self, out)
         return out
 
@@ -125,26 +129,35 @@ def raw_oob_count(reset: bool = True) -> int:
     return int(out.value)
 
 
-def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, padding_idx: int, want_S: bool = True):
+def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, padding_idx: int, want_S: bool = True,
+                     D: Optional[int] = None):
+    """W: [V, ldw] table.  W1: [V]/[V,1] first-order table, or None for the FUSED slot layout
+    (row = [D emb | w1 | pad], so W1 = W + D with the same stride; `D` must then be given)."""
     lib = _lib.load()
     W = _req(W, torch.float32, "W")
-    W1 = _req(W1, torch.float32, "W1")
     ids = _req(ids, torch.int64, "ids")
     dense = _req(dense, torch.float32, "dense")
     dense_w = _req(dense_w, torch.float32, "dense_w")
     dense_w1 = _req(dense_w1, torch.float32, "dense_w1")
     B, F = ids.shape
-    Dn = dense.shape[1] if dense.numel() or dense.dim() == 2 else 0
-    V, D = W.shape
-    assert W1.numel() == V and dense.shape[0] == B
-    assert dense_w.numel() == Dn * D and dense_w1.numel() == Dn
+    Dn = dense.shape[1]
+    V, ldw = W.shape
+    if W1 is None:
+        assert D is not None and D + 1 <= ldw, "fused layout needs D and a slot of >= D+1 floats"
+        w1_ptr, ldw1 = ctypes.c_void_p(W.data_ptr() + 4 * D), ldw
+    else:
+        W1 = _req(W1, torch.float32, "W1")
+        D = ldw if D is None else D
+        assert W1.numel() == V
+        w1_ptr, ldw1 = ptr(W1), 1
+    assert dense.shape[0] == B and dense_w.numel() == Dn * D and dense_w1.numel() == Dn
     dev = W.device
     feat = torch.empty(B, F + Dn, D, dtype=torch.float32, device=dev)
     y1 = torch.empty(B, dtype=torch.float32, device=dev)
     y2 = torch.empty(B, dtype=torch.float32, device=dev)
     S = torch.empty(B, D, dtype=torch.float32, device=dev) if want_S else None
     with _Timed("embed_fm_fwd"):
-        check(lib.b200rec_embed_fm_fwd(ptr(W), ptr(W1), ptr(ids), ptr(dense), ptr(dense_w),
+        check(lib.b200rec_embed_fm_fwd(ptr(W), ldw, w1_ptr, ldw1, ptr(ids), ptr(dense), ptr(dense_w),
                                        ptr(dense_w1), ptr(feat), ptr(y1), ptr(y2), ptr(S), B, F, Dn,
                                        D, V, int(padding_idx), _stream()), "embed_fm_fwd")
     _count("embed_fm_fwd")
@@ -170,8 +183,12 @@ def raw_group_ids(ids: torch.Tensor, V: int, padding_idx: int) -> IdGroups:
     return IdGroups(unique_ids, seg_offsets, sorted_pos, num, n, V)
 
 
-def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_pos, num, F: int):
-    """Returns (dW_rows [n,D], dW1_rows [n], ddense_w [Dn,D], ddense_w1 [Dn])."""
+def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_pos, num, F: int,
+                     fused_cols: int = 0):
+    """Returns (dW_rows, dW1_rows, ddense_w [Dn,D], ddense_w1 [Dn]).
+    fused_cols == 0: dW_rows [n,D], dW1_rows [n].
+    fused_cols == G (>= D+1, multiple of 4): ONE buffer dW_rows [n,G] = [D | g1 | zeros], and
+    dW1_rows is None."""
     lib = _lib.load()
     feat = _req(feat, torch.float32, "feat")
     S = _req(S, torch.float32, "S")
@@ -187,26 +204,38 @@ def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg_offsets, sorted_po
     nbytes = ctypes.c_size_t(0)
     check(lib.b200rec_embed_fm_bwd_workspace_bytes(B, F, Dn, D, ctypes.byref(nbytes)), "fm_bwd_ws")
     ws = workspace(nbytes.value, dev, "fm_bwd")
-    dW_rows = torch.empty(max(n, 1), D, dtype=torch.float32, device=dev)
-    dW1_rows = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    if fused_cols:
+        assert fused_cols >= D + 1
+        dW_rows = torch.empty(max(n, 1), fused_cols, dtype=torch.float32, device=dev)
+        dW1_rows = None
+        dw1_ptr = ctypes.c_void_p(dW_rows.data_ptr() + 4 * D)
+        ld_dw, ld_dw1, zero_pad = fused_cols, fused_cols, fused_cols - D - 1
+    else:
+        dW_rows = torch.empty(max(n, 1), D, dtype=torch.float32, device=dev)
+        dW1_rows = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        dw1_ptr, ld_dw, ld_dw1, zero_pad = ptr(dW1_rows), D, 1, 0
     ddense_w = torch.empty(Dn, D, dtype=torch.float32, device=dev)
     ddense_w1 = torch.empty(Dn, dtype=torch.float32, device=dev)
     check(lib.b200rec_embed_fm_bwd(ptr(feat), ptr(S), ptr(dfeat_dnn), ptr(gy1), ptr(gy2),
                                    ptr(dense), ptr(seg_offsets), ptr(sorted_pos), ptr(num),
-                                   ptr(dW_rows), ptr(dW1_rows), ptr(ddense_w), ptr(ddense_w1), B, F,
-                                   Dn, D, ptr(ws), ws.numel(), _stream()), "embed_fm_bwd")
+                                   ptr(dW_rows), ld_dw, dw1_ptr, ld_dw1, zero_pad, ptr(ddense_w),
+                                   ptr(ddense_w1), B, F, Dn, D, ptr(ws), ws.numel(), _stream()),
+          "embed_fm_bwd")
     _count("embed_fm_bwd")
     return dW_rows, dW1_rows, ddense_w, ddense_w1
 
 
-def raw_gather(W: torch.Tensor, ids: torch.Tensor, padding_idx: int) -> torch.Tensor:
+def raw_gather(W: torch.Tensor, ids: torch.Tensor, padding_idx: int,
+               D: Optional[int] = None) -> torch.Tensor:
+    """out[..., :] = W[ids, :D]; W is [V, ldw] (D defaults to ldw)."""
     lib = _lib.load()
     W = _req(W, torch.float32, "W")
     ids = _req(ids, torch.int64, "ids")
-    V, D = W.shape
+    V, ldw = W.shape
+    D = ldw if D is None else D
     n = ids.numel()
     out = torch.empty(*ids.shape, D, dtype=torch.float32, device=W.device)
-    check(lib.b200rec_gather(ptr(W), ptr(ids), ptr(out), n, D, V, int(padding_idx), _stream()),
+    check(lib.b200rec_gather(ptr(W), ldw, ptr(ids), ptr(out), n, D, V, int(padding_idx), _stream()),
           "gather")
     _count("gather")
     return out
@@ -230,36 +259,38 @@ def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int) 
 def raw_rows_to_dense(sr: SelectedRows, dW: torch.Tensor) -> None:
     lib = _lib.load()
     dW = _req(dW, torch.float32, "dW")
-    n, D = sr.value.shape
-    check(lib.b200rec_rows_to_dense(ptr(sr.rows), ptr(sr.value), ptr(sr.num), ptr(dW), n, D,
-                                    sr.height, _stream()), "rows_to_dense")
+    n, ld_rows = sr.value.shape
+    check(lib.b200rec_rows_to_dense(ptr(sr.rows), ptr(sr.value), ld_rows, ptr(sr.num), ptr(dW),
+                                    dW.shape[1], n, sr.cols, sr.height, _stream()), "rows_to_dense")
     _count("rows_to_dense")
 
 
 def raw_sparse_sgd(W: torch.Tensor, sr: SelectedRows, lr: float) -> None:
     lib = _lib.load()
-    n, D = sr.value.shape
-    check(lib.b200rec_sparse_sgd(ptr(W), ptr(sr.rows), ptr(sr.value), ptr(sr.num), n, D, sr.height,
-                                 float(lr), _stream()), "sparse_sgd")
+    n, ld_rows = sr.value.shape
+    check(lib.b200rec_sparse_sgd(ptr(W), W.shape[1], ptr(sr.rows), ptr(sr.value), ld_rows,
+                                 ptr(sr.num), n, sr.cols, sr.height, float(lr), _stream()),
+          "sparse_sgd")
     _count("sparse_sgd")
 
 
 def raw_sparse_adam(W, m, v, sr: SelectedRows, lr, beta1, beta2, eps, beta1_pow, beta2_pow) -> None:
     lib = _lib.load()
-    n, D = sr.value.shape
-    check(lib.b200rec_sparse_adam(ptr(W), ptr(m), ptr(v), ptr(sr.rows), ptr(sr.value), ptr(sr.num),
-                                  n, D, sr.height, float(lr), float(beta1), float(beta2),
-                                  float(eps), float(beta1_pow), float(beta2_pow), _stream()),
-          "sparse_adam")
+    n, ld_rows = sr.value.shape
+    check(lib.b200rec_sparse_adam(ptr(W), ptr(m), ptr(v), W.shape[1], ptr(sr.rows), ptr(sr.value),
+                                  ld_rows, ptr(sr.num), n, sr.cols, sr.height, float(lr),
+                                  float(beta1), float(beta2), float(eps), float(beta1_pow),
+                                  float(beta2_pow), _stream()), "sparse_adam")
     _count("sparse_adam")
 
 
 def raw_sparse_adagrad(W, g2sum, sr: SelectedRows, lr, initial_g2sum, lo, hi) -> None:
     lib = _lib.load()
-    n, D = sr.value.shape
-    check(lib.b200rec_sparse_adagrad(ptr(W), ptr(g2sum), ptr(sr.rows), ptr(sr.value), ptr(sr.num),
-                                     n, D, sr.height, float(lr), float(initial_g2sum), float(lo),
-                                     float(hi), _stream()), "sparse_adagrad")
+    n, ld_rows = sr.value.shape
+    check(lib.b200rec_sparse_adagrad(ptr(W), ptr(g2sum), W.shape[1], ptr(sr.rows), ptr(sr.value),
+                                     ld_rows, ptr(sr.num), n, sr.cols, sr.height, float(lr),
+                                     float(initial_g2sum), float(lo), float(hi), _stream()),
+          "sparse_adagrad")
     _count("sparse_adagrad")
 
 
@@ -370,18 +401,18 @@ def raw_tower_fold_dw(Mx: torch.Tensor, K: int, N: int) -> torch.Tensor:
 class _EmbedFM(torch.autograd.Function):
     """FM.forward of models/rank/deepfm/net.py:105-139 as one kernel (+ one in backward).
 
-    `sink` is the object (an `EmbeddingTablePair`) that receives the two SelectedRows gradients.
-    """
+    `sink` receives the SelectedRows gradient(s): `sink.accept(sr_w, sr_w1)` for two separate
+    tables, `sink.accept_fused(sr)` for the fused slot layout (W1 is None)."""
 
     @staticmethod
-    def forward(ctx, W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink):
-        D = W.shape[1]
+    def forward(ctx, W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink, D):
         feat, y1, y2, S = raw_embed_fm_fwd(W, W1, ids, dense, dense_w.reshape(-1, D),
-                                           dense_w1.reshape(-1), padding_idx)
+                                           dense_w1.reshape(-1), padding_idx, D=D)
         ctx.save_for_backward(ids, dense, feat, S)
         ctx.padding_idx = padding_idx
         ctx.sink = sink
         ctx.V = W.shape[0]
+        ctx.fused = W1 is None
         ctx.dense_w_shape = dense_w.shape
         ctx.mark_non_differentiable(S)
         return feat, y1.unsqueeze(1), y2.unsqueeze(1), S
@@ -390,17 +421,34 @@ class _EmbedFM(torch.autograd.Function):
     def backward(ctx, dfeat, dy1, dy2, _dS):
         ids, dense, feat, S = ctx.saved_tensors
         B, F = ids.shape
+        D = feat.shape[2]
         dev = feat.device
         gy1 = dy1.reshape(-1).contiguous() if dy1 is not None else torch.zeros(B, device=dev)
         gy2 = dy2.reshape(-1).contiguous() if dy2 is not None else torch.zeros(B, device=dev)
         if dfeat is not None:
             dfeat = dfeat.contiguous()
         groups = ctx.sink.groups_for(ids, ctx.V, ctx.padding_idx)
+        G = fused_grad_cols(D) if ctx.fused else 0
         dW_rows, dW1_rows, ddense_w, ddense_w1 = raw_embed_fm_bwd(
-            feat, S, dfeat, gy1, gy2, dense, groups.seg_offsets, groups.sorted_pos, groups.num, F)
-        ctx.sink.accept(SelectedRows(groups.unique_ids, dW_rows, groups.num, ctx.V),
-                        SelectedRows(groups.unique_ids, dW1_rows.unsqueeze(1), groups.num, ctx.V))
-        return (None, None, None, None, ddense_w.reshape(ctx.dense_w_shape), ddense_w1, None, None)
+            feat, S, dfeat, gy1, gy2, dense, groups.seg_offsets, groups.sorted_pos, groups.num, F,
+            fused_cols=G)
+        if ctx.fused:
+            ctx.sink.accept_fused(SelectedRows(groups.unique_ids, dW_rows, groups.num, ctx.V))
+        else:
+            ctx.sink.accept(SelectedRows(groups.unique_ids, dW_rows, groups.num, ctx.V),
+                            SelectedRows(groups.unique_ids, dW1_rows.unsqueeze(1), groups.num, ctx.V))
+        return (None, None, None, None, ddense_w.reshape(ctx.dense_w_shape), ddense_w1, None, None,
+                None)
+
+
+def fused_grad_cols(D: int) -> int:
+    """Columns of a fused gradient row [D | g1 | pad]: D+1 rounded up to a multiple of 4."""
+    return (D + 1 + 3) // 4 * 4
+
+
+def fused_slot(D: int) -> int:
+    """Floats per table row in the fused layout: 128-byte slots (32 floats)."""
+    return (D + 1 + 31) // 32 * 32
 
 
 class _Gather(torch.autograd.Function):
@@ -452,8 +500,9 @@ class _CrossV2(torch.autograd.Function):
 HAVE_DIN_ATTN = False
 
 
-def embed_fm(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink):
-    return _EmbedFM.apply(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink)
+def embed_fm(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink, D=None):
+    D = W.shape[1] if D is None else D
+    return _EmbedFM.apply(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink, D)
 
 
 def gather(W, ids, padding_idx, sink, hook):

@@ -19,7 +19,7 @@ from ... import tower
 
 class DeepFMLayer(tnn.Module):
     def __init__(self, sparse_feature_number, sparse_feature_dim, dense_feature_dim,
-                 sparse_num_field, layer_sizes, device="cuda"):
+                 sparse_num_field, layer_sizes, device="cuda", fused_table=None):
         super().__init__()
         self.sparse_feature_number = sparse_feature_number
         self.sparse_feature_dim = sparse_feature_dim
@@ -28,7 +28,7 @@ class DeepFMLayer(tnn.Module):
         self.layer_sizes = layer_sizes
 
         self.fm = FM(sparse_feature_number, sparse_feature_dim, dense_feature_dim,
-                     sparse_num_field, device=device)
+                     sparse_num_field, device=device, fused_table=fused_table)
         self.dnn = DNN(sparse_feature_number, sparse_feature_dim, dense_feature_dim,
                        dense_feature_dim + sparse_num_field, layer_sizes, device=device)
         self.bias = tnn.Parameter(torch.zeros(1, device=device))  # unused, as in net.py:36-39
@@ -39,9 +39,12 @@ class DeepFMLayer(tnn.Module):
         return torch.sigmoid(y_first_order + y_second_order + y_dnn)
 
 
-class FM(tnn.Module):
+class FM(bnn.FusedTableOwner):
+    """`fused_table` (default: on when D+1 fits one 128-byte slot) stores both tables as
+    bnn.FusedTable; state_dict keys stay `embedding.weight` / `embedding_one.weight`."""
+
     def __init__(self, sparse_feature_number, sparse_feature_dim, dense_feature_dim,
-                 sparse_num_field, device="cuda"):
+                 sparse_num_field, device="cuda", fused_table=None):
         super().__init__()
         self.sparse_feature_number = sparse_feature_number
         self.sparse_feature_dim = sparse_feature_dim
@@ -51,17 +54,30 @@ class FM(tnn.Module):
         self.init_value_ = 0.1
         std = self.init_value_ / math.sqrt(float(sparse_feature_dim))
         # net.py:66-86 — two tables indexed by the same ids
-        self.embedding_one = bnn.Embedding(sparse_feature_number, 1, padding_idx=0, init_std=std,
-                                           device=device)
-        self.embedding = bnn.Embedding(sparse_feature_number, sparse_feature_dim, padding_idx=0,
-                                       init_std=std, device=device)
+        self.fused = (sparse_feature_dim + 1 <= 32) if fused_table is None else bool(fused_table)
+        if self.fused:
+            self._fused = bnn.FusedTable(sparse_feature_number, sparse_feature_dim, padding_idx=0,
+                                         init_std=std, device=device)
+        else:
+            self.embedding_one = bnn.Embedding(sparse_feature_number, 1, padding_idx=0,
+                                               init_std=std, device=device)
+            self.embedding = bnn.Embedding(sparse_feature_number, sparse_feature_dim,
+                                           padding_idx=0, init_std=std, device=device)
+            self._pair = bnn.EmbeddingPair(self.embedding, self.embedding_one)
         # net.py:89-103
         self.dense_w_one = tnn.Parameter(torch.empty(dense_feature_dim, device=device))
         self.dense_w = tnn.Parameter(
             torch.empty(1, dense_feature_dim, self.dense_emb_dim, device=device))
         tnn.init.trunc_normal_(self.dense_w_one, 0.0, std, -2 * std, 2 * std)
         tnn.init.trunc_normal_(self.dense_w, 0.0, std, -2 * std, 2 * std)
-        self._pair = bnn.EmbeddingPair(self.embedding, self.embedding_one)
+
+    def table_grad_dense(self):
+        """(dW [V,D], dW1 [V,1]) dense gradients of the two tables (tests / small tables)."""
+        if self.fused:
+            return self._fused.grad_dense()
+        z = lambda e: (e.grad_rows.to_dense() if e.grad_rows is not None  # noqa: E731
+                       else torch.zeros_like(e.weight))
+        return z(self.embedding), z(self.embedding_one)
 
     def forward(self, sparse_inputs, dense_inputs):
         # net.py:107 concat of the 26 [B,1] slots; a ready-made [B,26] tensor is accepted too
@@ -69,8 +85,14 @@ class FM(tnn.Module):
             ids = torch.cat(list(sparse_inputs), dim=1)
         else:
             ids = sparse_inputs
-        feat, y1, y2, _S = ops.embed_fm(self.embedding.weight, self.embedding_one.weight, ids,
-                                        dense_inputs, self.dense_w, self.dense_w_one, 0, self._pair)
+        if self.fused:
+            feat, y1, y2, _S = ops.embed_fm(self._fused.weight, None, ids, dense_inputs,
+                                            self.dense_w, self.dense_w_one, 0, self._fused,
+                                            D=self.sparse_feature_dim)
+        else:
+            feat, y1, y2, _S = ops.embed_fm(self.embedding.weight, self.embedding_one.weight, ids,
+                                            dense_inputs, self.dense_w, self.dense_w_one, 0,
+                                            self._pair)
         return y1, y2, feat
 
 

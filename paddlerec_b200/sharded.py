@@ -66,10 +66,12 @@ class ShardExchange:
         dist.all_to_all_single(recv_ids, send_ids, recv_splits, send_splits, group=self.group)
         return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, recv_ids)
 
-    def pull(self, plan: ExchangePlan, shard: torch.Tensor, local_pad: int) -> torch.Tensor:
-        """Owner-side gather + rows back to the requesters: returns [n, D] in bucket order."""
-        rows_out = self.k.raw_gather(shard, plan.recv_ids, local_pad)
-        rows_in = torch.empty(plan.n, shard.shape[1], dtype=shard.dtype, device=shard.device)
+    def pull(self, plan: ExchangePlan, shard: torch.Tensor, local_pad: int,
+             D: Optional[int] = None) -> torch.Tensor:
+        """Owner-side gather of the first D columns (default: all) + rows back to the requesters:
+        returns [n, D] in bucket order."""
+        rows_out = self.k.raw_gather(shard, plan.recv_ids, local_pad, D)
+        rows_in = torch.empty(plan.n, rows_out.shape[-1], dtype=shard.dtype, device=shard.device)
         dist.all_to_all_single(rows_in, rows_out, plan.send_splits, plan.recv_splits,
                                group=self.group)
         return rows_in
@@ -87,8 +89,8 @@ class ShardExchange:
     def owner_reduce(self, plan: ExchangePlan, grads: torch.Tensor, V_loc: int, local_pad: int):
         """Merge the received gradients by local row -> SelectedRows on the local shard."""
         groups = self.k.raw_group_ids(plan.recv_ids, max(V_loc, 1), local_pad)
-        rows = self.k.raw_segment_reduce(grads, groups.seg_offsets, groups.sorted_pos, groups.num,
-                                         groups.n)
+        rows = self.k.raw_segment_reduce(grads.contiguous(), groups.seg_offsets, groups.sorted_pos,
+                                         groups.num, groups.n)
         return self.k.SelectedRows(groups.unique_ids, rows, groups.num, V_loc)
 
 
@@ -116,12 +118,19 @@ class _ShardedEmbedFM(torch.autograd.Function):
         k, ex = fm.k, fm.exchange
         B, F = ids.shape
         plan = ex.plan(ids)
-        rows = ex.pull(plan, fm.embedding.weight, fm.embedding.pad)
-        rows1 = ex.pull(plan, fm.embedding_one.weight, fm.embedding_one.pad)
-        D = rows.shape[1]
+        D = fm.sparse_feature_dim
         slot_ids = plan.perm.reshape(B, F)
-        feat, y1, y2, S = k.raw_embed_fm_fwd(rows, rows1, slot_ids, dense, dense_w.reshape(-1, D),
-                                             dense_w1.reshape(-1), -1)
+        if fm.fused:   # ONE exchange of [emb | w1 | pad] rows instead of two
+            tab = fm._fused
+            rows = ex.pull(plan, tab.weight, tab.pad, tab.grad_cols)
+            feat, y1, y2, S = k.raw_embed_fm_fwd(rows, None, slot_ids, dense,
+                                                 dense_w.reshape(-1, D), dense_w1.reshape(-1), -1,
+                                                 D=D)
+        else:
+            rows = ex.pull(plan, fm.embedding.weight, fm.embedding.pad)
+            rows1 = ex.pull(plan, fm.embedding_one.weight, fm.embedding_one.pad)
+            feat, y1, y2, S = k.raw_embed_fm_fwd(rows, rows1, slot_ids, dense,
+                                                 dense_w.reshape(-1, D), dense_w1.reshape(-1), -1)
         ctx.save_for_backward(dense, feat, S)
         ctx.plan, ctx.fm, ctx.F = plan, fm, F
         ctx.dense_w_shape = dense_w.shape
@@ -142,37 +151,70 @@ class _ShardedEmbedFM(torch.autograd.Function):
         iota = torch.arange(n + 1, dtype=torch.int32, device=dev)
         num = torch.tensor([n, n], dtype=torch.int32, device=dev)
         # seg_offsets = iota, sorted_pos = inv_perm: row k of the output is the gradient of slot k
-        dW, dW1, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
-                                                          plan.inv_perm, num, F)
-        g = ex.push(plan, dW[:n])
-        g1 = ex.push(plan, dW1[:n].unsqueeze(1))
-        emb, emb1 = fm.embedding, fm.embedding_one
-        emb.accept(ex.owner_reduce(plan, g, emb.num_embeddings, emb.pad))
-        emb1.accept(ex.owner_reduce(plan, g1, emb1.num_embeddings, emb1.pad))
+        if fm.fused:
+            tab = fm._fused
+            dW, _, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
+                                                            plan.inv_perm, num, F,
+                                                            fused_cols=tab.grad_cols)
+            g = ex.push(plan, dW[:n])
+            tab.accept_fused(ex.owner_reduce(plan, g, tab.num_embeddings, tab.pad))
+        else:
+            dW, dW1, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
+                                                              plan.inv_perm, num, F)
+            g = ex.push(plan, dW[:n])
+            g1 = ex.push(plan, dW1[:n].unsqueeze(1))
+            emb, emb1 = fm.embedding, fm.embedding_one
+            emb.accept(ex.owner_reduce(plan, g, emb.num_embeddings, emb.pad))
+            emb1.accept(ex.owner_reduce(plan, g1, emb1.num_embeddings, emb1.pad))
         return None, None, ddense_w.reshape(ctx.dense_w_shape), ddense_w1, None
 
 
-class ShardedFM(tnn.Module):
+class ShardedFusedTable(bnn.FusedTable):
+    """Local shard of a row-cyclically sharded FusedTable."""
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx, rank, world, init_std=None,
+                 device=None):
+        local_pad = None
+        if padding_idx is not None and padding_idx % world == rank:
+            local_pad = padding_idx // world
+        super().__init__(shard_rows(num_embeddings, rank, world), embedding_dim, local_pad,
+                         init_std=init_std, device=device)
+        self.global_rows, self.rank, self.world = num_embeddings, rank, world
+
+
+class ShardedFM(bnn.FusedTableOwner):
     """FM of models/rank/deepfm/net.py:52-139 with both tables sharded (same state_dict names;
-    `embedding*.weight` hold the LOCAL shard)."""
+    `embedding*.weight` hold the LOCAL shard).  With `fused_table` (default when D+1 <= 32) the
+    shard is a FusedTable and every exchange moves [emb | w1 | pad] rows in ONE all-to-all."""
 
     def __init__(self, sparse_feature_number, sparse_feature_dim, dense_feature_dim,
-                 sparse_num_field, rank, world, group=None, device="cuda", kernels=_cuda_ops):
+                 sparse_num_field, rank, world, group=None, device="cuda", kernels=_cuda_ops,
+                 fused_table=None):
         super().__init__()
         self.k = kernels
         self.sparse_feature_number = sparse_feature_number
         self.sparse_feature_dim = sparse_feature_dim
         std = 0.1 / math.sqrt(float(sparse_feature_dim))
-        self.embedding_one = ShardedEmbedding(sparse_feature_number, 1, 0, rank, world,
-                                              init_std=std, device=device)
-        self.embedding = ShardedEmbedding(sparse_feature_number, sparse_feature_dim, 0, rank,
-                                          world, init_std=std, device=device)
+        self.fused = (sparse_feature_dim + 1 <= 32) if fused_table is None else bool(fused_table)
+        if self.fused:
+            self._fused = ShardedFusedTable(sparse_feature_number, sparse_feature_dim, 0, rank,
+                                            world, init_std=std, device=device)
+        else:
+            self.embedding_one = ShardedEmbedding(sparse_feature_number, 1, 0, rank, world,
+                                                  init_std=std, device=device)
+            self.embedding = ShardedEmbedding(sparse_feature_number, sparse_feature_dim, 0, rank,
+                                              world, init_std=std, device=device)
         self.dense_w_one = tnn.Parameter(torch.empty(dense_feature_dim, device=device))
         self.dense_w = tnn.Parameter(
             torch.empty(1, dense_feature_dim, sparse_feature_dim, device=device))
         tnn.init.trunc_normal_(self.dense_w_one, 0.0, std, -2 * std, 2 * std)
         tnn.init.trunc_normal_(self.dense_w, 0.0, std, -2 * std, 2 * std)
         self.exchange = ShardExchange(sparse_feature_number, rank, world, group, kernels)
+
+    def table_grad_dense(self):
+        if self.fused:
+            return self._fused.grad_dense()
+        return (self.embedding.grad_rows.to_dense(), self.embedding_one.grad_rows.to_dense())
 
     def forward(self, sparse_inputs, dense_inputs):
         ids = (torch.cat(list(sparse_inputs), dim=1) if isinstance(sparse_inputs, (list, tuple))
@@ -186,11 +228,11 @@ class ShardedDeepFMLayer(tnn.Module):
 
     def __init__(self, sparse_feature_number, sparse_feature_dim, dense_feature_dim,
                  sparse_num_field, layer_sizes, rank, world, group=None, device="cuda",
-                 kernels=_cuda_ops):
+                 kernels=_cuda_ops, fused_table=None):
         super().__init__()
         from .rank.deepfm import net
         self.fm = ShardedFM(sparse_feature_number, sparse_feature_dim, dense_feature_dim,
-                            sparse_num_field, rank, world, group, device, kernels)
+                            sparse_num_field, rank, world, group, device, kernels, fused_table)
         self.dnn = net.DNN(sparse_feature_number, sparse_feature_dim, dense_feature_dim,
                            dense_feature_dim + sparse_num_field, layer_sizes, device=device)
         self.bias = tnn.Parameter(torch.zeros(1, device=device))

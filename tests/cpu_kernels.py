@@ -23,11 +23,16 @@ class SelectedRows:
     value: torch.Tensor
     num: torch.Tensor
     height: int
+    ncols: int = None
+
+    @property
+    def cols(self):
+        return self.value.shape[1] if self.ncols is None else self.ncols
 
     def to_dense(self):
         U = int(self.num[0])
-        out = torch.zeros(self.height, self.value.shape[1])
-        out[self.rows[:U]] += self.value[:U]
+        out = torch.zeros(self.height, self.cols)
+        out[self.rows[:U]] += self.value[:U, :self.cols]
         return out
 
 
@@ -44,12 +49,15 @@ def raw_shard_bucketize(ids, world, V):
     return local[inv_perm], perm, inv_perm.to(torch.int32), counts
 
 
-def raw_gather(W, ids, pad):
+def raw_gather(W, ids, pad, D=None):
+    W = W if D is None else W[:, :D]
     ok = (ids >= 0) & (ids < W.shape[0]) & (ids != pad)
     return W[ids.clamp(0, max(W.shape[0] - 1, 0))] * ok.unsqueeze(-1).to(W.dtype)
 
 
-def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, pad, want_S=True):
+def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, pad, want_S=True, D=None):
+    if W1 is None:       # fused [emb | w1 | pad] rows
+        W, W1 = W[:, :D], W[:, D]
     e = raw_gather(W, ids, pad)
     e1 = raw_gather(W1.reshape(-1, 1), ids, pad)
     feat = torch.cat([e, dense.unsqueeze(2) * dense_w.unsqueeze(0)], 1)
@@ -84,7 +92,7 @@ def raw_segment_reduce(dOut, seg, pos, num, n):
     return rows
 
 
-def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg, pos, num, F):
+def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg, pos, num, F, fused_cols=0):
     B, N, D = feat.shape
     dfeat = gy2.reshape(B, 1, 1) * (S.unsqueeze(1) - feat)
     if dfeat_dnn is not None:
@@ -96,4 +104,9 @@ def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg, pos, num, F):
     dW1 = raw_segment_reduce(g1, seg, pos, num, n).reshape(-1)
     ddense_w = (dense.unsqueeze(2) * dfeat[:, F:]).sum(0)
     ddense_w1 = (gy1.reshape(B, 1) * dense).sum(0)
+    if fused_cols:
+        fusedW = torch.zeros(dW.shape[0], fused_cols)
+        fusedW[:, :D] = dW
+        fusedW[:, D] = dW1
+        return fusedW, None, ddense_w, ddense_w1
     return dW, dW1, ddense_w, ddense_w1

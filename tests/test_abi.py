@@ -13,7 +13,7 @@ def test_build_and_load():
     path = _lib.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.b200rec_abi_version() == 1
+    assert lib.b200rec_abi_version() == _lib.ABI_VERSION
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -47,7 +47,7 @@ def test_argument_errors_are_reported_not_thrown():
     n = ctypes.c_size_t(0)
     rc = lib.b200rec_group_ids_workspace_bytes(-5, 100, ctypes.byref(n))
     assert rc == -1 and b"n=" in lib.b200rec_last_error()
-    rc = lib.b200rec_gather(None, None, None, 10, 16, 100, -1, None)
+    rc = lib.b200rec_gather(None, 16, None, None, 10, 16, 100, -1, None)
     assert rc == -1 and b"NULL" in lib.b200rec_last_error()
 
 

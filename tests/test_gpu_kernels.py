@@ -336,3 +336,51 @@ def test_tower_mlp_matches_fp64(last_act):
     assert rel_err(xc.grad, xd.grad) < 1e-4
     for a, b in zip(Wc + bc, Wd + bd):
         assert rel_err(a.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("D", [4, 9, 16])
+def test_fused_slot_layout_equals_two_tables(D):
+    """The B200-native fused slot layout ([D emb | w1 | pad] per 128-byte row) must give exactly the
+    same forward and the same gradients as the reference's two-table layout."""
+    ops = _ops()
+    B, F, Dn, V = 65, 26, 13, 300
+    ids, dense, W, W1, dense_w, dense_w1 = make_fm_inputs(B, F, Dn, D, V, seed=40 + D, zipf=True)
+    slot, G = ops.fused_slot(D), ops.fused_grad_cols(D)
+    assert slot == 32 and G % 4 == 0 and G >= D + 1
+    Wf = torch.zeros(V, slot)
+    Wf[:, :D] = W
+    Wf[:, D] = W1[:, 0]
+    Wf[:, D + 1:] = 123.0          # pad columns must never be read
+    args = (ids.to(DEV), dense.to(DEV), dense_w.reshape(Dn, D).to(DEV), dense_w1.to(DEV), 0)
+    f0, y10, y20, S0 = ops.raw_embed_fm_fwd(W.to(DEV), W1.to(DEV), *args)
+    f1, y11, y21, S1 = ops.raw_embed_fm_fwd(Wf.to(DEV), None, *args, D=D)
+    assert torch.equal(f0, f1) and torch.equal(y10, y11) and torch.equal(y20, y21)
+    g = torch.Generator().manual_seed(D)
+    A = torch.randn(B, F + Dn, D, generator=g).to(DEV)
+    g1 = torch.randn(B, generator=g).to(DEV)
+    g2 = torch.randn(B, generator=g).to(DEV)
+    gr = ops.raw_group_ids(ids.to(DEV), V, 0)
+    common = (f0, S0, A, g1, g2, dense.to(DEV), gr.seg_offsets, gr.sorted_pos, gr.num, F)
+    dW, dW1, ddw, ddw1 = ops.raw_embed_fm_bwd(*common)
+    dWf, none, ddwf, _ = ops.raw_embed_fm_bwd(*common, fused_cols=G)
+    U = int(gr.num[0])
+    assert none is None and dWf.shape[1] == G
+    assert torch.equal(dWf[:U, :D], dW[:U]) and torch.equal(dWf[:U, D], dW1[:U])
+    assert not dWf[:U, D + 1:].any() and torch.equal(ddw, ddwf)
+    # gather of the first G columns of a slot table; optimizer on slots == optimizer on two tables
+    rows = ops.raw_gather(Wf.to(DEV), ids.to(DEV), 0, D=G)
+    ref = Wf[ids][..., :G] * (ids != 0).unsqueeze(-1)
+    assert torch.equal(rows.cpu(), ref)
+    sr_f = ops.SelectedRows(gr.unique_ids, dWf, gr.num, V, ncols=G)
+    Wd, md, vd = Wf.to(DEV).clone(), torch.zeros(V, slot, device=DEV), torch.zeros(V, slot, device=DEV)
+    ops.raw_sparse_adam(Wd, md, vd, sr_f, 1e-2, 0.9, 0.999, 1e-8, 0.9, 0.999)
+    Wa, ma, va = W.to(DEV).clone(), torch.zeros(V, D, device=DEV), torch.zeros(V, D, device=DEV)
+    ops.raw_sparse_adam(Wa, ma, va, ops.SelectedRows(gr.unique_ids, dW, gr.num, V), 1e-2, 0.9, 0.999,
+                        1e-8, 0.9, 0.999)
+    Wb, mb, vb = W1.to(DEV).clone(), torch.zeros(V, 1, device=DEV), torch.zeros(V, 1, device=DEV)
+    ops.raw_sparse_adam(Wb, mb, vb, ops.SelectedRows(gr.unique_ids, dW1.unsqueeze(1), gr.num, V),
+                        1e-2, 0.9, 0.999, 1e-8, 0.9, 0.999)
+    assert torch.equal(Wd[:, :D], Wa) and torch.equal(Wd[:, D:D + 1], Wb)
+    assert (Wd[:, G:] == 123.0).all()               # slot padding beyond the gradient columns untouched
+    dense_grad = sr_f.to_dense()
+    assert dense_grad.shape == (V, G) and not dense_grad[0].any()

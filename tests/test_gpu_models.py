@@ -27,7 +27,14 @@ def load_state(layer, g, extra=None):
 def grads_of(layer, extra=None):
     out = {}
     for k, p in layer.named_parameters():
-        if getattr(p, "is_sparse_table", False):
+        if hasattr(p, "fused_D"):    # fused [emb | w1 | pad] slots -> the reference's two keys
+            D, names = p.fused_D, p.fused_names
+            parent = k.rsplit(".", 2)[0] + "." if k.count(".") >= 2 else ""
+            dense = (p.grad_rows.to_dense().cpu().numpy() if p.grad_rows is not None
+                     else np.zeros((p.shape[0], D + 1)))
+            out[parent + names[0]] = dense[:, :D]
+            out[parent + names[1]] = dense[:, D:D + 1]
+        elif getattr(p, "is_sparse_table", False):
             sr = p.grad_rows
             out[k] = sr.to_dense().cpu().numpy() if sr is not None else np.zeros(tuple(p.shape))
         else:
@@ -51,7 +58,8 @@ def check(g, pred, loss, grads, tol=TOL):
 @pytest.mark.parametrize("name", ["deepfm_d9", "deepfm_d16"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("as_list", [True, False])
-def test_deepfm_golden(name, precision, as_list):
+@pytest.mark.parametrize("fused", [True, False])
+def test_deepfm_golden(name, precision, as_list, fused):
     from paddlerec_b200 import functional as BF
     from paddlerec_b200 import nn as bnn
     from paddlerec_b200.rank.deepfm import net
@@ -60,7 +68,7 @@ def test_deepfm_golden(name, precision, as_list):
     fc = [g["param"]["dnn.linear_%d.weight" % i].shape[1] for i in range(2)]
     bnn.set_matmul_precision(precision)
     try:
-        layer = load_state(net.DeepFMLayer(V, D, 13, 26, fc), g)
+        layer = load_state(net.DeepFMLayer(V, D, 13, 26, fc, fused_table=fused), g)
         ids = torch.tensor(g["in"]["ids"], device="cuda")
         dense = torch.tensor(g["in"]["dense"], dtype=torch.float32, device="cuda")
         label = torch.tensor(g["in"]["label"], dtype=torch.float32, device="cuda")

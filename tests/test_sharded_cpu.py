@@ -44,7 +44,7 @@ def _full_problem():
     return p, ids, dense, label
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, fused=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -54,7 +54,7 @@ def _worker(rank, world, port, out_dir):
         p, ids, dense, label = _full_problem()
         torch.manual_seed(100 + rank)   # different init per rank: broadcast must fix the tower
         model = sharded.ShardedDeepFMLayer(V, D, Dn, F, FC, rank, world, device="cpu",
-                                           kernels=cpu_kernels)
+                                           kernels=cpu_kernels, fused_table=fused)
         with torch.no_grad():
             sd = model.state_dict()
             for k, v in p.items():
@@ -70,8 +70,8 @@ def _worker(rank, world, port, out_dir):
         opt.scale_loss(loss).backward()
         opt.step()   # all-reduce of the dense grads only
         res = {"pred": pred.detach().numpy(),
-               "dW": model.fm.embedding.grad_rows.to_dense().numpy(),
-               "dW1": model.fm.embedding_one.grad_rows.to_dense().numpy()}
+               "dW": model.fm.table_grad_dense()[0].numpy(),
+               "dW1": model.fm.table_grad_dense()[1].numpy()}
         for k, v in model.named_parameters():
             if v.grad is not None:
                 res["g:" + k] = v.grad.numpy()
@@ -88,10 +88,10 @@ class _NoStep:
         pass
 
 
-@pytest.mark.parametrize("world", [2])
-def test_sharded_deepfm_matches_oracle(world, tmp_path):
+@pytest.mark.parametrize("world,fused", [(2, True), (2, False)])
+def test_sharded_deepfm_matches_oracle(world, fused, tmp_path):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), fused), nprocs=world, join=True)
     p, ids, dense, label = _full_problem()
     pp = {k: v.double().requires_grad_(True) for k, v in p.items()}
     ids_ok = ids.clone()

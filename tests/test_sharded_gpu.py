@@ -39,8 +39,8 @@ def _worker(rank, world, port, out_dir):
         opt.scale_loss(loss).backward()
         opt.step()
         res = {"pred": pred.detach().cpu().numpy(),
-               "dW": model.fm.embedding.grad_rows.to_dense().cpu().numpy(),
-               "dW1": model.fm.embedding_one.grad_rows.to_dense().cpu().numpy()}
+               "dW": model.fm.table_grad_dense()[0].cpu().numpy(),
+               "dW1": model.fm.table_grad_dense()[1].cpu().numpy()}
         for k, v in model.named_parameters():
             if v.grad is not None:
                 res["g:" + k] = v.grad.cpu().numpy()

@@ -71,6 +71,39 @@ def main():
                 alg = B * (F * 8 + Dn * 4 + F * 4 * D + F * 4 + (F + Dn) * 4 * D + 8)
                 print(json.dumps({"kernel": "embed_fm_fwd", "V": V, "D": D, "dist": dist, "ms": ms,
                                   "GBps": alg / ms / 1e6, "frac": alg / ms / 1e6 / PEAK}), flush=True)
+                if D + 1 <= 32:   # B200-native fused slot layout [D emb | w1 | pad] (128-byte rows)
+                    Wf = torch.zeros(V, 32, device=dev)
+                    Wf[:, :D] = W
+                    Wf[:, D] = W1[:, 0]
+                    msf = time_it(lambda i: ops.raw_embed_fm_fwd(Wf, None, idl[i], den[i], dw, dw1,
+                                                                 0, D=D), nrot)
+                    print(json.dumps({"kernel": "embed_fm_fwd_fused_slots", "V": V, "D": D,
+                                      "dist": dist, "ms": msf, "GBps": alg / msf / 1e6,
+                                      "frac": alg / msf / 1e6 / PEAK}), flush=True)
+                    # lazy Adam: two tables vs one slot table
+                    gr = ops.raw_group_ids(idl[0], V, 0)
+                    n = B * F
+                    gW = torch.randn(n, D, device=dev)
+                    gW1 = torch.randn(n, 1, device=dev)
+                    gF = torch.randn(n, ops.fused_grad_cols(D), device=dev)
+                    m0, v0 = torch.zeros_like(W), torch.zeros_like(W)
+                    m1, v1 = torch.zeros_like(W1), torch.zeros_like(W1)
+                    mf, vf = torch.zeros_like(Wf), torch.zeros_like(Wf)
+                    srW = ops.SelectedRows(gr.unique_ids, gW, gr.num, V)
+                    srW1 = ops.SelectedRows(gr.unique_ids, gW1, gr.num, V)
+                    srF = ops.SelectedRows(gr.unique_ids, gF, gr.num, V, ncols=gF.shape[1])
+                    hp = (1e-3, 0.9, 0.999, 1e-8, 0.9, 0.999)
+
+                    def two(i):
+                        ops.raw_sparse_adam(W, m0, v0, srW, *hp)
+                        ops.raw_sparse_adam(W1, m1, v1, srW1, *hp)
+                    ms2 = time_it(two, 1)
+                    ms1 = time_it(lambda i: ops.raw_sparse_adam(Wf, mf, vf, srF, *hp), 1)
+                    print(json.dumps({"kernel": "lazy_adam_two_tables", "V": V, "D": D,
+                                      "dist": dist, "ms": ms2}), flush=True)
+                    print(json.dumps({"kernel": "lazy_adam_fused_slots", "V": V, "D": D,
+                                      "dist": dist, "ms": ms1}), flush=True)
+                    del Wf, mf, vf, m0, v0, gW, gF
                 # plain gather (Wide&Deep sweep, BASELINE config 5)
                 ms = time_it(lambda i: ops.raw_gather(W, idl[i], -1), nrot)
                 alg = B * F * (8 + 2 * 4 * D)
