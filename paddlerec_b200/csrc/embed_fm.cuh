@@ -14,12 +14,30 @@
 //   * feat is written once with evict-first stores (it is larger than L2 at B=65536).
 #pragma once
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "segreduce.cuh"
 
 namespace b200rec {
 
-constexpr int kFieldUnroll = 8;  // independent row loads in flight per lane
+// Tunables (env B200REC_K1_UNROLL = 8|13|26, B200REC_K1_CACHE = 0|1), read once per process:
+// U = independent row loads in flight per lane; CACHE = let row loads allocate in L1 (useful for
+// the fused slot layout, where the first-order weight sits in the same 128-byte line as the row).
+struct K1Config {
+  int unroll;
+  int cache_rows;
+};
+static K1Config k1_config() {
+  static K1Config cfg = [] {
+    K1Config c{13, -1};
+    if (const char* s = getenv("B200REC_K1_UNROLL")) c.unroll = atoi(s);
+    if (const char* s = getenv("B200REC_K1_CACHE")) c.cache_rows = atoi(s);
+    if (c.unroll != 8 && c.unroll != 13 && c.unroll != 26) c.unroll = 13;
+    return c;
+  }();
+  return cfg;
+}
 
 template <int TPR>
 struct FwdGeom {
@@ -27,7 +45,7 @@ struct FwdGeom {
   static constexpr int kSamples = kThreads / TPR;  // samples per CTA (64 for TPR<=4)
 };
 
-template <int VEC, int TPR>
+template <int VEC, int TPR, int kFieldUnroll, bool CACHE>
 __global__ void __launch_bounds__(FwdGeom<TPR>::kThreads)
 embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
                     const int64_t* __restrict__ ids, const float* __restrict__ dense,
@@ -62,20 +80,29 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
     const int64_t* my_ids = s_ids + (size_t)s * F;
     float* feat_row = feat + (size_t)b * N * D + r * VEC;
     for (int f0 = 0; f0 < F; f0 += kFieldUnroll) {
+      // phase 1: issue every load of the batch (rows AND first-order scalars) before anything
+      // consumes one — an early `first += W1[..]` would stall the in-order warp on each scalar
+      // and serialise the whole batch (ncu source view, profiles/r1a_k1_*).
       Vec<VEC> e[kFieldUnroll];
+      float w1v[kFieldUnroll];
 #pragma unroll
       for (int j = 0; j < kFieldUnroll; ++j) {
         e[j] = vzero<VEC>();
+        w1v[j] = 0.f;
         const int f = f0 + j;
         if (f < F) {
           const int64_t id = my_ids[f];
           const bool in_range = (uint64_t)id < (uint64_t)V;
           const bool live = in_range && id != pad;
-          if (live && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * ldw + r * VEC);
-          if (live && (f & (TPR - 1)) == r) first += __ldg(W1 + (size_t)id * ldw1);
+          if (live && lane_ok) {
+            const float* rp = W + (size_t)id * ldw + r * VEC;
+            e[j] = CACHE ? ld_cached<VEC>(rp) : ld_row<VEC>(rp);
+          }
+          if (live && (f & (TPR - 1)) == r) w1v[j] = ld_row<1>(W1 + (size_t)id * ldw1).v[0];
           if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
         }
       }
+      // phase 2: consume
 #pragma unroll
       for (int j = 0; j < kFieldUnroll; ++j) {
         const int f = f0 + j;
@@ -88,6 +115,8 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
           if (lane_ok) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
         }
       }
+#pragma unroll
+      for (int j = 0; j < kFieldUnroll; ++j) first += w1v[j];
     }
     const float* my_dense = s_dense + (size_t)s * Dn;
     for (int j = 0; j < Dn; ++j) {
@@ -122,6 +151,23 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
   }
 }
 
+struct K1Args {
+  const float* W; const float* W1; const int64_t* ids; const float* dense; const float* dense_w;
+  const float* dense_w1; float* feat; float* y1; float* y2; float* S;
+  int64_t B; int F, Dn, D; int64_t V, pad, ldw, ldw1;
+};
+
+template <int VEC, int TPR, int U, bool C>
+static int k1_launch(const K1Args& a, int64_t grid, size_t smem, cudaStream_t st) {
+  auto kern = embed_fm_fwd_kernel<VEC, TPR, U, C>;
+  if (smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)grid, FwdGeom<TPR>::kThreads, smem, st>>>(
+      a.W, a.W1, a.ids, a.dense, a.dense_w, a.dense_w1, a.feat, a.y1, a.y2, a.S, a.B, a.F, a.Dn, a.D,
+      a.V, a.pad, a.ldw, a.ldw1);
+  return B200REC_OK;
+}
+
 static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* ids,
                                const float* dense, const float* dense_w, const float* dense_w1,
                                float* feat, float* y1, float* y2, float* S, int64_t B, int F,
@@ -143,13 +189,23 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
     const size_t smem = (size_t)SPB * F * sizeof(int64_t) + (size_t)SPB * Dn * sizeof(float);
     B200_REQUIRE(smem <= 200 * 1024, "embed_fm_fwd: F=%d Dn=%d tile does not fit shared memory", F,
                  Dn);
-    auto kern = embed_fm_fwd_kernel<VEC, TPR>;
-    if (smem > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const K1Config cfg = k1_config();
+    // same 128-byte line as the row (fused slot layout)?  then let the row load allocate in L1
+    const bool same_line = (W1 >= W && W1 < W + ldw && ldw1 == ldw);
+    const bool cache = cfg.cache_rows < 0 ? same_line : cfg.cache_rows != 0;
     const int64_t grid = (B + SPB - 1) / SPB;
-    kern<<<(unsigned)grid, FwdGeom<TPR>::kThreads, smem, st>>>(W, W1, ids, dense, dense_w, dense_w1,
-                                                               feat, y1, y2, S, B, F, Dn, D, V, pad, ldw,
-                                                               ldw1);
+    K1Args a{W, W1, ids, dense, dense_w, dense_w1, feat, y1, y2, S, B, F, Dn, D, V, pad, ldw, ldw1};
+    int rc;
+    if (cfg.unroll == 8)
+      rc = cache ? k1_launch<VEC, TPR, 8, true>(a, grid, smem, st)
+                 : k1_launch<VEC, TPR, 8, false>(a, grid, smem, st);
+    else if (cfg.unroll == 26)
+      rc = cache ? k1_launch<VEC, TPR, 26, true>(a, grid, smem, st)
+                 : k1_launch<VEC, TPR, 26, false>(a, grid, smem, st);
+    else
+      rc = cache ? k1_launch<VEC, TPR, 13, true>(a, grid, smem, st)
+                 : k1_launch<VEC, TPR, 13, false>(a, grid, smem, st);
+    if (rc != B200REC_OK) return rc;
   });
   B200_LAUNCH_CHECK();
   return B200REC_OK;

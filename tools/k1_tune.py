@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Times the fused gather+FM forward (K1) for each (unroll, row-cache policy) build-time variant,
+two-table vs fused-slot layout, V=1e8, D=16, B=65536.  One subprocess per env setting."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def child():
+    import torch
+    from paddlerec_b200 import ops
+    dev, B, F, Dn, D, V = "cuda", 65536, 26, 13, 16, 100_000_000
+    g = torch.Generator().manual_seed(1)
+    W = torch.empty(V, D, device=dev).uniform_(-0.05, 0.05)
+    W1 = torch.empty(V, 1, device=dev).uniform_(-0.05, 0.05)
+    Wf = torch.zeros(V, 32, device=dev)
+    Wf[:, :D] = W
+    Wf[:, D] = W1[:, 0]
+    dw = torch.randn(Dn, D, device=dev) * 0.05
+    dw1 = torch.randn(Dn, device=dev) * 0.05
+    ids = [torch.randint(1, V, (B, F), generator=g).to(dev) for _ in range(4)]
+    den = [torch.rand(B, Dn, generator=g).to(dev) for _ in range(4)]
+
+    def t(fn):
+        for i in range(3):
+            fn(i % 4)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(20):
+            fn(i % 4)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 20
+    alg = B * (F * 8 + Dn * 4 + F * 4 * D + F * 4 + (F + Dn) * 4 * D + 8)
+    a = t(lambda i: ops.raw_embed_fm_fwd(W, W1, ids[i], den[i], dw, dw1, 0))
+    b = t(lambda i: ops.raw_embed_fm_fwd(Wf, None, ids[i], den[i], dw, dw1, 0, D=D))
+    print(json.dumps({"unroll": os.environ.get("B200REC_K1_UNROLL"),
+                      "cache": os.environ.get("B200REC_K1_CACHE"),
+                      "two_tables_ms": a, "two_tables_GBps": alg / a / 1e6,
+                      "fused_slots_ms": b, "fused_slots_GBps": alg / b / 1e6}), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "child":
+        child()
+    else:
+        for u in ("8", "13", "26"):
+            for c in ("0", "1"):
+                env = dict(os.environ, B200REC_K1_UNROLL=u, B200REC_K1_CACHE=c)
+                subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
