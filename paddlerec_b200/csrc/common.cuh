@@ -87,6 +87,58 @@ __device__ __forceinline__ Vec<1> ld_row<1>(const float* p) {
   return r;
 }
 
+// Predicated variants: branch-free "load if pred else zeros" (the predicate is a PTX guard, so the
+// compiler cannot turn it into a divergent branch around the volatile asm).  ALLOC selects whether
+// the line may allocate in L1 (rows whose line is re-read by a neighbouring scalar lookup).
+template <int VEC, bool ALLOC>
+__device__ __forceinline__ Vec<VEC> ld_row_pred(const float* p, bool pred);
+#define B200_LD_PRED(VECN, ALLOCB, PTXOP, OUTS, REGS)                                           \
+  template <>                                                                                    \
+  __device__ __forceinline__ Vec<VECN> ld_row_pred<VECN, ALLOCB>(const float* p, bool pred) {    \
+    Vec<VECN> r = vzero_init<VECN>();                                                            \
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %" #REGS ", 0;\n\t@q " PTXOP          \
+                 ";\n\t}"                                                                       \
+                 : OUTS                                                                          \
+                 : "l"(p), "r"((int)pred));                                                      \
+    return r;                                                                                    \
+  }
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> vzero_init() {
+  Vec<VEC> r;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) r.v[i] = 0.f;
+  return r;
+}
+#define B200_OUT4 "+f"(r.v[0]), "+f"(r.v[1]), "+f"(r.v[2]), "+f"(r.v[3])
+#define B200_OUT2 "+f"(r.v[0]), "+f"(r.v[1])
+#define B200_OUT1 "+f"(r.v[0])
+B200_LD_PRED(4, false, "ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4]", B200_OUT4, 5)
+B200_LD_PRED(4, true, "ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4]", B200_OUT4, 5)
+B200_LD_PRED(2, false, "ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2]", B200_OUT2, 3)
+B200_LD_PRED(2, true, "ld.global.nc.v2.f32 {%0,%1}, [%2]", B200_OUT2, 3)
+B200_LD_PRED(1, false, "ld.global.nc.L1::no_allocate.f32 %0, [%1]", B200_OUT1, 2)
+B200_LD_PRED(1, true, "ld.global.nc.f32 %0, [%1]", B200_OUT1, 2)
+#undef B200_LD_PRED
+
+// cp.async (LDGSTS) helpers: global -> shared without register staging
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // cached read (small broadcast operands: dense_w, S rows, bias)
 template <int VEC>
 __device__ __forceinline__ Vec<VEC> ld_cached(const float* p);

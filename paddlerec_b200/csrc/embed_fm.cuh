@@ -21,18 +21,22 @@
 
 namespace b200rec {
 
-// Tunables (env B200REC_K1_UNROLL = 8|13|26, B200REC_K1_CACHE = 0|1), read once per process:
+// Tunables (env B200REC_K1_UNROLL = 8|13|26, B200REC_K1_CACHE = 0|1, B200REC_K1_CTAS = persistent
+// CTAs per SM), read once per process:
 // U = independent row loads in flight per lane; CACHE = let row loads allocate in L1 (useful for
 // the fused slot layout, where the first-order weight sits in the same 128-byte line as the row).
 struct K1Config {
   int unroll;
   int cache_rows;
+  int ctas_per_sm;
 };
 static K1Config k1_config() {
   static K1Config cfg = [] {
-    K1Config c{13, -1};
+    K1Config c{13, 0, 8};
     if (const char* s = getenv("B200REC_K1_UNROLL")) c.unroll = atoi(s);
     if (const char* s = getenv("B200REC_K1_CACHE")) c.cache_rows = atoi(s);
+    if (const char* s = getenv("B200REC_K1_CTAS")) c.ctas_per_sm = atoi(s);
+    if (c.ctas_per_sm < 1 || c.ctas_per_sm > 16) c.ctas_per_sm = 8;
     if (c.unroll != 8 && c.unroll != 13 && c.unroll != 26) c.unroll = 13;
     return c;
   }();
@@ -41,10 +45,15 @@ static K1Config k1_config() {
 
 template <int TPR>
 struct FwdGeom {
-  static constexpr int kThreads = TPR >= 4 ? 256 : 64 * TPR;
-  static constexpr int kSamples = kThreads / TPR;  // samples per CTA (64 for TPR<=4)
+  static constexpr int kThreads = 128;
+  static constexpr int kSamples = kThreads / TPR;  // samples per tile (32 at D=16)
 };
 
+// Persistent CTAs: each loops over tiles of kSamples samples (static stride).  While tile t is
+// processed, the ids/dense of tile t+gridDim.x stream into the other shared-memory buffer with
+// cp.async, so the id round trip is off the critical path.  Per tile and lane: all row loads and
+// first-order lookups of a batch of kFieldUnroll fields are issued (predicated PTX, no branches)
+// before the first one is consumed.
 template <int VEC, int TPR, int kFieldUnroll, bool CACHE>
 __global__ void __launch_bounds__(FwdGeom<TPR>::kThreads)
 embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
@@ -56,99 +65,115 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
   constexpr int kThreads = FwdGeom<TPR>::kThreads;
   constexpr int SPB = FwdGeom<TPR>::kSamples;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int64_t* s_ids = reinterpret_cast<int64_t*>(smem_raw);  // [SPB*F]
-  float* s_dense = reinterpret_cast<float*>(s_ids + (size_t)SPB * F);  // [SPB*Dn]
+  const size_t ids_elems = (size_t)SPB * F;
+  const size_t dense_elems = (size_t)SPB * Dn;
+  const size_t buf_bytes = (ids_elems * 8 + dense_elems * 4 + 15) / 16 * 16;
 
-  const int64_t b0 = (int64_t)blockIdx.x * SPB;
-  const int nb = (int)min((int64_t)SPB, B - b0);
-  for (int i = threadIdx.x; i < nb * F; i += kThreads) s_ids[i] = ids[b0 * F + i];
-  for (int i = threadIdx.x; i < nb * Dn; i += kThreads) s_dense[i] = dense[b0 * Dn + i];
-  __syncthreads();
-
+  const int64_t ntiles = (B + SPB - 1) / SPB;
   const int s = threadIdx.x / TPR;
   const int r = threadIdx.x % TPR;
-  const bool sample_ok = s < nb;
   const bool lane_ok = r * VEC < D;
-  const int64_t b = b0 + s;
   const int N = F + Dn;
 
-  Vec<VEC> Ssum = vzero<VEC>();
-  Vec<VEC> Q = vzero<VEC>();
-  float first = 0.f;
+  auto stage = [&](int64_t tile, int buf) {
+    int64_t* s_ids = reinterpret_cast<int64_t*>(smem_raw + (size_t)buf * buf_bytes);
+    float* s_dense = reinterpret_cast<float*>(s_ids + ids_elems);
+    const int64_t b0 = tile * SPB;
+    const int nb = (int)min((int64_t)SPB, B - b0);
+    for (int i = threadIdx.x; i < nb * F; i += kThreads) cp_async_8(s_ids + i, ids + b0 * F + i);
+    for (int i = threadIdx.x; i < nb * Dn; i += kThreads)
+      cp_async_4(s_dense + i, dense + b0 * Dn + i);
+  };
 
-  if (sample_ok) {
-    const int64_t* my_ids = s_ids + (size_t)s * F;
-    float* feat_row = feat + (size_t)b * N * D + r * VEC;
-    for (int f0 = 0; f0 < F; f0 += kFieldUnroll) {
-      // phase 1: issue every load of the batch (rows AND first-order scalars) before anything
-      // consumes one — an early `first += W1[..]` would stall the in-order warp on each scalar
-      // and serialise the whole batch (ncu source view, profiles/r1a_k1_*).
-      Vec<VEC> e[kFieldUnroll];
-      float w1v[kFieldUnroll];
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) stage(tile, 0);
+  cp_async_commit();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) stage(next, (it + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();  // everything but the newest group (the next tile) has landed
+    __syncthreads();
+
+    const int64_t* s_ids = reinterpret_cast<const int64_t*>(smem_raw + (size_t)(it & 1) * buf_bytes);
+    const float* s_dense = reinterpret_cast<const float*>(s_ids + ids_elems);
+    const int64_t b0 = tile * SPB;
+    const int nb = (int)min((int64_t)SPB, B - b0);
+    const bool sample_ok = s < nb;
+    const int64_t b = b0 + s;
+
+    Vec<VEC> Ssum = vzero<VEC>();
+    Vec<VEC> Q = vzero<VEC>();
+    float first = 0.f;
+
+    if (sample_ok) {
+      const int64_t* my_ids = s_ids + (size_t)s * F;
+      float* feat_row = feat + (size_t)b * N * D + r * VEC;
+      for (int f0 = 0; f0 < F; f0 += kFieldUnroll) {
+        Vec<VEC> e[kFieldUnroll];
+        float w1v[kFieldUnroll];
+        // phase 1: issue every load of the batch before anything consumes one
 #pragma unroll
-      for (int j = 0; j < kFieldUnroll; ++j) {
-        e[j] = vzero<VEC>();
-        w1v[j] = 0.f;
-        const int f = f0 + j;
-        if (f < F) {
-          const int64_t id = my_ids[f];
+        for (int j = 0; j < kFieldUnroll; ++j) {
+          const int f = f0 + j;
+          const int64_t id = (f < F) ? my_ids[f] : pad;
           const bool in_range = (uint64_t)id < (uint64_t)V;
-          const bool live = in_range && id != pad;
-          if (live && lane_ok) {
-            const float* rp = W + (size_t)id * ldw + r * VEC;
-            e[j] = CACHE ? ld_cached<VEC>(rp) : ld_row<VEC>(rp);
-          }
-          if (live && (f & (TPR - 1)) == r) w1v[j] = ld_row<1>(W1 + (size_t)id * ldw1).v[0];
-          if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
+          const bool live = (f < F) && in_range && id != pad;
+          const size_t row = live ? (size_t)id : 0;
+          e[j] = ld_row_pred<VEC, CACHE>(W + row * ldw + r * VEC, live && lane_ok);
+          w1v[j] = ld_row_pred<1, true>(W1 + row * ldw1, live && ((f & (TPR - 1)) == r)).v[0];
+          if ((f < F) && !in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
         }
-      }
-      // phase 2: consume
+        // phase 2: consume
 #pragma unroll
-      for (int j = 0; j < kFieldUnroll; ++j) {
-        const int f = f0 + j;
-        if (f < F) {
+        for (int j = 0; j < kFieldUnroll; ++j) {
+          const int f = f0 + j;
+          if (f < F) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            Ssum.v[k] += e[j].v[k];
-            Q.v[k] = fmaf(e[j].v[k], e[j].v[k], Q.v[k]);
+            for (int k = 0; k < VEC; ++k) {
+              Ssum.v[k] += e[j].v[k];
+              Q.v[k] = fmaf(e[j].v[k], e[j].v[k], Q.v[k]);
+            }
+            if (lane_ok) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
           }
-          if (lane_ok) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
         }
-      }
 #pragma unroll
-      for (int j = 0; j < kFieldUnroll; ++j) first += w1v[j];
+        for (int j = 0; j < kFieldUnroll; ++j) first += w1v[j];
+      }
+      const float* my_dense = s_dense + (size_t)s * Dn;
+      for (int j = 0; j < Dn; ++j) {
+        const float x = my_dense[j];
+        Vec<VEC> e = vzero<VEC>();
+        if (lane_ok) {
+          const Vec<VEC> w = ld_cached<VEC>(dense_w + (size_t)j * D + r * VEC);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) e.v[k] = x * w.v[k];
+          st_stream<VEC>(feat_row + (size_t)(F + j) * D, e);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          Ssum.v[k] += e.v[k];
+          Q.v[k] = fmaf(e.v[k], e.v[k], Q.v[k]);
+        }
+        if ((j & (TPR - 1)) == r) first = fmaf(x, __ldg(dense_w1 + j), first);
+      }
     }
-    const float* my_dense = s_dense + (size_t)s * Dn;
-    for (int j = 0; j < Dn; ++j) {
-      const float x = my_dense[j];
-      Vec<VEC> e = vzero<VEC>();
-      if (lane_ok) {
-        const Vec<VEC> w = ld_cached<VEC>(dense_w + (size_t)j * D + r * VEC);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) e.v[k] = x * w.v[k];
-        st_stream<VEC>(feat_row + (size_t)(F + j) * D, e);
-      }
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        Ssum.v[k] += e.v[k];
-        Q.v[k] = fmaf(e.v[k], e.v[k], Q.v[k]);
-      }
-      if ((j & (TPR - 1)) == r) first = fmaf(x, __ldg(dense_w1 + j), first);
-    }
-  }
 
-  float t = 0.f;
+    float t = 0.f;
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) t += Ssum.v[k] * Ssum.v[k] - Q.v[k];
-  t = group_sum<TPR>(t);
-  first = group_sum<TPR>(first);
-  if (sample_ok) {
-    if (r == 0) {
-      y1[b] = first;
-      y2[b] = 0.5f * t;
+    for (int k = 0; k < VEC; ++k) t += Ssum.v[k] * Ssum.v[k] - Q.v[k];
+    t = group_sum<TPR>(t);
+    first = group_sum<TPR>(first);
+    if (sample_ok) {
+      if (r == 0) {
+        y1[b] = first;
+        y2[b] = 0.5f * t;
+      }
+      if (S != nullptr && lane_ok) st_plain<VEC>(S + (size_t)b * D + r * VEC, Ssum);
     }
-    if (S != nullptr && lane_ok) st_plain<VEC>(S + (size_t)b * D + r * VEC, Ssum);
+    __syncthreads();  // buffer (it&1) is free for the prefetch issued two iterations later
   }
+  cp_async_wait<0>();
 }
 
 struct K1Args {
@@ -186,14 +211,17 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
   if (B == 0) return B200REC_OK;
   B200_DISPATCH_ROW_SHAPE(rs, {
     constexpr int SPB = FwdGeom<TPR>::kSamples;
-    const size_t smem = (size_t)SPB * F * sizeof(int64_t) + (size_t)SPB * Dn * sizeof(float);
+    const size_t buf = ((size_t)SPB * F * sizeof(int64_t) + (size_t)SPB * Dn * sizeof(float) + 15) /
+                       16 * 16;
+    const size_t smem = 2 * buf;
     B200_REQUIRE(smem <= 200 * 1024, "embed_fm_fwd: F=%d Dn=%d tile does not fit shared memory", F,
                  Dn);
     const K1Config cfg = k1_config();
     // same 128-byte line as the row (fused slot layout)?  then let the row load allocate in L1
     const bool same_line = (W1 >= W && W1 < W + ldw && ldw1 == ldw);
     const bool cache = cfg.cache_rows < 0 ? same_line : cfg.cache_rows != 0;
-    const int64_t grid = (B + SPB - 1) / SPB;
+    const int64_t ntiles = (B + SPB - 1) / SPB;
+    const int64_t grid = min(ntiles, (int64_t)sm_count() * cfg.ctas_per_sm);
     K1Args a{W, W1, ids, dense, dense_w, dense_w1, feat, y1, y2, S, B, F, Dn, D, V, pad, ldw, ldw1};
     int rc;
     if (cfg.unroll == 8)

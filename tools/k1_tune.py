@@ -41,6 +41,7 @@ def child():
     b = t(lambda i: ops.raw_embed_fm_fwd(Wf, None, ids[i], den[i], dw, dw1, 0, D=D))
     print(json.dumps({"unroll": os.environ.get("B200REC_K1_UNROLL"),
                       "cache": os.environ.get("B200REC_K1_CACHE"),
+                      "ctas_per_sm": os.environ.get("B200REC_K1_CTAS"),
                       "two_tables_ms": a, "two_tables_GBps": alg / a / 1e6,
                       "fused_slots_ms": b, "fused_slots_GBps": alg / b / 1e6}), flush=True)
 
@@ -49,7 +50,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for u in ("8", "13", "26"):
+        for u, ctas in (("8", "4"), ("8", "5"), ("8", "8"), ("13", "3"), ("13", "4"), ("13", "8"),
+                        ("26", "2")):
             for c in ("0", "1"):
-                env = dict(os.environ, B200REC_K1_UNROLL=u, B200REC_K1_CACHE=c)
+                env = dict(os.environ, B200REC_K1_UNROLL=u, B200REC_K1_CACHE=c,
+                           B200REC_K1_CTAS=ctas)
                 subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
