@@ -158,6 +158,22 @@ int b200rec_cross_v2_bwd(const float* dout, const float* x0, const float* xw, co
                          float* dxw, float* dx0, float* dbias, int64_t B, int C,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K4: DIN attention pooling (forward) ---------------------------------- */
+/* Replaces the attention unit + masked softmax + pooling of DINLayer.forward,
+ * models/rank/din/net.py:155-173, for the reader's tiled target (dinReader.py:85-90):
+ *   a[b,l]  = MLP([h, t, h-t, h*t]),  MLP = Linear(4E,80)-sigmoid-Linear(80,40)-sigmoid-Linear(40,1)
+ *   w[b,:]  = softmax_l((a[b,:] + mask[b,:]) * scale)            (mask added BEFORE the scale)
+ *   out[b,:] = sum_l w[b,l] * hist[b,l,:]
+ * with the first layer re-associated:  [h,t,h-t,h*t] W1 = h Wac + (h*t) Wd + tb,
+ *   Wac = W1[0:E] + W1[2E:3E],  Wd = W1[3E:4E],  tb = t (W1[E:2E] - W1[2E:3E]) + b1   ([B,80], by
+ * the caller: one small library GEMM per step).  hist [B,L,E], tseq [B,E], mask int64 [B,L]
+ * (0 / -1e9, may be NULL), scores/weights [B,L] (scratch / saved softmax), out [B,E].
+ * E % 4 == 0, E <= 128; hidden sizes are the reference's fixed 80 and 40. */
+int b200rec_din_attn_fwd(const float* hist, const float* tseq, const float* tb, const float* Wac,
+                         const float* Wd, const float* W2, const float* b2, const float* W3,
+                         const float* b3, const int64_t* mask, float* scores, float* weights,
+                         float* out, int64_t B, int L, int E, float scale, void* stream);
+
 /* ---- tower epilogues (bf16 hi/lo split operands for the tensor-core GEMMs) -- */
 /* The MLP tower (DNN.forward, models/rank/deepfm/net.py:169-174) runs its GEMMs on the bf16 tensor
  * cores as a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32 accumulate).  These fuse everything

@@ -43,7 +43,7 @@ KERNELS_PER_CALL = {
     "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
     "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
-    "tower_prep_weight": 1, "tower_fold_dw": 1,
+    "tower_prep_weight": 1, "tower_fold_dw": 1, "din_attn_fwd": 2,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
 EVENTS = None
@@ -496,8 +496,92 @@ class _CrossV2(torch.autograd.Function):
         return dx0, dxl, dW, dbias, None
 
 
-# K4 (DIN attention pooling) is wired in by din_attention_fwd once the kernel is in the library.
-HAVE_DIN_ATTN = False
+# ---- K4: DIN attention pooling ------------------------------------------------------------------
+HAVE_DIN_ATTN = True
+
+
+def raw_din_attn_fwd(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    """hist [B,L,E], tseq [B,E] (tiled target), mask int64 [B,L(,1)] or None.
+    Returns (out [B,E], weights [B,L])."""
+    lib = _lib.load()
+    hist = _req(hist, torch.float32, "hist")
+    tseq = _req(tseq, torch.float32, "tseq")
+    B, L, E = hist.shape
+    W1 = W1.detach()
+    Wa, Wb, Wc, Wd = W1[0:E], W1[E:2 * E], W1[2 * E:3 * E], W1[3 * E:4 * E]
+    Wac = (Wa + Wc).contiguous()
+    Wd = Wd.contiguous()
+    tb = torch.addmm(b1.detach(), tseq, Wb - Wc)            # [B,80]: the per-sample t-term
+    if mask is not None:
+        mask = _req(mask.reshape(B, L), torch.int64, "mask")
+    dev = hist.device
+    scores = torch.empty(B, L, dtype=torch.float32, device=dev)
+    weights = torch.empty(B, L, dtype=torch.float32, device=dev)
+    out = torch.empty(B, E, dtype=torch.float32, device=dev)
+    check(lib.b200rec_din_attn_fwd(ptr(hist), ptr(tseq), ptr(tb), ptr(Wac), ptr(Wd),
+                                   ptr(_req(W2.detach(), torch.float32, "W2")), ptr(b2.detach()),
+                                   ptr(_req(W3.detach().reshape(-1), torch.float32, "W3")),
+                                   ptr(b3.detach()), ptr(mask), ptr(scores), ptr(weights), ptr(out),
+                                   B, L, E, float(E) ** -0.5, _stream()), "din_attn_fwd")
+    _count("din_attn_fwd")
+    return out, weights
+
+
+def _din_attention_composite(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    """The reference's op sequence (din/net.py:155-173) in torch — used to differentiate."""
+    E = hist.shape[2]
+    t = tseq.unsqueeze(1).expand_as(hist)
+    c = torch.cat([hist, t, hist - t, hist * t], dim=2)
+    a = torch.sigmoid(c @ W1 + b1)
+    a = torch.sigmoid(a @ W2 + b2)
+    a = a @ W3 + b3
+    if mask is not None:
+        a = a + mask.reshape(a.shape).to(a.dtype)
+    w = torch.softmax(a.transpose(1, 2) * (E ** -0.5), dim=-1)
+    return torch.matmul(w, hist).reshape(-1, E)
+
+
+class _DinAttn(torch.autograd.Function):
+    """Forward: the fused K4 kernels.  Backward (this round): re-runs the reference's op sequence
+    under autograd on chunks of samples (bounded memory) — the fused backward kernel is listed as
+    next in DESIGN.md."""
+
+    CHUNK_BYTES = 256 << 20
+
+    @staticmethod
+    def forward(ctx, hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+        out, _w = raw_din_attn_fwd(hist, tseq, mask, W1, b1, W2, b2, W3, b3)
+        ctx.save_for_backward(hist, tseq, W1, b1, W2, b2, W3, b3)
+        ctx.mask = mask
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        hist, tseq, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
+        B, L, E = hist.shape
+        per_sample = L * 4 * E * 4 * 3
+        chunk = max(1, min(B, _DinAttn.CHUNK_BYTES // max(per_sample, 1)))
+        params = [p.detach().requires_grad_(True) for p in (W1, b1, W2, b2, W3, b3)]
+        dhist = torch.empty_like(hist)
+        dtseq = torch.empty_like(tseq)
+        pgrads = [torch.zeros_like(p) for p in params]
+        for s in range(0, B, chunk):
+            e = min(B, s + chunk)
+            h = hist[s:e].detach().requires_grad_(True)
+            t = tseq[s:e].detach().requires_grad_(True)
+            m = ctx.mask[s:e] if ctx.mask is not None else None
+            with torch.enable_grad():
+                o = _din_attention_composite(h, t, m, *params)
+            gs = torch.autograd.grad(o, [h, t] + params, dout[s:e])
+            dhist[s:e] = gs[0]
+            dtseq[s:e] = gs[1]
+            for acc, g in zip(pgrads, gs[2:]):
+                acc += g
+        return (dhist, dtseq, None, *pgrads)
+
+
+def din_attention(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    return _DinAttn.apply(hist, tseq, mask, W1, b1, W2, b2, W3, b3)
 
 
 def embed_fm(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink, D=None):

@@ -41,8 +41,9 @@ class _MLP3(tnn.Module):
 class DINLayer(tnn.Module):
     def __init__(self, item_emb_size, cat_emb_size, act, is_sparse, use_DataLoader, item_count,
                  cat_count, device="cuda", faithful_frozen_attention=True,
-                 tiled_target_seq=True):
+                 tiled_target_seq=True, fused_attention=True):
         super().__init__()
+        self.fused_attention = fused_attention
         self.item_emb_size, self.cat_emb_size = item_emb_size, cat_emb_size
         self.item_count, self.cat_count = item_count, cat_count
         self.tiled_target_seq = tiled_target_seq
@@ -72,10 +73,12 @@ class DINLayer(tnn.Module):
         """net.py:155-173 on already gathered rows.  hist [B,L,E]; tseq [B,E] (tiled) or [B,L,E];
         mask [B,L,1] (0 / -1e9, any dtype).  Returns [B,E]."""
         att = self.attention
-        if ops.HAVE_DIN_ATTN and hist.is_cuda and not torch.is_grad_enabled():
-            return ops.din_attention_fwd(hist, tseq, mask, att.linear_0.weight, att.linear_0.bias,
-                                         att.linear_1.weight, att.linear_1.bias,
-                                         att.linear_2.weight, att.linear_2.bias)
+        if (ops.HAVE_DIN_ATTN and self.fused_attention and hist.is_cuda and tseq.dim() == 2
+                and hist.shape[2] % 4 == 0 and hist.shape[2] <= 128
+                and att.linear_0.out_features == 80 and att.linear_1.out_features == 40):
+            return ops.din_attention(hist.contiguous(), tseq.contiguous(), mask,
+                                     att.linear_0.weight, att.linear_0.bias, att.linear_1.weight,
+                                     att.linear_1.bias, att.linear_2.weight, att.linear_2.bias)
         if tseq.dim() == 2:
             tseq = tseq.unsqueeze(1).expand_as(hist)
         concat = torch.cat([hist, tseq, hist - tseq, hist * tseq], dim=2)

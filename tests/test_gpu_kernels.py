@@ -384,3 +384,46 @@ def test_fused_slot_layout_equals_two_tables(D):
     assert (Wd[:, G:] == 123.0).all()               # slot padding beyond the gradient columns untouched
     dense_grad = sr_f.to_dense()
     assert dense_grad.shape == (V, G) and not dense_grad[0].any()
+
+
+@pytest.mark.parametrize("B,L,E", [(1, 1, 16), (5, 7, 16), (3, 100, 128), (2, 152, 128), (70, 13, 64)])
+def test_din_attention_fused_forward_and_grads(B, L, E):
+    """K4 against the reference's op sequence (din/net.py:155-173) in float64; the autograd node
+    (fused forward, composite backward) must also give the right gradients."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + L + E)
+    hist = torch.randn(B, L, E, generator=g) * 0.5
+    tseq = torch.randn(B, E, generator=g) * 0.5
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    lens[0] = L
+    mask = torch.zeros(B, L, 1, dtype=torch.int64)
+    for b in range(B):
+        mask[b, int(lens[b]):] = int(-1e9)
+    W1 = torch.randn(4 * E, 80, generator=g) / (4 * E) ** 0.5
+    b1 = torch.randn(80, generator=g) * 0.1
+    W2 = torch.randn(80, 40, generator=g) / 80 ** 0.5
+    b2 = torch.randn(40, generator=g) * 0.1
+    W3 = torch.randn(40, 1, generator=g) / 40 ** 0.5
+    b3 = torch.randn(1, generator=g) * 0.1
+    params = [W1, b1, W2, b2, W3, b3]
+    ref_in = [t.double().requires_grad_(True) for t in [hist, tseq] + params]
+    ref = ops._din_attention_composite(ref_in[0], ref_in[1], mask, *ref_in[2:])
+    gout = torch.randn(B, E, generator=g)
+    (ref * gout.double()).sum().backward()
+    dev_in = [t.to(DEV).requires_grad_(True) for t in [hist, tseq] + params]
+    out = ops.din_attention(dev_in[0], dev_in[1], mask.to(DEV), *dev_in[2:])
+    assert rel_err(out, ref) < 2e-5
+    out_nomask = ops.raw_din_attn_fwd(hist.to(DEV), tseq.to(DEV), None, *[p.to(DEV) for p in params])[0]
+    ref_nomask = ops._din_attention_composite(hist.double(), tseq.double(), None,
+                                              *[p.double() for p in params])
+    assert rel_err(out_nomask, ref_nomask) < 2e-5
+    (out * gout.to(DEV)).sum().backward()
+    for a, b in zip(dev_in, ref_in):
+        if float(b.grad.abs().max()) < 1e-12:
+            assert float(a.grad.abs().max()) < 1e-6
+        else:
+            assert rel_err(a.grad, b.grad) < 1e-4
+    w = ops.raw_din_attn_fwd(hist.to(DEV), tseq.to(DEV), mask.to(DEV), *[p.to(DEV) for p in params])[1]
+    assert rel_err(w.sum(1).cpu(), torch.ones(B)) < 1e-5
+    for b in range(B):
+        assert float(w[b, int(lens[b]):].abs().sum()) == 0.0     # masked positions get zero weight
