@@ -224,18 +224,33 @@ def run_b200(args, rank, world, local_rank):
 
     scale = optimizer.scale_loss if hasattr(optimizer, "scale_loss") else (lambda x: x)
 
+    prefetch = getattr(model, "prefetch", None)
+
     def step_resident(i):
         label, ids, dense = resident[i % len(resident)]
         optimizer.clear_grad()
         pred = model(ids, dense)
+        if prefetch is not None:   # plan the NEXT batch's exchange while this step computes
+            prefetch(resident[(i + 1) % len(resident)][1])
         loss = dm.create_loss(pred, label_f[i % len(resident)])
         scale(loss).backward()
         optimizer.step()
         return loss
 
+    pending = {"feeds": None}
+
     def step_e2e(i):
+        """Public API (DygraphModel.create_feeds / create_loss) with HOST batches: the H2D copy of
+        batch i+1 is issued while step i computes (one copy per step, inside the timed region) and
+        the loss is read back every step."""
+        feeds = pending["feeds"] or dm.create_feeds(host[i % len(host)], config)
+        label, ids, dense = feeds
         optimizer.clear_grad()
-        loss, _, _ = dm.train_forward(model, None, host[i % len(host)], config)
+        pred = model(ids, dense)
+        loss = dm.create_loss(pred, label)
+        pending["feeds"] = dm.create_feeds(host[(i + 1) % len(host)], config)
+        if prefetch is not None:
+            prefetch(pending["feeds"][1])
         scale(loss).backward()
         optimizer.step()
         return loss.item()  # D2H read of the step's result

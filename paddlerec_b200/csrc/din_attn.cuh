@@ -37,8 +37,13 @@ struct DinSmem {
     const size_t EP = E + 4;
     return 2 * (size_t)kDinH1 * EP            // WacT, WdT  [80][EP]
            + (size_t)kDinH1 * kDinH2          // W2s [80][40]
-           + 2 * (size_t)kDinTile * EP        // hs, hts [64][EP]  (hts is reused for z1s [64][81])
+           + (size_t)kDinTile * EP            // hs [64][EP]
+           + hts_floats(E)                    // hts [64][EP], reused for z1s [64][81]
            + 2 * kDinH2 + 8;                  // b2, W3
+  }
+  static __host__ __device__ size_t hts_floats(int E) {
+    const size_t EP = E + 4;
+    return (size_t)kDinTile * (EP > (size_t)(kDinH1 + 1) ? EP : (size_t)(kDinH1 + 1));
   }
 };
 
@@ -57,7 +62,7 @@ din_scores_kernel(const float* __restrict__ hist, const float* __restrict__ tseq
   float* hs = W2s + kDinH1 * kDinH2;              // [64][EP]
   float* hts = hs + (size_t)kDinTile * EP;        // [64][EP]
   float* z1s = hts;                               // [64][81]  (after GEMM1)
-  float* b2s = hts + (size_t)kDinTile * EP;       // [40]
+  float* b2s = hts + DinSmem::hts_floats(E);      // [40]
   float* W3s = b2s + kDinH2;                      // [40]
 
   const int tid = threadIdx.x;

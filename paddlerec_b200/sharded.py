@@ -48,20 +48,65 @@ class ExchangePlan:
     recv_ids: torch.Tensor    # int64 [m]: local rows requested from this rank (owner view)
 
 
+class _PendingPlan:
+    """Bucketing + count exchange of a FUTURE batch, running on a side stream."""
+
+    def __init__(self, ids, send_ids, perm, inv_perm, host_counts, event):
+        self.ids, self.send_ids, self.perm, self.inv_perm = ids, send_ids, perm, inv_perm
+        self.host_counts, self.event = host_counts, event
+
+
 class ShardExchange:
-    """The all-to-all choreography; shared by every table that is looked up with the same ids."""
+    """The all-to-all choreography; shared by every table that is looked up with the same ids.
+
+    The split sizes of the id exchange must be known on the host.  `plan()` alone therefore costs a
+    device->host sync per step, which also drains the launch queue (the CPU can no longer run
+    ahead of the GPU).  `prefetch(ids_next)` removes it: bucketing, the count all-to-all and the
+    D2H copy of the NEXT batch run on a side stream while the current step computes; by the time
+    `plan(ids_next)` is called the counts are already on the host."""
 
     def __init__(self, V: int, rank: int, world: int, group=None, kernels=_cuda_ops):
         self.V, self.rank, self.world, self.group, self.k = V, rank, world, group, kernels
+        self._pending = None
+        self._side = None
 
-    def plan(self, ids: torch.Tensor) -> ExchangePlan:
-        ids = ids.reshape(-1)
-        n = ids.numel()
+    def _bucketize_and_count(self, ids):
         send_ids, perm, inv_perm, counts = self.k.raw_shard_bucketize(ids, self.world, self.V)
         recv_counts = torch.empty_like(counts)
         dist.all_to_all_single(recv_counts, counts, group=self.group)
-        both = torch.stack([counts, recv_counts]).cpu()      # the one host sync of the exchange
-        send_splits, recv_splits = both[0].tolist(), both[1].tolist()
+        return send_ids, perm, inv_perm, torch.stack([counts, recv_counts])
+
+    def prefetch(self, ids: torch.Tensor) -> None:
+        """Start planning the exchange of a future batch (CUDA only; a no-op on CPU tensors)."""
+        if not ids.is_cuda:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=ids.device)
+        flat = ids.reshape(-1)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            send_ids, perm, inv_perm, both = self._bucketize_and_count(flat)
+            host = torch.empty(both.shape, dtype=both.dtype, pin_memory=True)
+            host.copy_(both, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        for t in (flat, send_ids, perm, inv_perm, both):
+            t.record_stream(self._side)
+        self._pending = _PendingPlan(ids, send_ids, perm, inv_perm, host, ev)
+
+    def plan(self, ids: torch.Tensor) -> ExchangePlan:
+        pend, self._pending = self._pending, None
+        flat = ids.reshape(-1)
+        n = flat.numel()
+        if pend is not None and pend.ids is ids:
+            pend.event.synchronize()                              # normally long complete
+            torch.cuda.current_stream().wait_event(pend.event)
+            send_ids, perm, inv_perm = pend.send_ids, pend.perm, pend.inv_perm
+            send_splits, recv_splits = pend.host_counts[0].tolist(), pend.host_counts[1].tolist()
+        else:
+            send_ids, perm, inv_perm, both = self._bucketize_and_count(flat)
+            both = both.cpu()                                     # host sync (no prefetch)
+            send_splits, recv_splits = both[0].tolist(), both[1].tolist()
         recv_ids = torch.empty(sum(recv_splits), dtype=torch.int64, device=ids.device)
         dist.all_to_all_single(recv_ids, send_ids, recv_splits, send_splits, group=self.group)
         return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, recv_ids)
@@ -242,6 +287,10 @@ class ShardedDeepFMLayer(tnn.Module):
     def forward(self, sparse_inputs, dense_inputs):
         y1, y2, feat = self.fm(sparse_inputs, dense_inputs)
         return torch.sigmoid(y1 + y2 + self.dnn(feat))
+
+    def prefetch(self, next_sparse_inputs) -> None:
+        """Hint: the ids of the NEXT batch (the very tensor that will be passed to forward)."""
+        self.fm.exchange.prefetch(next_sparse_inputs)
 
 
 def dense_parameters(model: tnn.Module) -> List[torch.Tensor]:
