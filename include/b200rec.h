@@ -193,6 +193,29 @@ int b200rec_tower_prep_weight(const float* W, void* W2r_bf16, void* W2c_bf16, vo
                               int K, int N, void* stream);
 int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream);
 
+/* Backward of b200rec_din_attn_fwd.  Inputs as forward plus the saved softmax `weights` and
+ * dout [B,E].  Outputs: dhist [B,L,E]; dtseq [B,E] = the (h*t)-path part of d/dtseq; dtb [B,80] =
+ * d/d(tb); dWac, dWd [E,80]; dW2 [80,40]; db2 [40]; dW3 [40]; da [B,L] scratch (d/d(pre-mask
+ * score)).  The caller finishes the t-path with two small library GEMMs:
+ *   dtseq += dtb (Wb-Wc)^T,  Gt = tseq^T dtb,  dW1 = [dWac ; Gt ; dWac-Gt ; dWd],  db1 = sum_b dtb.
+ * dtseq/dtb are accumulated with float atomics (a few adds per element; not bit-reproducible);
+ * the weight gradients are reduced in a fixed order (deterministic). */
+int b200rec_din_attn_bwd_workspace_bytes(int64_t B, int L, int E, size_t* bytes_host);
+int b200rec_din_attn_bwd(const float* hist, const float* tseq, const float* tb, const float* Wac,
+                         const float* Wd, const float* W2, const float* b2, const float* W3,
+                         const float* weights, const float* dout, float* da, float* dhist,
+                         float* dtseq, float* dtb, float* dWac, float* dWd, float* dW2, float* db2,
+                         float* dW3, int64_t B, int L, int E, float scale, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- continuous_value_model (GPUBox branch) -------------------------------- */
+/* models/rank/wide_deep/net.py:81-88: x [N,D+2] (cols 0,1 = show, click).
+ * use_cvm=1: y [N,D+2], y0=log(x0+1), y1=log(x1+1)-y0, rest copied; use_cvm=0: y [N,D] = x[:,2:].
+ * backward: dx[:,2:] = dy[:, (2|0):], dx[:,0:2] = show_click[:,0:2]. */
+int b200rec_cvm_fwd(const float* x, float* y, int64_t N, int D, int use_cvm, void* stream);
+int b200rec_cvm_bwd(const float* dy, const float* show_click, float* dx, int64_t N, int D,
+                    int use_cvm, void* stream);
+
 /* ---- K5: row-cyclic sharding helpers (owner = id mod world) --------------- */
 /* Stable bucketing of n ids by owner rank (bucket order = owner-major, original order inside).
  *   send_ids[k]   local row (id div world) of the k-th id in bucket order; -1 if out of range

@@ -95,6 +95,11 @@ _SIG = {
     "b200rec_cross_bwd_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_cross_v2_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "b200rec_din_attn_fwd": (c_int, [_P] * 13 + [c_int64, c_int, c_int, c_float, _P]),
+    "b200rec_din_attn_bwd_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "b200rec_din_attn_bwd": (c_int, [_P] * 19 + [c_int64, c_int, c_int, c_float, _P, c_size_t,
+                                                  _P]),
+    "b200rec_cvm_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
+    "b200rec_cvm_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "b200rec_tower_split": (c_int, [_P, _P, c_int, _P, c_int64, c_int, _P]),
     "b200rec_tower_bwd_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_tower_relu_bwd_split": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),

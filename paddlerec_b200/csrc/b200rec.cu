@@ -11,6 +11,7 @@
 #include "cross.cuh"
 #include "shard.cuh"
 #include "tower.cuh"
+#include "cvm.cuh"
 #include "din_attn.cuh"
 
 namespace b200rec {
@@ -272,6 +273,29 @@ int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream
   NOT_NULL(Mx); NOT_NULL(dW);
   const int64_t total = (int64_t)K * N;
   tower_fold_dw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(Mx, dW, K, N);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_cvm_fwd(const float* x, float* y, int64_t N, int D, int use_cvm, void* stream) {
+  B200_REQUIRE(N >= 0 && D > 0, "cvm_fwd: bad sizes");
+  if (N == 0) return B200REC_OK;
+  NOT_NULL(x); NOT_NULL(y);
+  const int64_t total = N * (use_cvm ? D + 2 : D);
+  const unsigned grid = (unsigned)min((total + 255) / 256, (int64_t)sm_count() * 16);
+  cvm_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(x, y, N, D, use_cvm);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_cvm_bwd(const float* dy, const float* show_click, float* dx, int64_t N, int D,
+                    int use_cvm, void* stream) {
+  B200_REQUIRE(N >= 0 && D > 0, "cvm_bwd: bad sizes");
+  if (N == 0) return B200REC_OK;
+  NOT_NULL(dy); NOT_NULL(show_click); NOT_NULL(dx);
+  const int64_t total = N * (D + 2);
+  const unsigned grid = (unsigned)min((total + 255) / 256, (int64_t)sm_count() * 16);
+  cvm_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(dy, show_click, dx, N, D, use_cvm);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

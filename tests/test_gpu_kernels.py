@@ -427,3 +427,23 @@ def test_din_attention_fused_forward_and_grads(B, L, E):
     assert rel_err(w.sum(1).cpu(), torch.ones(B)) < 1e-5
     for b in range(B):
         assert float(w[b, int(lens[b]):].abs().sum()) == 0.0     # masked positions get zero weight
+
+
+@pytest.mark.parametrize("use_cvm", [False, True])
+def test_cvm(use_cvm):
+    """continuous_value_model against oracle/nets.py:cvm (forward) and Paddle's documented
+    cvm_grad semantics (show/click written into the first two gradient columns)."""
+    ops = _ops()
+    N, D = 1000, 11
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(N, D + 2, generator=g) * 5
+    sc = torch.rand(N, 2, generator=g) * 3
+    xd = x.to(DEV).requires_grad_(True)
+    y = ops.continuous_value_model(xd, sc.to(DEV), use_cvm)
+    ref = nets.cvm(x.double(), use_cvm)
+    assert y.shape == ref.shape and rel_err(y, ref) < 1e-6
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy.to(DEV))
+    dx = xd.grad.cpu()
+    assert torch.equal(dx[:, :2], sc)
+    assert torch.equal(dx[:, 2:], dy[:, 2:] if use_cvm else dy)
