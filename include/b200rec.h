@@ -113,12 +113,21 @@ int b200rec_gather(const float* W, int64_t ldw, const int64_t* ids, float* out, 
                    int64_t V, int64_t padding_idx, void* stream);
 /* rows[u,:] = sum_{p in segment u} dOut[p,:]  — the SelectedRows merge of
  * lookup_table_v2_grad.  Deterministic (fixed order inside a segment); ids occurring more than
- * 64 times are reduced by a whole CTA each (skew-proof). */
+ * 64 times are reduced by whole CTAs (skew-proof).  row_of_pos (may be NULL) redirects position p to
+ * row row_of_pos[p] of dOut (pooled lookups: many positions share one output row). */
 int b200rec_segment_reduce_workspace_bytes(int64_t n, int D, size_t* bytes_host);
-int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
-                           const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
-                           int64_t n, int D, void* workspace, size_t workspace_bytes,
-                           void* stream);
+int b200rec_segment_reduce(const float* dOut, const int32_t* row_of_pos,
+                           const int32_t* seg_offsets, const int32_t* sorted_pos,
+                           const int32_t* num_unique, float* rows, int64_t n, int D,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* Multi-hot slots (LoD): out[bag,:] = sum_{i in [offsets[bag], offsets[bag+1])} W[keys[i],:D]
+ * (sequence_pool(sum) after sparse_embedding, models/rank/slot_dnn/net.py:63-75; the pooling half
+ * of fused_seqpool_cvm, tools/utils/static_ps/model_util.py:411-415).  Empty bags give zeros.
+ * bag_of_pos (int32 [nnz], may be NULL) receives the owning bag of every key position: pass it as
+ * `row_of_pos` to b200rec_segment_reduce (with dOut = d/d(out)) for the backward. */
+int b200rec_gather_pool_sum(const float* W, int64_t ldw, const int64_t* keys,
+                            const int64_t* offsets, float* out, int32_t* bag_of_pos, int64_t n_bags,
+                            int D, int64_t V, int64_t padding_idx, void* stream);
 /* dW[unique_ids[u],:] += rows[u,:] into a dense [V,D] gradient (small tables / tests). */
 int b200rec_rows_to_dense(const int64_t* unique_ids, const float* rows, int64_t ld_rows,
                           const int32_t* num_unique, float* dW, int64_t ld_dw, int64_t n, int D,

@@ -81,7 +81,9 @@ _SIG = {
                                      _P]),
     "b200rec_gather": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int64, c_int64, _P]),
     "b200rec_segment_reduce_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
-    "b200rec_segment_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "b200rec_segment_reduce": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "b200rec_gather_pool_sum": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_int64,
+                                        c_int64, _P]),
     "b200rec_rows_to_dense": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int64,
                                       _P]),
     "b200rec_sparse_sgd": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int, c_int64,

@@ -141,13 +141,23 @@ int b200rec_segment_reduce_workspace_bytes(int64_t n, int D, size_t* bytes_host)
   return B200REC_OK;
 }
 
-int b200rec_segment_reduce(const float* dOut, const int32_t* seg_offsets,
-                           const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
-                           int64_t n, int D, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+int b200rec_gather_pool_sum(const float* W, int64_t ldw, const int64_t* keys,
+                            const int64_t* offsets, float* out, int32_t* bag_of_pos, int64_t n_bags,
+                            int D, int64_t V, int64_t padding_idx, void* stream) {
+  B200_REQUIRE(n_bags >= 0 && D > 0 && V > 0, "gather_pool_sum: bad sizes");
+  if (n_bags > 0) { NOT_NULL(W); NOT_NULL(offsets); NOT_NULL(out); }
+  return launch_gather_pool(W, keys, offsets, out, bag_of_pos, n_bags, D, V, padding_idx, ldw,
+                            ST(stream));
+}
+
+int b200rec_segment_reduce(const float* dOut, const int32_t* row_of_pos,
+                           const int32_t* seg_offsets, const int32_t* sorted_pos,
+                           const int32_t* num_unique, float* rows, int64_t n, int D,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   B200_REQUIRE(n >= 0 && D > 0, "segment_reduce: bad sizes");
   if (n > 0) { NOT_NULL(dOut); NOT_NULL(seg_offsets); NOT_NULL(sorted_pos); NOT_NULL(num_unique); NOT_NULL(rows); NOT_NULL(workspace); }
-  return launch_segment_reduce(dOut, seg_offsets, sorted_pos, num_unique, rows, n, D, workspace,
+  return launch_segment_reduce(dOut, row_of_pos, seg_offsets, sorted_pos, num_unique, rows, n, D,
+                               workspace,
                                workspace_bytes, ST(stream));
 }
 

@@ -66,23 +66,104 @@ static int launch_gather(const float* W, const int64_t* ids, float* out, int64_t
   return B200REC_OK;
 }
 
+// ---- multi-hot slots: gather + sum-pool over variable-length key lists (LoD) -----------------
+// Reference: sequence_pool(sum) after sparse_embedding, models/rank/slot_dnn/net.py:63-75, and the
+// fused_seqpool_cvm call sites tools/utils/static_ps/model_util.py:411-415,465-469.  One lane
+// group per bag; empty bags give zeros (pad_value 0); padding / out-of-range keys are skipped.
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_pool_kernel(const float* __restrict__ W, const int64_t* __restrict__ keys,
+                   const int64_t* __restrict__ offsets, float* __restrict__ out, int64_t n_bags,
+                   int D, int64_t V, int64_t pad, int64_t ldw) {
+  constexpr int GPB = kGatherThreads / TPR;
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  for (int64_t bag = (int64_t)blockIdx.x * GPB + threadIdx.x / TPR; bag < n_bags;
+       bag += (int64_t)gridDim.x * GPB) {
+    const int64_t beg = offsets[bag], end = offsets[bag + 1];
+    Vec<VEC> acc = vzero<VEC>();
+    int64_t i = beg;
+    for (; i + 1 < end; i += 2) {  // two rows in flight
+      const int64_t k0 = __ldg(keys + i), k1 = __ldg(keys + i + 1);
+      const bool ok0 = (uint64_t)k0 < (uint64_t)V && k0 != pad;
+      const bool ok1 = (uint64_t)k1 < (uint64_t)V && k1 != pad;
+      const Vec<VEC> a = ld_row_pred<VEC, false>(W + (size_t)(ok0 ? k0 : 0) * ldw + r * VEC,
+                                                 ok0 && lane_ok);
+      const Vec<VEC> b = ld_row_pred<VEC, false>(W + (size_t)(ok1 ? k1 : 0) * ldw + r * VEC,
+                                                 ok1 && lane_ok);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc.v[k] = (acc.v[k] + a.v[k]) + b.v[k];
+      if (r == 0 && ((uint64_t)k0 >= (uint64_t)V)) atomicAdd(&g_oob_count, 1ull);
+      if (r == 0 && ((uint64_t)k1 >= (uint64_t)V)) atomicAdd(&g_oob_count, 1ull);
+    }
+    if (i < end) {
+      const int64_t k0 = __ldg(keys + i);
+      const bool ok0 = (uint64_t)k0 < (uint64_t)V && k0 != pad;
+      const Vec<VEC> a = ld_row_pred<VEC, false>(W + (size_t)(ok0 ? k0 : 0) * ldw + r * VEC,
+                                                 ok0 && lane_ok);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc.v[k] += a.v[k];
+      if (r == 0 && ((uint64_t)k0 >= (uint64_t)V)) atomicAdd(&g_oob_count, 1ull);
+    }
+    if (lane_ok) st_stream<VEC>(out + (size_t)bag * D + r * VEC, acc);
+  }
+}
+
+// bag_of_pos[i] = bag that owns key position i (for the pooled backward)
+__global__ void bag_of_positions_kernel(const int64_t* __restrict__ offsets, int64_t n_bags,
+                                        int32_t* __restrict__ bag_of_pos) {
+  const int64_t bag = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bag >= n_bags) return;
+  for (int64_t i = offsets[bag]; i < offsets[bag + 1]; ++i) bag_of_pos[i] = (int32_t)bag;
+}
+
+static int launch_gather_pool(const float* W, const int64_t* keys, const int64_t* offsets,
+                              float* out, int32_t* bag_of_pos, int64_t n_bags, int D, int64_t V,
+                              int64_t pad, int64_t ldw, cudaStream_t st) {
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "gather_pool: unsupported D=%d", D);
+  B200_REQUIRE(ldw >= D && ldw % rs.vec == 0, "gather_pool: bad row stride %lld", (long long)ldw);
+  const int align = rs.vec * 4;
+  B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % align == 0 &&
+                   reinterpret_cast<uintptr_t>(out) % align == 0,
+               "gather_pool: W/out must be %d-byte aligned", align);
+  if (n_bags == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int GPB = kGatherThreads / TPR;
+    const int64_t want = (n_bags + GPB - 1) / GPB;
+    const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 64);
+    gather_pool_kernel<VEC, TPR><<<grid, kGatherThreads, 0, st>>>(W, keys, offsets, out, n_bags, D, V,
+                                                                  pad, ldw);
+  });
+  B200_LAUNCH_CHECK();
+  if (bag_of_pos != nullptr) {
+    bag_of_positions_kernel<<<(unsigned)((n_bags + 255) / 256), 256, 0, st>>>(offsets, n_bags,
+                                                                              bag_of_pos);
+    B200_LAUNCH_CHECK();
+  }
+  return B200REC_OK;
+}
+
 // rows[u,:] = sum over the segment of dOut[sorted_pos[i],:], fixed order (segreduce.cuh).
 struct PlainRowContrib {
   const float* dOut;
+  const int32_t* row_of_pos;  // nullptr: dOut row = position; else dOut row = row_of_pos[position]
   int D;
   template <int VEC>
   __device__ __forceinline__ void add(int p, int r, bool lane_ok, Vec<VEC>& acc, float&) const {
     if (lane_ok) {
-      const Vec<VEC> a = ld_row<VEC>(dOut + (size_t)p * D + r * VEC);
+      const size_t row = row_of_pos ? (size_t)__ldg(row_of_pos + p) : (size_t)p;
+      const Vec<VEC> a = ld_row<VEC>(dOut + row * D + r * VEC);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc.v[k] += a.v[k];
     }
   }
 };
 
-static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
-                                 const int32_t* sorted_pos, const int32_t* num_unique, float* rows,
-                                 int64_t n, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int launch_segment_reduce(const float* dOut, const int32_t* row_of_pos,
+                                 const int32_t* seg_offsets, const int32_t* sorted_pos,
+                                 const int32_t* num_unique, float* rows, int64_t n, int D, void* ws,
+                                 size_t ws_bytes, cudaStream_t st) {
   RowShape rs;
   B200_REQUIRE(pick_row_shape(D, &rs), "segment_reduce: unsupported D=%d", D);
   const int align = rs.vec * 4;
@@ -96,7 +177,7 @@ static int launch_segment_reduce(const float* dOut, const int32_t* seg_offsets,
   }
   int rc = B200REC_OK;
   B200_DISPATCH_ROW_SHAPE(rs, {
-    PlainRowContrib contrib{dOut, D};
+    PlainRowContrib contrib{dOut, row_of_pos, D};
     rc = launch_seg_reduce<VEC, TPR, PlainRowContrib>(seg_offsets, sorted_pos, num_unique, contrib,
                                                       rows, nullptr, SegOut{D, 1, 0}, n, D, ws,
                                                       st);

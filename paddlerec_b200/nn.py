@@ -176,6 +176,11 @@ class Embedding(tnn.Module):
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
         return ops.gather(self.weight, ids, self.pad, self, _autograd_hook(ids.device))
 
+    def forward_pooled(self, keys: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+        """Multi-hot slot: sum of the rows of each variable-length key list (LoD offsets)."""
+        return ops.gather_pool_sum(self.weight, keys, offsets, self.pad, self,
+                                   _autograd_hook(keys.device))
+
     def clear_grad(self) -> None:
         self.weight.grad_rows = None
 

@@ -43,7 +43,7 @@ KERNELS_PER_CALL = {
     "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
     "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
-    "tower_prep_weight": 1, "tower_fold_dw": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "cvm_fwd": 1, "cvm_bwd": 1,
+    "tower_prep_weight": 1, "tower_fold_dw": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
 EVENTS = None
@@ -241,7 +241,27 @@ def raw_gather(W: torch.Tensor, ids: torch.Tensor, padding_idx: int,
     return out
 
 
-def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int) -> torch.Tensor:
+def raw_gather_pool_sum(W, keys, offsets, padding_idx: int, D: Optional[int] = None):
+    """Sum-pooled lookup of variable-length key lists.  keys int64 [nnz], offsets int64
+    [n_bags+1].  Returns (out [n_bags, D], bag_of_pos int32 [nnz])."""
+    lib = _lib.load()
+    W = _req(W, torch.float32, "W")
+    keys = _req(keys, torch.int64, "keys").reshape(-1)
+    offsets = _req(offsets, torch.int64, "offsets").reshape(-1)
+    V, ldw = W.shape
+    D = ldw if D is None else D
+    n_bags = offsets.numel() - 1
+    out = torch.empty(n_bags, D, dtype=torch.float32, device=W.device)
+    bag_of_pos = torch.empty(max(keys.numel(), 1), dtype=torch.int32, device=W.device)
+    check(lib.b200rec_gather_pool_sum(ptr(W), ldw, ptr(keys), ptr(offsets), ptr(out),
+                                      ptr(bag_of_pos), n_bags, D, V, int(padding_idx), _stream()),
+          "gather_pool_sum")
+    _count("gather_pool_sum")
+    return out, bag_of_pos
+
+
+def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int,
+                       row_of_pos=None) -> torch.Tensor:
     lib = _lib.load()
     dOut = _req(dOut, torch.float32, "dOut")
     D = dOut.shape[-1]
@@ -249,8 +269,8 @@ def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int) 
     nbytes = ctypes.c_size_t(0)
     check(lib.b200rec_segment_reduce_workspace_bytes(n, D, ctypes.byref(nbytes)), "segment_reduce_ws")
     ws = workspace(nbytes.value, dOut.device, "segred")
-    check(lib.b200rec_segment_reduce(ptr(dOut), ptr(groups_seg), ptr(groups_pos), ptr(num),
-                                     ptr(rows), n, D, ptr(ws), ws.numel(), _stream()),
+    check(lib.b200rec_segment_reduce(ptr(dOut), ptr(row_of_pos), ptr(groups_seg), ptr(groups_pos),
+                                     ptr(num), ptr(rows), n, D, ptr(ws), ws.numel(), _stream()),
           "segment_reduce")
     _count("segment_reduce")
     return rows
@@ -472,6 +492,30 @@ class _Gather(torch.autograd.Function):
                                   groups.sorted_pos, groups.num, groups.n)
         ctx.sink.accept(SelectedRows(groups.unique_ids, rows, groups.num, ctx.V))
         return None, None, None, None, None
+
+
+class _GatherPool(torch.autograd.Function):
+    """sparse_embedding + sequence_pool(sum) over LoD key lists (slot_dnn/net.py:63-75)."""
+
+    @staticmethod
+    def forward(ctx, W, keys, offsets, padding_idx, sink, _hook):
+        out, bag_of_pos = raw_gather_pool_sum(W, keys, offsets, padding_idx)
+        ctx.save_for_backward(keys, bag_of_pos)
+        ctx.padding_idx, ctx.sink, ctx.V = padding_idx, sink, W.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        keys, bag_of_pos = ctx.saved_tensors
+        groups = raw_group_ids(keys, ctx.V, ctx.padding_idx)
+        rows = raw_segment_reduce(dout.contiguous(), groups.seg_offsets, groups.sorted_pos,
+                                  groups.num, groups.n, row_of_pos=bag_of_pos)
+        ctx.sink.accept(SelectedRows(groups.unique_ids, rows, groups.num, ctx.V))
+        return None, None, None, None, None, None
+
+
+def gather_pool_sum(W, keys, offsets, padding_idx, sink, hook):
+    return _GatherPool.apply(W, keys, offsets, padding_idx, sink, hook)
 
 
 class _CrossV2(torch.autograd.Function):

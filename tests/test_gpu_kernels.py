@@ -447,3 +447,34 @@ def test_cvm(use_cvm):
     dx = xd.grad.cpu()
     assert torch.equal(dx[:, :2], sc)
     assert torch.equal(dx[:, 2:], dy[:, 2:] if use_cvm else dy)
+
+
+@pytest.mark.parametrize("D", [8, 9, 16, 64])
+def test_gather_pool_sum_lod(D):
+    """Multi-hot slots: sum-pooled lookups over LoD key lists (empty bags, padding keys, hot keys)
+    and their backward through the shared segmented reduce."""
+    from paddlerec_b200 import nn as bnn
+    ops = _ops()
+    V, n_bags = 200, 300
+    g = torch.Generator().manual_seed(D)
+    lens = torch.randint(0, 6, (n_bags,), generator=g)
+    lens[5] = 0
+    lens[7] = 150                                   # one long bag
+    offsets = torch.zeros(n_bags + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(lens, 0)
+    nnz = int(offsets[-1])
+    keys = torch.randint(0, V, (nnz,), generator=g)
+    keys[::9] = 17                                   # a hot key (>64 occurrences)
+    emb = bnn.Embedding(V, D, padding_idx=0, init_std=0.1, device=DEV)
+    W = emb.weight.detach().cpu().double()
+    out = emb.forward_pooled(keys.to(DEV), offsets.to(DEV))
+    ref = torch.zeros(n_bags, D, dtype=torch.float64)
+    Wr = W.clone().requires_grad_(True)
+    rows = Wr[keys] * (keys != 0).unsqueeze(1)
+    ref = torch.zeros(n_bags, D, dtype=torch.float64).index_add(
+        0, torch.repeat_interleave(torch.arange(n_bags), lens), rows)
+    assert rel_err(out, ref) < 2e-6 and not out[5].any()
+    gout = torch.randn(n_bags, D, generator=g)
+    (out * gout.to(DEV)).sum().backward()
+    (ref * gout.double()).sum().backward()
+    assert rel_err(emb.grad_rows.to_dense(), Wr.grad) < 3e-6
