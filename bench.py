@@ -296,6 +296,12 @@ def run_b200(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath) and args.dim == 16 and args.batch == 65536:
+        with open(tpath) as fh:
+            t = json.load(fh)
+        traffic = t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
     alg = algorithmic_bytes_fwd(args.dim) * args.batch
     achieved = alg / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
     line = {
@@ -307,7 +313,8 @@ def run_b200(args, rank, world, local_rank):
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
-                     "kernel_share_of_step": kernel_ms / (ms / K), "traffic": None,
+                     "kernel_share_of_step": kernel_ms / (ms / K), "traffic": traffic,
+                     "traffic_source": "profiles/k1_traffic.json (ncu --set full, one launch)",
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": args.batch * (F_SPARSE * 8 + N_DENSE * 4 + 8),
