@@ -139,20 +139,65 @@ class ShardExchange:
         return self.k.SelectedRows(groups.unique_ids, rows, groups.num, V_loc)
 
 
+class _ShardedLookup(torch.autograd.Function):
+    """paddle.nn.Embedding forward/backward over a row-cyclically sharded table: the generic
+    (non-FM) lookup used by DCN-V2 / Wide&Deep / DIN when their tables are sharded."""
+
+    @staticmethod
+    def forward(ctx, ids, emb, _hook):
+        ex, k = emb.exchange, emb.exchange.k
+        plan = ex.plan(ids)
+        rows = ex.pull(plan, emb.weight, emb.pad)                  # [n, D] in bucket order
+        out = k.raw_gather(rows, plan.perm, -1)                    # back to position order
+        ctx.plan, ctx.emb = plan, emb
+        return out.reshape(*ids.shape, rows.shape[1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan, emb = ctx.plan, ctx.emb
+        ex, k = emb.exchange, emb.exchange.k
+        D = dout.shape[-1]
+        g = k.raw_gather(dout.reshape(-1, D).contiguous(), plan.inv_perm.to(torch.int64), -1)
+        g = ex.push(plan, g)
+        emb.accept(ex.owner_reduce(plan, g, emb.num_embeddings, emb.pad))
+        return None, None, None
+
+
 class ShardedEmbedding(bnn.Embedding):
-    """The local shard ([ceil((V-rank)/world), D]) of a row-cyclically sharded table."""
+    """The local shard ([ceil((V-rank)/world), D]) of a row-cyclically sharded table.  `forward`
+    has paddle.nn.Embedding's signature; the all-to-all exchange happens inside."""
 
     def __init__(self, num_embeddings, embedding_dim, padding_idx, rank, world, init_std=None,
-                 init="truncated_normal", device=None):
+                 init="truncated_normal", device=None, group=None, kernels=_cuda_ops):
         local_pad = None
         if padding_idx is not None and padding_idx % world == rank:
             local_pad = padding_idx // world
         super().__init__(shard_rows(num_embeddings, rank, world), embedding_dim, local_pad,
                          init_std=init_std, init=init, device=device)
         self.global_rows, self.rank, self.world = num_embeddings, rank, world
+        self.exchange = ShardExchange(num_embeddings, rank, world, group, kernels)
 
     def forward(self, ids):
-        raise RuntimeError("a sharded table is looked up through ShardExchange")
+        return _ShardedLookup.apply(ids, self, bnn._autograd_hook(ids.device))
+
+
+@torch.no_grad()
+def shard_embeddings(model: tnn.Module, rank: int, world: int, group=None, min_rows: int = 0,
+                     kernels=_cuda_ops) -> tnn.Module:
+    """Replace every `bnn.Embedding` of `model` whose table has >= min_rows rows by the local
+    shard of a row-cyclic ShardedEmbedding (rows rank, rank+world, ... of the original, so a
+    replicated initialisation stays consistent), then broadcast the dense parameters.  This is how
+    DCN-V2 (BASELINE config 3), Wide&Deep and large-vocabulary DIN run on N GPUs."""
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if type(child) is bnn.Embedding and child.num_embeddings >= min_rows:
+                sh = ShardedEmbedding(child.num_embeddings, child.embedding_dim, child.padding_idx,
+                                      rank, world, init="empty", device=child.weight.device,
+                                      group=group, kernels=kernels)
+                sh.weight.copy_(child.weight[rank::world])
+                setattr(parent, name, sh)
+    sync_dense_parameters(model, group)
+    return model
 
 
 class _ShardedEmbedFM(torch.autograd.Function):

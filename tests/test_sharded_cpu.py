@@ -120,3 +120,61 @@ def test_shard_rows_partition():
     for V_ in (1, 7, 8, 9, 100000001):
         for w in (1, 2, 4, 8):
             assert sum(shard_rows(V_, r, w) for r in range(w)) == V_
+
+
+def _dcn_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import nn as bnn
+        from paddlerec_b200 import sharded
+        from paddlerec_b200.rank.wide_deep import net
+        from tests.util import load_golden
+        g = load_golden("wide_deep")
+        Vg, Dg = g["param"]["embedding.weight"].shape
+        fc = [g["param"]["linear_%d.weight" % i].shape[1] for i in range(2)]
+        torch.manual_seed(7 + rank)
+        model = net.WideDeepLayer(Vg, Dg, 13, 26, fc, device="cpu")
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(torch.tensor(g["param"][k], dtype=torch.float32))
+        # the plain gather of bnn.Embedding is CUDA-only; the sharded lookup takes the stand-in
+        sharded.shard_embeddings(model, rank, world, kernels=cpu_kernels)
+        ids = torch.tensor(g["in"]["ids"])
+        dense = torch.tensor(g["in"]["dense"], dtype=torch.float32)
+        label = torch.tensor(g["in"]["label"], dtype=torch.float32)
+        Bg = ids.shape[0] // world * world
+        per = Bg // world
+        sl = slice(rank * per, (rank + 1) * per)
+        pred = model(ids[sl], dense[sl])
+        loss = BF.log_loss(pred, label[sl]).sum() / Bg       # global-batch mean
+        loss.backward()
+        np.savez(os.path.join(out_dir, "wd%d.npz" % rank), pred=pred.detach().numpy(),
+                 dW=model.embedding.grad_rows.to_dense().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_embeddings_generic_lookup(tmp_path):
+    """shard_embeddings() on Wide&Deep: the generic sharded lookup (exchange + gather) must give the
+    single-process predictions and table gradients (golden truncated to a multiple of world)."""
+    from tests.util import load_golden, to_params, slots
+    world = 2
+    mp.spawn(_dcn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = load_golden("wide_deep")
+    p = to_params(g["param"])
+    ids = torch.tensor(g["in"]["ids"])
+    Bg = ids.shape[0] // world * world
+    dense = torch.tensor(g["in"]["dense"], dtype=torch.float64)[:Bg]
+    label = torch.tensor(g["in"]["label"], dtype=torch.float64)[:Bg]
+    pred = nets.wide_deep_forward(p, slots(ids[:Bg]), dense, 2)
+    nets.log_loss(pred, label).mean().backward()
+    per = Bg // world
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "wd%d.npz" % rank))
+        np.testing.assert_allclose(r["pred"], pred.detach().numpy()[rank * per:(rank + 1) * per],
+                                   rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(r["dW"], p["embedding.weight"].grad.numpy()[rank::world],
+                                   rtol=2e-4, atol=1e-7)

@@ -73,3 +73,65 @@ def test_sharded_deepfm_nccl(world, tmp_path):
             if not k.startswith("fm.embedding"):
                 np.testing.assert_allclose(r["g:" + k], pp[k].grad.numpy(), rtol=1e-4, atol=1e-7,
                                            err_msg=k)
+
+
+def _dcn_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import sharded
+        from paddlerec_b200.rank.dcn_v2 import net
+        from tests.util import load_golden
+        dev = torch.device("cuda", rank)
+        g = load_golden("dcn_v2_v2_stacked")
+        Vg, Dg = g["param"]["embedding.weight"].shape
+        fc = [g["param"]["DNN_.linear_%d.weight" % i].shape[1] for i in range(2)]
+        torch.manual_seed(3 + rank)
+        model = net.DCN_V2Layer(Vg, Dg, 13, 26, fc, 2, True, False, 6, 4, device=dev)
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(torch.tensor(g["param"][k], dtype=torch.float32))
+        sharded.shard_embeddings(model, rank, world)
+        model.eval()
+        ids = torch.tensor(g["in"]["ids"])
+        Bg = ids.shape[0] // world * world
+        per = Bg // world
+        sl = slice(rank * per, (rank + 1) * per)
+        dense = torch.tensor(g["in"]["dense"], dtype=torch.float32)
+        label = torch.tensor(g["in"]["label"], dtype=torch.float32)
+        pred = model(ids[sl].to(dev), dense[sl].to(dev))
+        loss = BF.log_loss(pred, label[sl].to(dev)).sum() / Bg
+        loss.backward()
+        np.savez(os.path.join(out_dir, "dcn%d.npz" % rank), pred=pred.detach().cpu().numpy(),
+                 dW=model.embedding.grad_rows.to_dense().cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_dcn_v2_nccl(tmp_path):
+    """BASELINE config 3 in miniature: DCN-V2 with its table row-sharded over 2 GPUs."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    from tests.util import load_golden, slots, to_params
+    mp.spawn(_dcn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = load_golden("dcn_v2_v2_stacked")
+    p = to_params(g["param"])
+    ids = torch.tensor(g["in"]["ids"])
+    Bg = ids.shape[0] // world * world
+    dense = torch.tensor(g["in"]["dense"], dtype=torch.float64)[:Bg]
+    label = torch.tensor(g["in"]["label"], dtype=torch.float64)[:Bg]
+    pred = nets.dcn_v2_forward(p, slots(ids[:Bg]), dense, n_fc=2, cross_num=2, is_stacked=True,
+                               use_low_rank_mixture=False)
+    nets.log_loss(pred, label).mean().backward()
+    per = Bg // world
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "dcn%d.npz" % rank))
+        np.testing.assert_allclose(r["pred"], pred.detach().numpy()[rank * per:(rank + 1) * per],
+                                   rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(r["dW"], p["embedding.weight"].grad.numpy()[rank::world],
+                                   rtol=1e-4, atol=1e-7)
