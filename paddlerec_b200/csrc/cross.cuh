@@ -119,7 +119,8 @@ static int launch_cross_v2_bwd(const float* dout, const float* x0, const float* 
     cross_v2_bwd_kernel<1><<<grid, kCrossThreads, 0, st>>>(dout, x0, xw, bias, dxw, dx0,
                                                            partials, B, C);
   B200_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, slices, C, dbias, C, nullptr);
+  reduce_partials_kernel<<<reduce_partials_grid(C), kRedThreads, 0, st>>>(partials, slices, C, dbias, C,
+                                                                          nullptr);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

@@ -364,19 +364,34 @@ embed_fm_bwd_dense_kernel(const float* __restrict__ feat, const float* __restric
   }
 }
 
-// out[k] = sum_g partials[g][k] in ascending g (deterministic).  `len` is small (Dn*D+Dn).
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int G, int len,
-                                       float* __restrict__ out0, int len0,
-                                       float* __restrict__ out1) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= len) return;
+// out[k] = sum_g partials[g][k] (deterministic: fixed strided order + fixed shared-memory tree).
+// `len` is small (<= a few thousand) but G can be hundreds: 32 columns x 8 g-lanes per block so
+// the G-long sums are not one serial dependent chain per column.
+constexpr int kRedCols = 32;
+constexpr int kRedLanes = 8;
+__global__ void __launch_bounds__(kRedCols * kRedLanes)
+reduce_partials_kernel(const float* __restrict__ partials, int G, int len,
+                       float* __restrict__ out0, int len0, float* __restrict__ out1) {
+  __shared__ float s[kRedLanes][kRedCols + 1];
+  const int cx = threadIdx.x % kRedCols, gy = threadIdx.x / kRedCols;
+  const int k = blockIdx.x * kRedCols + cx;
   float t = 0.f;
-  for (int g = 0; g < G; ++g) t += partials[(size_t)g * len + k];
-  if (k < len0)
-    out0[k] = t;
-  else
-    out1[k - len0] = t;
+  if (k < len)
+    for (int g = gy; g < G; g += kRedLanes) t += partials[(size_t)g * len + k];
+  s[gy][cx] = t;
+  __syncthreads();
+  if (gy == 0 && k < len) {
+    float r = 0.f;
+#pragma unroll
+    for (int y = 0; y < kRedLanes; ++y) r += s[y][cx];
+    if (k < len0)
+      out0[k] = r;
+    else
+      out1[k - len0] = r;
+  }
 }
+static inline unsigned reduce_partials_grid(int len) { return (unsigned)((len + kRedCols - 1) / kRedCols); }
+constexpr int kRedThreads = kRedCols * kRedLanes;
 
 static int bwd_dense_grid() { return sm_count() * 2; }
 
@@ -429,8 +444,8 @@ static int launch_embed_fm_bwd(const float* feat, const float* S, const float* d
   B200_LAUNCH_CHECK();
   if (Dn > 0) {
     const int len = Dn * D + Dn;
-    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), G,
-                                                              len, ddense_w, Dn * D, ddense_w1);
+    reduce_partials_kernel<<<reduce_partials_grid(len), kRedThreads, 0, st>>>(
+        static_cast<const float*>(ws), G, len, ddense_w, Dn * D, ddense_w1);
     B200_LAUNCH_CHECK();
   }
   return B200REC_OK;

@@ -229,7 +229,8 @@ static int launch_tower_relu_bwd_split(const float* dy, const void* act, void* d
   else
     tower_relu_bwd_split_kernel<1><<<grid, block, 0, st>>>(dy, a, z, partials, M, N);
   B200_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(N + 127) / 128, 128, 0, st>>>(partials, slices, N, dbias, N, nullptr);
+  reduce_partials_kernel<<<reduce_partials_grid(N), kRedThreads, 0, st>>>(partials, slices, N, dbias, N,
+                                                                          nullptr);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }
