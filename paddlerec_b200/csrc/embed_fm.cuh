@@ -29,13 +29,17 @@ struct K1Config {
   int unroll;
   int cache_rows;
   int ctas_per_sm;
+  int debug;
+  int tma;  // 1: shared-memory-staged variant with a bulk (TMA) store of the feat tile
 };
 static K1Config k1_config() {
   static K1Config cfg = [] {
-    K1Config c{13, 0, 8};
+    K1Config c{13, 0, 8, 0, 0};
     if (const char* s = getenv("B200REC_K1_UNROLL")) c.unroll = atoi(s);
     if (const char* s = getenv("B200REC_K1_CACHE")) c.cache_rows = atoi(s);
     if (const char* s = getenv("B200REC_K1_CTAS")) c.ctas_per_sm = atoi(s);
+    if (const char* s = getenv("B200REC_K1_DEBUG")) c.debug = atoi(s);
+    if (const char* s = getenv("B200REC_K1_TMA")) c.tma = atoi(s);
     if (c.ctas_per_sm < 1 || c.ctas_per_sm > 16) c.ctas_per_sm = 8;
     if (c.unroll != 8 && c.unroll != 13 && c.unroll != 26) c.unroll = 13;
     return c;
@@ -61,7 +65,9 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
                     const float* __restrict__ dense_w, const float* __restrict__ dense_w1,
                     float* __restrict__ feat, float* __restrict__ y1, float* __restrict__ y2,
                     float* __restrict__ S, int64_t B, int F, int Dn, int D, int64_t V,
-                    int64_t pad, int64_t ldw, int64_t ldw1) {
+                    int64_t pad, int64_t ldw, int64_t ldw1, int dbg) {
+  // dbg (env B200REC_K1_DEBUG, measurement only): bit 0 = skip the feat stores, bit 1 = skip the
+  // table loads.  0 in production.
   constexpr int kThreads = FwdGeom<TPR>::kThreads;
   constexpr int SPB = FwdGeom<TPR>::kSamples;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -118,7 +124,7 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
           const int f = f0 + j;
           const int64_t id = (f < F) ? my_ids[f] : pad;
           const bool in_range = (uint64_t)id < (uint64_t)V;
-          const bool live = (f < F) && in_range && id != pad;
+          const bool live = (f < F) && in_range && id != pad && !(dbg & 2);
           const size_t row = live ? (size_t)id : 0;
           e[j] = ld_row_pred<VEC, CACHE>(W + row * ldw + r * VEC, live && lane_ok);
           w1v[j] = ld_row_pred<1, true>(W1 + row * ldw1, live && ((f & (TPR - 1)) == r)).v[0];
@@ -134,7 +140,7 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
               Ssum.v[k] += e[j].v[k];
               Q.v[k] = fmaf(e[j].v[k], e[j].v[k], Q.v[k]);
             }
-            if (lane_ok) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
+            if (lane_ok && !(dbg & 1)) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
           }
         }
 #pragma unroll
@@ -148,7 +154,7 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
           const Vec<VEC> w = ld_cached<VEC>(dense_w + (size_t)j * D + r * VEC);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) e.v[k] = x * w.v[k];
-          st_stream<VEC>(feat_row + (size_t)(F + j) * D, e);
+          if (!(dbg & 1)) st_stream<VEC>(feat_row + (size_t)(F + j) * D, e);
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
@@ -176,11 +182,211 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1, shared-memory-staged variant (D % 4 == 0): the tile of `feat` is ASSEMBLED IN SHARED MEMORY in
+// exactly its global layout ([sample][field][D], contiguous over the tile) and leaves the SM as ONE
+// bulk asynchronous copy (cp.async.bulk / TMA, SASS UBLKCP) — no per-thread global stores at all.
+//   * the random table rows are fetched with cp.async 16 B (LDGSTS) straight into their place in
+//     the tile: all F rows of a lane are in flight at once at zero register cost (the register
+//     variant above can afford 13);
+//   * first-order scalars land in a [sample][field] side tile the same way; padding / out-of-range
+//     ids store zeros;
+//   * the dense-feature rows are computed into the tile while the gathers fly;
+//   * after cp.async.wait_group + barrier each lane re-reads its 39 chunks (LDS.128, conflict-free)
+//     for S, Q, y1, y2; fence.proxy.async; one thread issues the bulk store and the CTA only
+//     waits for it (wait_group.read) right before it overwrites the tile for its next iteration —
+//     the second CTA of the SM gathers meanwhile.
+// ids/dense of the next tile are prefetched with cp.async into a second small buffer.
+// STATUS (round 1): correct (same tests as the register variant) but slower — 0.141 ms vs 0.092 ms
+// at B=65536, D=16: one 32-sample tile is 80 KB, so only 2 CTAs = 8 warps fit per SM and the
+// per-field issue chain (LDS id -> compare -> address -> LDGSTS) is not hidden (ncu:
+// profiles/r1g_k1_tma_variant.txt).  Opt-in with B200REC_K1_TMA=1; the register variant is default.
+constexpr int kTmaThreads = 128;
+
+__device__ __forceinline__ void cp_async_16_cg(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_smem_to_global(void* gdst, const void* ssrc,
+                                                          unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+struct K1TmaSmem {
+  size_t feat_bytes, w1_bytes, ids_bytes, dense_bytes, total;
+  __host__ __device__ K1TmaSmem(int spb, int F, int Dn, int D) {
+    feat_bytes = ((size_t)spb * (F + Dn) * D * 4 + 127) / 128 * 128;
+    w1_bytes = ((size_t)spb * F * 4 + 15) / 16 * 16;
+    ids_bytes = ((size_t)spb * F * 8 + 15) / 16 * 16;
+    dense_bytes = ((size_t)spb * Dn * 4 + 15) / 16 * 16;
+    total = feat_bytes + w1_bytes + 2 * (ids_bytes + dense_bytes);
+  }
+};
+
+template <int TPR>
+__global__ void __launch_bounds__(kTmaThreads)
+embed_fm_fwd_tma_kernel(const float* __restrict__ W, const float* __restrict__ W1,
+                        const int64_t* __restrict__ ids, const float* __restrict__ dense,
+                        const float* __restrict__ dense_w, const float* __restrict__ dense_w1,
+                        float* __restrict__ feat, float* __restrict__ y1, float* __restrict__ y2,
+                        float* __restrict__ S, int64_t B, int F, int Dn, int D, int64_t V,
+                        int64_t pad, int64_t ldw, int64_t ldw1) {
+  constexpr int VEC = 4;
+  constexpr int SPB = kTmaThreads / TPR;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const K1TmaSmem L(SPB, F, Dn, D);
+  float* feat_tile = reinterpret_cast<float*>(smem_raw);
+  float* w1_tile = reinterpret_cast<float*>(smem_raw + L.feat_bytes);
+  unsigned char* stage0 = smem_raw + L.feat_bytes + L.w1_bytes;
+  const size_t stage_bytes = L.ids_bytes + L.dense_bytes;
+
+  const int N = F + Dn;
+  const int row_floats = N * D;  // one sample of feat
+  const int64_t ntiles = (B + SPB - 1) / SPB;
+  const int s = threadIdx.x / TPR;
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+
+  auto stage = [&](int64_t tile, int buf) {
+    int64_t* s_ids = reinterpret_cast<int64_t*>(stage0 + (size_t)buf * stage_bytes);
+    float* s_dense = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_ids) + L.ids_bytes);
+    const int64_t b0 = tile * SPB;
+    const int nb = (int)min((int64_t)SPB, B - b0);
+    for (int i = threadIdx.x; i < nb * F; i += kTmaThreads) cp_async_8(s_ids + i, ids + b0 * F + i);
+    for (int i = threadIdx.x; i < nb * Dn; i += kTmaThreads)
+      cp_async_4(s_dense + i, dense + b0 * Dn + i);
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) stage(tile, 0);
+  cp_async_commit();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) stage(next, (it + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    // the previous iteration's bulk store must have finished READING the tile before we refill it
+    if (threadIdx.x == 0) bulk_store_wait_read();
+    __syncthreads();
+
+    const int64_t* s_ids = reinterpret_cast<const int64_t*>(stage0 + (size_t)(it & 1) * stage_bytes);
+    const float* s_dense = reinterpret_cast<const float*>(
+        reinterpret_cast<const unsigned char*>(s_ids) + L.ids_bytes);
+    const int64_t b0 = tile * SPB;
+    const int nb = (int)min((int64_t)SPB, B - b0);
+    const bool sample_ok = s < nb;
+    const int64_t b = b0 + s;
+    float* my_feat = feat_tile + (size_t)s * row_floats + r * VEC;
+    float* my_w1 = w1_tile + (size_t)s * F;
+
+    // ---- issue: every row of this lane, straight into its place in the tile -------------------
+    if (sample_ok) {
+      const int64_t* my_ids = s_ids + (size_t)s * F;
+      for (int f = 0; f < F; ++f) {
+        const int64_t id = my_ids[f];
+        const bool in_range = (uint64_t)id < (uint64_t)V;
+        const bool live = in_range && id != pad;
+        if (lane_ok) {
+          if (live)
+            cp_async_16_cg(my_feat + (size_t)f * D, W + (size_t)id * ldw + r * VEC);
+          else
+            *reinterpret_cast<float4*>(my_feat + (size_t)f * D) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if ((f & (TPR - 1)) == r) {
+          if (live)
+            cp_async_4(my_w1 + f, W1 + (size_t)id * ldw1);
+          else
+            my_w1[f] = 0.f;
+        }
+        if (!in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
+      }
+    }
+    cp_async_commit();
+    // ---- dense-feature rows while the gathers are in flight -----------------------------------
+    float first = 0.f;
+    if (sample_ok) {
+      const float* my_dense = s_dense + (size_t)s * Dn;
+      for (int j = 0; j < Dn; ++j) {
+        const float x = my_dense[j];
+        if (lane_ok) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(dense_w + (size_t)j * D) + r);
+          *reinterpret_cast<float4*>(my_feat + (size_t)(F + j) * D) =
+              make_float4(x * w.x, x * w.y, x * w.z, x * w.w);
+        }
+        if ((j & (TPR - 1)) == r) first = fmaf(x, __ldg(dense_w1 + j), first);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- consume from the tile ----------------------------------------------------------------
+    float4 Ssum = make_float4(0.f, 0.f, 0.f, 0.f), Q = Ssum;
+    if (sample_ok) {
+      if (lane_ok) {
+#pragma unroll 13
+        for (int n = 0; n < N; ++n) {
+          const float4 e = *reinterpret_cast<const float4*>(my_feat + (size_t)n * D);
+          Ssum.x += e.x; Ssum.y += e.y; Ssum.z += e.z; Ssum.w += e.w;
+          Q.x = fmaf(e.x, e.x, Q.x); Q.y = fmaf(e.y, e.y, Q.y);
+          Q.z = fmaf(e.z, e.z, Q.z); Q.w = fmaf(e.w, e.w, Q.w);
+        }
+      }
+      for (int f = r; f < F; f += TPR) first += my_w1[f];
+    }
+    float t = (Ssum.x * Ssum.x - Q.x) + (Ssum.y * Ssum.y - Q.y) + (Ssum.z * Ssum.z - Q.z) +
+              (Ssum.w * Ssum.w - Q.w);
+    t = group_sum<TPR>(t);
+    first = group_sum<TPR>(first);
+    if (sample_ok) {
+      if (r == 0) {
+        y1[b] = first;
+        y2[b] = 0.5f * t;
+      }
+      if (S != nullptr && lane_ok)
+        *reinterpret_cast<float4*>(S + (size_t)b * D + r * VEC) = Ssum;
+    }
+    // ---- the whole tile leaves as one bulk copy -----------------------------------------------
+    fence_proxy_async_smem();  // generic-proxy writes (st.shared, cp.async) -> visible to the TMA
+    __syncthreads();
+    if (threadIdx.x == 0)
+      bulk_store_smem_to_global(feat + (size_t)b0 * row_floats, feat_tile,
+                                (unsigned)((size_t)nb * row_floats * sizeof(float)));
+  }
+  if (threadIdx.x == 0) bulk_store_wait_read();
+  cp_async_wait<0>();
+}
+
 struct K1Args {
   const float* W; const float* W1; const int64_t* ids; const float* dense; const float* dense_w;
   const float* dense_w1; float* feat; float* y1; float* y2; float* S;
   int64_t B; int F, Dn, D; int64_t V, pad, ldw, ldw1;
 };
+
+template <int TPR>
+static int k1_tma_launch(const K1Args& a, cudaStream_t st) {
+  constexpr int SPB = kTmaThreads / TPR;
+  const K1TmaSmem L(SPB, a.F, a.Dn, a.D);
+  auto kern = embed_fm_fwd_tma_kernel<TPR>;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int64_t ntiles = (a.B + SPB - 1) / SPB;
+  const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / L.total));
+  const int64_t grid = min(ntiles, (int64_t)sm_count() * per_sm);
+  kern<<<(unsigned)grid, kTmaThreads, L.total, st>>>(a.W, a.W1, a.ids, a.dense, a.dense_w, a.dense_w1,
+                                                    a.feat, a.y1, a.y2, a.S, a.B, a.F, a.Dn, a.D, a.V,
+                                                    a.pad, a.ldw, a.ldw1);
+  return B200REC_OK;
+}
 
 template <int VEC, int TPR, int U, bool C>
 static int k1_launch(const K1Args& a, int64_t grid, size_t smem, cudaStream_t st) {
@@ -189,7 +395,7 @@ static int k1_launch(const K1Args& a, int64_t grid, size_t smem, cudaStream_t st
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, FwdGeom<TPR>::kThreads, smem, st>>>(
       a.W, a.W1, a.ids, a.dense, a.dense_w, a.dense_w1, a.feat, a.y1, a.y2, a.S, a.B, a.F, a.Dn, a.D,
-      a.V, a.pad, a.ldw, a.ldw1);
+      a.V, a.pad, a.ldw, a.ldw1, k1_config().debug);
   return B200REC_OK;
 }
 
@@ -224,7 +430,10 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
     const int64_t grid = min(ntiles, (int64_t)sm_count() * cfg.ctas_per_sm);
     K1Args a{W, W1, ids, dense, dense_w, dense_w1, feat, y1, y2, S, B, F, Dn, D, V, pad, ldw, ldw1};
     int rc;
-    if (cfg.unroll == 8)
+    if (VEC == 4 && cfg.tma && cfg.debug == 0 && aligned16(dense_w) && (ldw % 4 == 0) &&
+        K1TmaSmem(kTmaThreads / TPR, F, Dn, D).total <= 110 * 1024)
+      rc = k1_tma_launch<TPR>(a, st);
+    else if (cfg.unroll == 8)
       rc = cache ? k1_launch<VEC, TPR, 8, true>(a, grid, smem, st)
                  : k1_launch<VEC, TPR, 8, false>(a, grid, smem, st);
     else if (cfg.unroll == 26)

@@ -117,7 +117,8 @@ class CrossNetV2(tnn.Module):
         X_0 = X_0.contiguous()
         X_i = X_0
         for layer in self.cross_layers:       # X_i + X_0 * (X_i W + b): GEMM + fused epilogue
-            X_i = ops.cross_v2(X_0, X_i, layer.weight, layer.bias, bnn.mm)
+            X_i = ops.cross_v2(X_0, X_i, layer.weight, layer.bias, bnn.mm,
+                               bnn.get_matmul_precision() if X_i.is_cuda else "fp32")
         return X_i
 
 

@@ -42,6 +42,8 @@ def child():
     print(json.dumps({"unroll": os.environ.get("B200REC_K1_UNROLL"),
                       "cache": os.environ.get("B200REC_K1_CACHE"),
                       "ctas_per_sm": os.environ.get("B200REC_K1_CTAS"),
+                      "debug_mask": os.environ.get("B200REC_K1_DEBUG"),
+                      "tma_variant": os.environ.get("B200REC_K1_TMA"),
                       "two_tables_ms": a, "two_tables_GBps": alg / a / 1e6,
                       "fused_slots_ms": b, "fused_slots_GBps": alg / b / 1e6}), flush=True)
 
@@ -50,6 +52,17 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
+        if len(sys.argv) > 1 and sys.argv[1] == "tma":
+            for tma in ("0", "1"):
+                env = dict(os.environ, B200REC_K1_TMA=tma)
+                subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
+            sys.exit(0)
+        if len(sys.argv) > 1 and sys.argv[1] == "decompose":
+            # where does K1's time go?  0 = full kernel, 1 = no feat stores, 2 = no table loads
+            for dbg in ("0", "1", "2", "3"):
+                env = dict(os.environ, B200REC_K1_DEBUG=dbg, B200REC_K1_TMA="0")
+                subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
+            sys.exit(0)
         for u, ctas in (("8", "4"), ("8", "5"), ("8", "8"), ("13", "3"), ("13", "4"), ("13", "8"),
                         ("26", "2")):
             for c in ("0", "1"):
