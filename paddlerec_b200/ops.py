@@ -561,6 +561,57 @@ class _CrossV2(torch.autograd.Function):
         return dx0, dxl, dW, dbias, None, None
 
 
+class _SplitMM(torch.autograd.Function):
+    """a @ W for fp32 operands on the bf16 tensor cores (hi/lo split, three products, fp32
+    accumulate) with the fused split kernels — the GEMM building block of tower.py as a
+    stand-alone autograd node (used by CrossNetMix's two large projections)."""
+
+    @staticmethod
+    def forward(ctx, a, W):
+        K, N = W.shape
+        a_s = raw_tower_split(a.contiguous(), None, False)
+        W2r, W2c, Wlo = raw_tower_prep_weight(W)
+        out = torch.mm(a_s, W2r, out_dtype=torch.float32)
+        torch.addmm(out, a_s[:, :K], Wlo, out_dtype=torch.float32, out=out)
+        ctx.a_s, ctx.wprep, ctx.shape = a_s, (W2c, Wlo), (K, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        K, N = ctx.shape
+        W2c, Wlo = ctx.wprep
+        gs, _ = raw_tower_relu_bwd_split(dout.contiguous(), None)
+        dW = raw_tower_fold_dw(torch.mm(ctx.a_s.t(), gs, out_dtype=torch.float32), K, N)
+        da = torch.mm(gs, W2c.t(), out_dtype=torch.float32)
+        torch.addmm(da, gs[:, :N], Wlo.t(), out_dtype=torch.float32, out=da)
+        ctx.a_s = ctx.wprep = None
+        return da, dW
+
+
+class _CrossCombine(torch.autograd.Function):
+    """out = xl + x0 * (xw + bias) with xw given (K3 epilogue as its own node)."""
+
+    @staticmethod
+    def forward(ctx, x0, xl, xw, bias):
+        ctx.save_for_backward(x0, xw, bias)
+        return raw_cross_v2_fwd(x0, xl, xw, bias)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x0, xw, bias = ctx.saved_tensors
+        dout = dout.contiguous()
+        dxw, dx0, dbias = raw_cross_v2_bwd(dout, x0, xw, bias)
+        return dx0, dout, dxw, dbias
+
+
+def split_mm(a, W):
+    return _SplitMM.apply(a, W)
+
+
+def cross_combine(x0, xl, xw, bias):
+    return _CrossCombine.apply(x0, xl, xw, bias)
+
+
 def embed_fm(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink, D=None):
     D = W.shape[1] if D is None else D
     return _EmbedFM.apply(W, W1, ids, dense, dense_w, dense_w1, padding_idx, sink, D)

@@ -131,6 +131,14 @@ def _xavier_normal(*shape):
 
 
 class CrossNetMix(tnn.Module):
+    """net.py:229-320.  Two evaluation orders of the same mathematics:
+      * reference order (per expert, fp32 library batched GEMMs) — exact path, any device;
+      * tensor-core order (bf16x3 precision on CUDA): the E projections V_e^T x are ONE
+        [B,in]x[in,E*r] GEMM, and because the gate is a per-sample scalar,
+            sum_e g_e * (x0 * (U_e v_e + b)) = x0 * ( [g_1 v_1 | .. | g_E v_E] U_cat^T + b )
+        (softmax gates sum to 1), i.e. ONE [B,E*r]x[E*r,in] GEMM followed by the very same fused
+        K3 epilogue as CrossNetV2.  ~60x fewer fp32-pipe FLOPs than the per-sample GEMV form."""
+
     def __init__(self, in_features, layer_num=2, low_rank=32, num_experts=4):
         super().__init__()
         self.layer_num, self.num_experts, self.low_rank = layer_num, num_experts, low_rank
@@ -145,6 +153,8 @@ class CrossNetMix(tnn.Module):
             [tnn.Parameter(torch.zeros(in_features, 1)) for _ in range(layer_num)])
 
     def forward(self, inputs):
+        if bnn.get_matmul_precision() == "bf16x3" and inputs.is_cuda:
+            return self._forward_tensor_core(inputs.contiguous())
         x_0 = inputs
         x_l = inputs
         Wg = torch.cat([g.weight for g in self.gating], dim=1)                 # [in, E]
@@ -156,4 +166,21 @@ class CrossNetMix(tnn.Module):
             u = torch.einsum("ebr,eir->ebi", v, self.U_list[i])                # :300
             dot_ = x_0.unsqueeze(0) * (u + self.bias[i].reshape(1, 1, -1))     # :303-304
             x_l = torch.einsum("ebi,be->bi", dot_, gate) + x_l                 # :314-317
+        return x_l
+
+    def _forward_tensor_core(self, x_0):
+        E, r = self.num_experts, self.low_rank
+        B, C = x_0.shape
+        x_l = x_0
+        Wg = torch.cat([g.weight for g in self.gating], dim=1)
+        bg = torch.cat([g.bias for g in self.gating], dim=0)
+        for i in range(self.layer_num):
+            gate = torch.softmax(x_l @ Wg + bg, dim=1)                                  # [B,E]
+            V_cat = self.V_list[i].permute(1, 0, 2).reshape(C, E * r)                    # [in, E*r]
+            v = torch.tanh(ops.split_mm(x_l, V_cat)).reshape(B, E, r)
+            v = torch.tanh(torch.einsum("ber,esr->bes", v, self.C_list[i]))              # r x r, fp32
+            gv = (v * gate.unsqueeze(2)).reshape(B, E * r)
+            U_cat_t = self.U_list[i].permute(0, 2, 1).reshape(E * r, C)                  # [E*r, in]
+            xw = ops.split_mm(gv, U_cat_t)
+            x_l = ops.cross_combine(x_0, x_l, xw, self.bias[i].reshape(-1))
         return x_l
