@@ -225,6 +225,7 @@ def run_b200(args, rank, world, local_rank):
     scale = optimizer.scale_loss if hasattr(optimizer, "scale_loss") else (lambda x: x)
 
     prefetch = getattr(model, "prefetch", None)
+    finish_prefetch = getattr(model, "finish_prefetch", None)
 
     def step_resident(i):
         label, ids, dense = resident[i % len(resident)]
@@ -234,6 +235,8 @@ def run_b200(args, rank, world, local_rank):
             prefetch(resident[(i + 1) % len(resident)][1])
         loss = dm.create_loss(pred, label_f[i % len(resident)])
         scale(loss).backward()
+        if finish_prefetch is not None:
+            finish_prefetch()
         optimizer.step()
         return loss
 
@@ -265,6 +268,8 @@ def run_b200(args, rank, world, local_rank):
             cur.wait_stream(copy_stream)
             prefetch(pending["feeds"][1])
         scale(loss).backward()
+        if finish_prefetch is not None:
+            finish_prefetch()
         optimizer.step()
         return loss.item()  # D2H read of the step's result
 

@@ -94,14 +94,41 @@ class ShardExchange:
             t.record_stream(self._side)
         self._pending = _PendingPlan(ids, send_ids, perm, inv_perm, host, ev)
 
+    def finish_prefetch(self) -> None:
+        """Second half of the prefetch (call it later in the step, e.g. after backward was
+        launched): once the counts are on the host, run the id all-to-all of the NEXT batch on the
+        side stream too, so the next forward starts directly with the owner-side gather."""
+        pend = self._pending
+        if pend is None or getattr(pend, "recv_ids", None) is not None:
+            return
+        # Every rank must issue its collectives in the same order, so this must not depend on a
+        # rank-local "is it ready yet" test: always wait for the counts (the GPU is busy with the
+        # backward pass that was already enqueued, so the host wait costs no GPU time).
+        pend.event.synchronize()
+        send_splits, recv_splits = pend.host_counts[0].tolist(), pend.host_counts[1].tolist()
+        with torch.cuda.stream(self._side):
+            recv_ids = torch.empty(sum(recv_splits), dtype=torch.int64, device=pend.send_ids.device)
+            dist.all_to_all_single(recv_ids, pend.send_ids, recv_splits, send_splits,
+                                   group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        recv_ids.record_stream(self._side)
+        pend.recv_ids, pend.splits, pend.event2 = recv_ids, (send_splits, recv_splits), ev
+
     def plan(self, ids: torch.Tensor) -> ExchangePlan:
         pend, self._pending = self._pending, None
         flat = ids.reshape(-1)
         n = flat.numel()
         if pend is not None and pend.ids is ids:
+            send_ids, perm, inv_perm = pend.send_ids, pend.perm, pend.inv_perm
+            if getattr(pend, "recv_ids", None) is not None:       # fully prefetched
+                torch.cuda.current_stream().wait_event(pend.event2)
+                send_splits, recv_splits = pend.splits
+                for t in (pend.recv_ids, perm, inv_perm):
+                    t.record_stream(torch.cuda.current_stream())
+                return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, pend.recv_ids)
             pend.event.synchronize()                              # normally long complete
             torch.cuda.current_stream().wait_event(pend.event)
-            send_ids, perm, inv_perm = pend.send_ids, pend.perm, pend.inv_perm
             send_splits, recv_splits = pend.host_counts[0].tolist(), pend.host_counts[1].tolist()
         else:
             send_ids, perm, inv_perm, both = self._bucketize_and_count(flat)
@@ -238,8 +265,7 @@ class _ShardedEmbedFM(torch.autograd.Function):
         if dfeat is not None:
             dfeat = dfeat.contiguous()
         n = plan.n
-        iota = torch.arange(n + 1, dtype=torch.int32, device=dev)
-        num = torch.tensor([n, n], dtype=torch.int32, device=dev)
+        iota, num = fm.trivial_groups(n, dev)
         # seg_offsets = iota, sorted_pos = inv_perm: row k of the output is the gradient of slot k
         if fm.fused:
             tab = fm._fused
@@ -300,11 +326,23 @@ class ShardedFM(bnn.FusedTableOwner):
         tnn.init.trunc_normal_(self.dense_w_one, 0.0, std, -2 * std, 2 * std)
         tnn.init.trunc_normal_(self.dense_w, 0.0, std, -2 * std, 2 * std)
         self.exchange = ShardExchange(sparse_feature_number, rank, world, group, kernels)
+        self._trivial = {}
 
     def table_grad_dense(self):
         if self.fused:
             return self._fused.grad_dense()
         return (self.embedding.grad_rows.to_dense(), self.embedding_one.grad_rows.to_dense())
+
+    def trivial_groups(self, n: int, device):
+        """seg_offsets = 0..n and num = {n, n}: "every slot is its own segment" (cached per n so
+        the backward issues no allocation / host->device copy for them)."""
+        key = (n, str(device))
+        hit = self._trivial.get(key)
+        if hit is None:
+            hit = (torch.arange(n + 1, dtype=torch.int32, device=device),
+                   torch.full((2,), n, dtype=torch.int32, device=device))
+            self._trivial[key] = hit
+        return hit
 
     def forward(self, sparse_inputs, dense_inputs):
         ids = (torch.cat(list(sparse_inputs), dim=1) if isinstance(sparse_inputs, (list, tuple))
@@ -336,6 +374,9 @@ class ShardedDeepFMLayer(tnn.Module):
     def prefetch(self, next_sparse_inputs) -> None:
         """Hint: the ids of the NEXT batch (the very tensor that will be passed to forward)."""
         self.fm.exchange.prefetch(next_sparse_inputs)
+
+    def finish_prefetch(self) -> None:
+        self.fm.exchange.finish_prefetch()
 
 
 def dense_parameters(model: tnn.Module) -> List[torch.Tensor]:
