@@ -206,11 +206,20 @@ class FusedTable(tnn.Module):
     stay interchangeable.  The gradient is one SelectedRows of width D+1 (+pad) on `weight`."""
 
     def __init__(self, num_embeddings, embedding_dim, padding_idx=None, init_std=None, device=None,
-                 names=("embedding.weight", "embedding_one.weight"), attr="_fused"):
+                 names=("embedding.weight", "embedding_one.weight"), attr="_fused",
+                 moments_in_slot=True):
         super().__init__()
         D = embedding_dim
         self.num_embeddings, self.embedding_dim = num_embeddings, D
         self.slot, self.grad_cols = ops.fused_slot(D), ops.fused_grad_cols(D)
+        # Optimizer state inside the slot: [w (G cols) | m (G) | v (G) | pad] in 2 x 128 bytes, so a
+        # lazy-Adam update touches 2 lines per row instead of 3 (and the three lines it needs share
+        # a DRAM page); the forward still reads only the first line.  Falls back to separate
+        # moment arrays when 3*G floats do not fit 64.
+        self.moment_cols = None
+        if moments_in_slot and 3 * self.grad_cols <= 64 and self.slot == 32:
+            self.slot = 64
+            self.moment_cols = (self.grad_cols, 2 * self.grad_cols)
         self.padding_idx = padding_idx
         self._names, self._attr = names, attr
         w = torch.zeros(num_embeddings, self.slot, device=device)
@@ -226,6 +235,7 @@ class FusedTable(tnn.Module):
         self.weight.is_sparse_table = True
         self.weight.fused_D = self.embedding_dim
         self.weight.fused_names = self._names
+        self.weight.inslot_moments = self.moment_cols
         if not hasattr(self.weight, "grad_rows"):
             self.weight.grad_rows = None
 

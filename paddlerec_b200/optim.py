@@ -134,6 +134,12 @@ class Adam(_Base):
         self._v = {}
 
     def moments(self, p):
+        """(m, v) with the row stride of `p`: views INTO the table slots when the table keeps its
+        optimizer state in-slot (nn.FusedTable), separate zero-initialised arrays otherwise."""
+        inslot = getattr(p, "inslot_moments", None)
+        if inslot is not None:
+            G = inslot[1] - inslot[0]
+            return p.data[:, inslot[0]:inslot[0] + G], p.data[:, inslot[1]:inslot[1] + G]
         k = id(p)
         if k not in self._m:
             self._m[k] = torch.zeros_like(p.data)
