@@ -561,6 +561,183 @@ class _CrossV2(torch.autograd.Function):
         return dx0, dxl, dW, dbias, None, None
 
 
+# ---- continuous_value_model ---------------------------------------------------------------------
+def raw_cvm_fwd(x: torch.Tensor, use_cvm: bool) -> torch.Tensor:
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    N, W = x.shape
+    D = W - 2
+    y = torch.empty(N, W if use_cvm else D, dtype=torch.float32, device=x.device)
+    check(lib.b200rec_cvm_fwd(ptr(x), ptr(y), N, D, int(use_cvm), _stream()), "cvm_fwd")
+    _count("cvm_fwd")
+    return y
+
+
+def raw_cvm_bwd(dy: torch.Tensor, show_click: torch.Tensor, D: int, use_cvm: bool) -> torch.Tensor:
+    lib = _lib.load()
+    dy = _req(dy, torch.float32, "dy")
+    show_click = _req(show_click, torch.float32, "show_click")
+    N = dy.shape[0]
+    dx = torch.empty(N, D + 2, dtype=torch.float32, device=dy.device)
+    check(lib.b200rec_cvm_bwd(ptr(dy), ptr(show_click), ptr(dx), N, D, int(use_cvm), _stream()),
+          "cvm_bwd")
+    _count("cvm_bwd")
+    return dx
+
+
+class _CVM(torch.autograd.Function):
+    """paddle.static.nn.continuous_value_model(input, cvm, use_cvm) — wide_deep/net.py:87-88."""
+
+    @staticmethod
+    def forward(ctx, x, show_click, use_cvm):
+        ctx.save_for_backward(show_click)
+        ctx.use_cvm, ctx.D = use_cvm, x.shape[1] - 2
+        return raw_cvm_fwd(x, use_cvm)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (show_click,) = ctx.saved_tensors
+        return raw_cvm_bwd(dy.contiguous(), show_click, ctx.D, ctx.use_cvm), None, None
+
+
+def continuous_value_model(x, show_click, use_cvm):
+    return _CVM.apply(x, show_click, use_cvm)
+
+
+# ---- K4: DIN attention pooling ------------------------------------------------------------------
+HAVE_DIN_ATTN = True
+
+
+def raw_din_attn_fwd(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    """hist [B,L,E], tseq [B,E] (tiled target), mask int64 [B,L(,1)] or None.
+    Returns (out [B,E], weights [B,L])."""
+    lib = _lib.load()
+    hist = _req(hist, torch.float32, "hist")
+    tseq = _req(tseq, torch.float32, "tseq")
+    B, L, E = hist.shape
+    W1 = W1.detach()
+    Wa, Wb, Wc, Wd = W1[0:E], W1[E:2 * E], W1[2 * E:3 * E], W1[3 * E:4 * E]
+    Wac = (Wa + Wc).contiguous()
+    Wd = Wd.contiguous()
+    tb = torch.addmm(b1.detach(), tseq, Wb - Wc)            # [B,80]: the per-sample t-term
+    if mask is not None:
+        mask = _req(mask.reshape(B, L), torch.int64, "mask")
+    dev = hist.device
+    scores = torch.empty(B, L, dtype=torch.float32, device=dev)
+    weights = torch.empty(B, L, dtype=torch.float32, device=dev)
+    out = torch.empty(B, E, dtype=torch.float32, device=dev)
+    check(lib.b200rec_din_attn_fwd(ptr(hist), ptr(tseq), ptr(tb), ptr(Wac), ptr(Wd),
+                                   ptr(_req(W2.detach(), torch.float32, "W2")), ptr(b2.detach()),
+                                   ptr(_req(W3.detach().reshape(-1), torch.float32, "W3")),
+                                   ptr(b3.detach()), ptr(mask), ptr(scores), ptr(weights), ptr(out),
+                                   B, L, E, float(E) ** -0.5, _stream()), "din_attn_fwd")
+    _count("din_attn_fwd")
+    return out, weights
+
+
+def raw_din_attn_bwd(hist, tseq, W1, b1, W2, b2, W3, weights, dout):
+    """Fused backward of the DIN attention pooling.  Returns
+    (dhist, dtseq, dW1, db1, dW2, db2, dW3 [40,1], db3 [1])."""
+    lib = _lib.load()
+    hist = _req(hist, torch.float32, "hist")
+    tseq = _req(tseq, torch.float32, "tseq")
+    dout = _req(dout, torch.float32, "dout")
+    weights = _req(weights, torch.float32, "weights")
+    B, L, E = hist.shape
+    W1 = W1.detach()
+    Wa, Wb, Wc, Wd = W1[0:E], W1[E:2 * E], W1[2 * E:3 * E], W1[3 * E:4 * E]
+    Wac, Wbc, Wd = (Wa + Wc).contiguous(), (Wb - Wc), Wd.contiguous()
+    tb = torch.addmm(b1.detach(), tseq, Wbc)
+    dev = hist.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    da = torch.empty(B, L, **f32)
+    dhist = torch.empty_like(hist)
+    dtseq = torch.empty(B, E, **f32)
+    dtb = torch.empty(B, 80, **f32)
+    dWac, dWd = torch.empty(E, 80, **f32), torch.empty(E, 80, **f32)
+    dW2, db2, dW3 = torch.empty(80, 40, **f32), torch.empty(40, **f32), torch.empty(40, **f32)
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_din_attn_bwd_workspace_bytes(B, L, E, ctypes.byref(nbytes)), "din_bwd_ws")
+    ws = workspace(nbytes.value, dev, "din_bwd")
+    check(lib.b200rec_din_attn_bwd(ptr(hist), ptr(tseq), ptr(tb), ptr(Wac), ptr(Wd),
+                                   ptr(_req(W2.detach(), torch.float32, "W2")), ptr(b2.detach()),
+                                   ptr(_req(W3.detach().reshape(-1), torch.float32, "W3")),
+                                   ptr(weights), ptr(dout), ptr(da), ptr(dhist), ptr(dtseq),
+                                   ptr(dtb), ptr(dWac), ptr(dWd), ptr(dW2), ptr(db2), ptr(dW3), B, L,
+                                   E, float(E) ** -0.5, ptr(ws), ws.numel(), _stream()),
+          "din_attn_bwd")
+    _count("din_attn_bwd")
+    # the t-path: tb = t (Wb - Wc) + b1
+    dtseq = torch.addmm(dtseq, dtb, Wbc.t())
+    Gt = tseq.t() @ dtb
+    dW1 = torch.cat([dWac, Gt, dWac - Gt, dWd], dim=0)
+    return dhist, dtseq, dW1, dtb.sum(0), dW2, db2, dW3.reshape(-1, 1), da.sum().reshape(1)
+
+
+def _din_attention_composite(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    """The reference's op sequence (din/net.py:155-173) in torch — used to differentiate."""
+    E = hist.shape[2]
+    t = tseq.unsqueeze(1).expand_as(hist)
+    c = torch.cat([hist, t, hist - t, hist * t], dim=2)
+    a = torch.sigmoid(c @ W1 + b1)
+    a = torch.sigmoid(a @ W2 + b2)
+    a = a @ W3 + b3
+    if mask is not None:
+        a = a + mask.reshape(a.shape).to(a.dtype)
+    w = torch.softmax(a.transpose(1, 2) * (E ** -0.5), dim=-1)
+    return torch.matmul(w, hist).reshape(-1, E)
+
+
+FUSED_DIN_BACKWARD = True
+
+
+class _DinAttn(torch.autograd.Function):
+    """Forward and backward are the fused K4 kernels (only the softmax weights are saved; z1/z2
+    are recomputed in backward).  With FUSED_DIN_BACKWARD = False the backward re-runs the
+    reference's op sequence under autograd on chunks of samples (kept as a cross-check)."""
+
+    CHUNK_BYTES = 256 << 20
+
+    @staticmethod
+    def forward(ctx, hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+        out, w = raw_din_attn_fwd(hist, tseq, mask, W1, b1, W2, b2, W3, b3)
+        ctx.save_for_backward(hist, tseq, W1, b1, W2, b2, W3, b3, w)
+        ctx.mask = mask
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        hist, tseq, W1, b1, W2, b2, W3, b3, w = ctx.saved_tensors
+        if FUSED_DIN_BACKWARD:
+            dhist, dtseq, dW1, db1, dW2, db2, dW3, db3 = raw_din_attn_bwd(
+                hist, tseq, W1, b1, W2, b2, W3, w, dout.contiguous())
+            return dhist, dtseq, None, dW1, db1, dW2, db2, dW3.reshape(W3.shape), db3
+        B, L, E = hist.shape
+        per_sample = L * 4 * E * 4 * 3
+        chunk = max(1, min(B, _DinAttn.CHUNK_BYTES // max(per_sample, 1)))
+        params = [p.detach().requires_grad_(True) for p in (W1, b1, W2, b2, W3, b3)]
+        dhist = torch.empty_like(hist)
+        dtseq = torch.empty_like(tseq)
+        pgrads = [torch.zeros_like(p) for p in params]
+        for s in range(0, B, chunk):
+            e = min(B, s + chunk)
+            h = hist[s:e].detach().requires_grad_(True)
+            t = tseq[s:e].detach().requires_grad_(True)
+            m = ctx.mask[s:e] if ctx.mask is not None else None
+            with torch.enable_grad():
+                o = _din_attention_composite(h, t, m, *params)
+            gs = torch.autograd.grad(o, [h, t] + params, dout[s:e])
+            dhist[s:e] = gs[0]
+            dtseq[s:e] = gs[1]
+            for acc, g in zip(pgrads, gs[2:]):
+                acc += g
+        return (dhist, dtseq, None, *pgrads)
+
+
+def din_attention(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    return _DinAttn.apply(hist, tseq, mask, W1, b1, W2, b2, W3, b3)
+
+
 class _SplitMM(torch.autograd.Function):
     """a @ W for fp32 operands on the bf16 tensor cores (hi/lo split, three products, fp32
     accumulate) with the fused split kernels — the GEMM building block of tower.py as a
