@@ -58,3 +58,18 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_every_entry_point_has_a_torch_wrapper():
+    """Guards the binding layer: every C entry point must be called from paddlerec_b200/ops.py (a
+    refactor once dropped the DIN/CVM wrappers silently — only the GPU tests noticed)."""
+    from paddlerec_b200 import ops
+    src = open(os.path.join(_lib.REPO_ROOT, "paddlerec_b200", "ops.py")).read()
+    for name in _lib.declared_symbols():
+        if name in ("b200rec_abi_version", "b200rec_last_error"):
+            continue
+        assert "lib." + name + "(" in src, "no wrapper calls " + name
+    for attr in ("embed_fm", "gather", "gather_pool_sum", "cross_v2", "cross_combine", "split_mm",
+                 "din_attention", "continuous_value_model", "raw_shard_bucketize", "SelectedRows",
+                 "raw_sparse_adam", "raw_sparse_sgd", "raw_sparse_adagrad", "raw_tower_split"):
+        assert hasattr(ops, attr), attr
