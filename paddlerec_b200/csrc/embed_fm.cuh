@@ -31,15 +31,17 @@ struct K1Config {
   int ctas_per_sm;
   int debug;
   int tma;  // 1: shared-memory-staged variant with a bulk (TMA) store of the feat tile
+  int minb;  // __launch_bounds__ min blocks/SM (register cap) variants: 4 (default), 5, 6, 8
 };
 static K1Config k1_config() {
   static K1Config cfg = [] {
-    K1Config c{13, 0, 8, 0, 0};
+    K1Config c{13, 0, 8, 0, 0, 4};
     if (const char* s = getenv("B200REC_K1_UNROLL")) c.unroll = atoi(s);
     if (const char* s = getenv("B200REC_K1_CACHE")) c.cache_rows = atoi(s);
     if (const char* s = getenv("B200REC_K1_CTAS")) c.ctas_per_sm = atoi(s);
     if (const char* s = getenv("B200REC_K1_DEBUG")) c.debug = atoi(s);
     if (const char* s = getenv("B200REC_K1_TMA")) c.tma = atoi(s);
+    if (const char* s = getenv("B200REC_K1_MINB")) c.minb = atoi(s);
     if (c.ctas_per_sm < 1 || c.ctas_per_sm > 16) c.ctas_per_sm = 8;
     if (c.unroll != 8 && c.unroll != 13 && c.unroll != 26) c.unroll = 13;
     return c;
@@ -58,8 +60,8 @@ struct FwdGeom {
 // cp.async, so the id round trip is off the critical path.  Per tile and lane: all row loads and
 // first-order lookups of a batch of kFieldUnroll fields are issued (predicated PTX, no branches)
 // before the first one is consumed.
-template <int VEC, int TPR, int kFieldUnroll, bool CACHE>
-__global__ void __launch_bounds__(FwdGeom<TPR>::kThreads)
+template <int VEC, int TPR, int kFieldUnroll, bool CACHE, int MINB = 4>
+__global__ void __launch_bounds__(FwdGeom<TPR>::kThreads, MINB)
 embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
                     const int64_t* __restrict__ ids, const float* __restrict__ dense,
                     const float* __restrict__ dense_w, const float* __restrict__ dense_w1,
@@ -388,9 +390,9 @@ static int k1_tma_launch(const K1Args& a, cudaStream_t st) {
   return B200REC_OK;
 }
 
-template <int VEC, int TPR, int U, bool C>
+template <int VEC, int TPR, int U, bool C, int MINB = 4>
 static int k1_launch(const K1Args& a, int64_t grid, size_t smem, cudaStream_t st) {
-  auto kern = embed_fm_fwd_kernel<VEC, TPR, U, C>;
+  auto kern = embed_fm_fwd_kernel<VEC, TPR, U, C, MINB>;
   if (smem > 48 * 1024)
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, FwdGeom<TPR>::kThreads, smem, st>>>(
@@ -433,6 +435,14 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
     if (VEC == 4 && cfg.tma && cfg.debug == 0 && aligned16(dense_w) && (ldw % 4 == 0) &&
         K1TmaSmem(kTmaThreads / TPR, F, Dn, D).total <= 110 * 1024)
       rc = k1_tma_launch<TPR>(a, st);
+    else if (cfg.minb == 5 && cfg.unroll == 13)
+      rc = k1_launch<VEC, TPR, 13, false, 5>(a, grid, smem, st);
+    else if (cfg.minb == 6 && cfg.unroll == 13)
+      rc = k1_launch<VEC, TPR, 13, false, 6>(a, grid, smem, st);
+    else if (cfg.minb == 6 && cfg.unroll == 8)
+      rc = k1_launch<VEC, TPR, 8, false, 6>(a, grid, smem, st);
+    else if (cfg.minb == 8 && cfg.unroll == 8)
+      rc = k1_launch<VEC, TPR, 8, false, 8>(a, grid, smem, st);
     else if (cfg.unroll == 8)
       rc = cache ? k1_launch<VEC, TPR, 8, true>(a, grid, smem, st)
                  : k1_launch<VEC, TPR, 8, false>(a, grid, smem, st);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 4: DIN AmazonElec-shape (item 63001, cat 801, E=64+64, history length 100).
 Times (CUDA events) the fused attention-pooling forward kernel pair (K4) alone and one full
-training step of DINLayer (gathers, K4 forward, composite backward, SGD); prints JSON lines."""
+training step of DINLayer (gathers, K4 forward and fused backward, SGD); prints JSON lines."""
 import argparse
 import json
 import os
@@ -84,7 +84,7 @@ def main():
         loss.backward()
         opt.step()
     ms = timeit(step, a.iters)
-    print(json.dumps({"what": "DIN train step (gathers, K4 fwd, composite bwd, SGD)", "B": B, "L": L,
+    print(json.dumps({"what": "DIN train step (gathers, K4 fwd + fused bwd, SGD)", "B": B, "L": L,
                       "ms": ms, "samples_per_s": B / ms * 1e3}), flush=True)
 
 

@@ -44,6 +44,7 @@ def child():
                       "ctas_per_sm": os.environ.get("B200REC_K1_CTAS"),
                       "debug_mask": os.environ.get("B200REC_K1_DEBUG"),
                       "tma_variant": os.environ.get("B200REC_K1_TMA"),
+                      "minb": os.environ.get("B200REC_K1_MINB"),
                       "two_tables_ms": a, "two_tables_GBps": alg / a / 1e6,
                       "fused_slots_ms": b, "fused_slots_GBps": alg / b / 1e6}), flush=True)
 
@@ -52,6 +53,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
+        if len(sys.argv) > 1 and sys.argv[1] == "minb":
+            for u, mb, ctas in (("13", "4", "8"), ("13", "5", "5"), ("13", "5", "10"), ("13", "6", "6"),
+                                ("13", "6", "12"), ("8", "6", "6"), ("8", "8", "8"), ("8", "8", "16")):
+                env = dict(os.environ, B200REC_K1_UNROLL=u, B200REC_K1_MINB=mb, B200REC_K1_CTAS=ctas)
+                subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
+            sys.exit(0)
         if len(sys.argv) > 1 and sys.argv[1] == "tma":
             for tma in ("0", "1"):
                 env = dict(os.environ, B200REC_K1_TMA=tma)
