@@ -10,7 +10,7 @@ non-lazy Adam would stream all V rows every step (77 GB at V=1e8, D=16).
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, List, Optional, Union
+from typing import Iterable, List, Optional
 
 import torch
 

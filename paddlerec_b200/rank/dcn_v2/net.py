@@ -123,11 +123,13 @@ class CrossNetV2(tnn.Module):
 
 
 def _xavier_normal(*shape):
-    t = torch.empty(*shape)
-    fan_in, fan_out = shape[-2] * (1 if len(shape) == 2 else 1), shape[-1]
-    if len(shape) == 3:   # paddle fans for a 3-D tensor: shape[0]*rf, shape[1]*rf with rf=shape[2]
-        fan_in, fan_out = shape[0] * shape[2], shape[1] * shape[2]
-    return t.normal_(0.0, math.sqrt(2.0 / (fan_in + fan_out)))
+    """paddle.nn.initializer.XavierNormal: N(0, 2/(fan_in+fan_out)); for an [E, in, r] parameter
+    Paddle's fans are shape[0]*r and shape[1]*r (receptive field = prod(shape[2:]))."""
+    rf = 1
+    for s in shape[2:]:
+        rf *= s
+    fan_in, fan_out = shape[0] * rf, shape[1] * rf
+    return torch.empty(*shape).normal_(0.0, math.sqrt(2.0 / (fan_in + fan_out)))
 
 
 class CrossNetMix(tnn.Module):
