@@ -15,10 +15,17 @@ committed tests/golden/*.npz were minted from that execution by tests/golden/mak
 So the composition of operators is the reference's; the per-operator semantics (Embedding
 padding, Linear layout, log_loss eps, softmax axis) are restated from Paddle's public docs.
 
+PINNED, in contrast: oracle/readers.py (the input-format row) — the reference's own
+tools/dataset/parser.cpp compiles from its single source file (oracle/Makefile -> oracle/_ref/
+criteo_parser) and its models/rank/deepfm/criteo_reader.py imports unmodified; the goldens
+tests/golden/criteo_tsv_parser_cpp.txt and slot_text_criteo_reader.npz are their outputs.
+
 Files
   nets.py         forward restatements (torch CPU, fp32/fp64), file:line cited per statement
   optim.py        row-wise optimizer rules (numpy)
   paddle_shim.py  the stand-in used to run the reference's net.py here
+  readers.py      the reference's text readers (slot:value, raw Criteo TSV, multislot) + the two
+                  string hashes they use, pure Python
   fm_ref.c        plain-C restatement of the fused FM forward/backward (double accumulation),
                   built by oracle/Makefile into oracle/_build/libfm_ref.so
 """

@@ -100,6 +100,20 @@ def create_data_loader(config, mode="train", rank=0, world_size=1):
     abs_dir = config["config_abs_dir"]
     data_dir = os.path.join(abs_dir, data_dir)
     file_list = [os.path.join(data_dir, x) for x in sorted(os.listdir(data_dir))]
+    reader_type = config.get("runner.reader_type", "DataLoader")
+    if reader_type == "PackedReader":
+        # native parser (dataio.py / libb200rec_io.so): Criteo `slot:value` files -> packed
+        # (label, ids, dense) batches in pinned memory; same sample order and drop-last rule
+        from . import dataio
+
+        fmt = config.get("runner.packed_format", "slot_text")
+        return dataio.PackedBatchReader(
+            file_list, batch_size=batch_size, fmt=fmt, drop_last=True,
+            threads=int(config.get("runner.reader_threads", 0)),
+            pin_memory=torch.cuda.is_available(), rank=rank, world_size=world_size,
+            shard_files=bool(config.get("runner.use_fleet", False)))
+    if reader_type != "DataLoader":
+        raise ValueError("runner.reader_type %r is not supported (DataLoader | PackedReader)" % reader_type)
     reader = _import_from_dir(abs_dir, reader_path)
     dataset = reader.RecDataset(file_list, config=config)
     return torch.utils.data.DataLoader(dataset, batch_size=batch_size, drop_last=True,

@@ -3,6 +3,7 @@ trainer.py:55-65), the Criteo and DIN readers, AUC, LR schedule, the oracle's op
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from paddlerec_b200 import functional as BF
@@ -49,6 +50,21 @@ def test_criteo_reader_contract():
                   "config_abs_dir": os.path.join(PKG, "rank", "deepfm")}
     batch = next(iter(runner.create_data_loader(loader_cfg)))
     assert len(batch) == 28 and batch[1].shape == (2, 1) and batch[27].shape == (2, 13)
+
+
+def test_packed_reader_type_yields_the_same_batches_as_the_dataloader():
+    cfg = {"runner.train_data_dir": "data/sample_data/train", "runner.train_batch_size": 16,
+           "runner.train_reader_path": "criteo_reader",
+           "config_abs_dir": os.path.join(PKG, "rank", "deepfm")}
+    plain = list(runner.create_data_loader(cfg))
+    packed = list(runner.create_data_loader({**cfg, "runner.reader_type": "PackedReader"}))
+    assert len(plain) == len(packed) == 5
+    for a, b in zip(plain, packed):
+        label, ids, dense = b
+        assert torch.equal(label, a[0]) and torch.equal(ids, torch.cat(a[1:27], 1))
+        assert torch.equal(dense, a[27])
+    with pytest.raises(ValueError, match="reader_type"):
+        runner.create_data_loader({**cfg, "runner.reader_type": "QueueDataset"})
 
 
 def test_din_reader_contract(tmp_path):
