@@ -46,3 +46,14 @@ def adagrad_row(W, g2sum, rows, g, lr, g0, lo, hi):
     W[rows] = np.clip(W[rows] - lr * g * scale, lo, hi)
     g2sum[rows] += (g * g).mean(1)
     return W, g2sum
+
+
+def clip_then_l2(grads, params, l2_coeffs, clip_norm=None):
+    """Dense-gradient preparation order of paddle.optimizer.Optimizer.apply_gradients (public API
+    docs): ClipGradByGlobalNorm first (models/rank/dcn_v2/dygraph_model.py:81-88), then each
+    parameter's ParamAttr regulariser, L2Decay(c): g += c * w (models/rank/dcn_v2/net.py:166-168)."""
+    grads = [np.asarray(g, np.float64) for g in grads]
+    if clip_norm is not None:
+        norm = np.sqrt(sum(float((g * g).sum()) for g in grads))
+        grads = [g * (clip_norm / max(norm, clip_norm)) for g in grads]
+    return [g + c * np.asarray(w, np.float64) for g, w, c in zip(grads, params, l2_coeffs)]

@@ -85,10 +85,14 @@ class Linear(tnn.Module):
     """paddle.nn.Linear: weight is [in_features, out_features] (transposed w.r.t. torch)."""
 
     def __init__(self, in_features: int, out_features: int, weight_std: Optional[float] = None,
-                 xavier: bool = False, bias: bool = True):
+                 xavier: bool = False, bias: bool = True, weight_l2_decay: float = 0.0):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.weight = tnn.Parameter(torch.empty(in_features, out_features))
+        if weight_l2_decay:
+            # ParamAttr(regularizer=L2Decay(c)): the optimizer adds c*w to this parameter's
+            # gradient (after clipping) — optim._Base._apply_regularizers
+            self.weight.l2_decay = float(weight_l2_decay)
         self.bias = tnn.Parameter(torch.zeros(out_features)) if bias else None
         if xavier:  # paddle XavierUniform: U(-sqrt(6/(fan_in+fan_out)), +)
             lim = math.sqrt(6.0 / (in_features + out_features))

@@ -95,6 +95,20 @@ class _Base:
                 sr.value.mul_(scale)
 
 
+    def _apply_regularizers(self) -> None:
+        """Per-parameter L2Decay set through ParamAttr (nn.Linear(weight_l2_decay=c), reference:
+        models/rank/dcn_v2/net.py:166-168): grad += c * param.  Paddle's Optimizer.apply_gradients
+        clips first and appends the regularisation term afterwards, so this runs after _apply_clip."""
+        for p in self._dense:
+            c = getattr(p, "l2_decay", 0.0)
+            if c and p.grad is not None:
+                p.grad.add_(p.detach(), alpha=c)
+
+    def _prepare_grads(self) -> None:
+        self._apply_clip()
+        self._apply_regularizers()
+
+
 class SGD(_Base):
     def __init__(self, learning_rate, parameters, grad_clip=None):
         super().__init__(learning_rate, parameters, grad_clip)
@@ -102,7 +116,7 @@ class SGD(_Base):
 
     @torch.no_grad()
     def step(self) -> None:
-        self._apply_clip()
+        self._prepare_grads()
         lr = self.get_lr()
         if self._torch is not None:
             for g in self._torch.param_groups:
@@ -148,7 +162,7 @@ class Adam(_Base):
 
     @torch.no_grad()
     def step(self) -> None:
-        self._apply_clip()
+        self._prepare_grads()
         lr = self.get_lr()
         self.step_count += 1
         if self._torch is not None:
@@ -187,6 +201,7 @@ class SparseAdaGrad(_Base):
 
     @torch.no_grad()
     def step(self) -> None:
+        self._apply_regularizers()
         if self._torch is not None:
             self._torch.step()
         for p in self._sparse:

@@ -7,7 +7,7 @@ CrossNetV2 layer is one library GEMM + the fused b200rec_cross_v2 epilogue; the 
 tensor-core tower (tower.py).  CrossNetMix is re-associated from the reference's per-sample
 [B,in,1] batched GEMVs into three batched GEMMs over all experts (mathematically identical).
 Quirks kept: Dropout(0.5) after every Linear AND every ReLU in train
-mode; dense_emb is a full Linear(13 -> 13*D).
+mode; L2Decay(1e-7) on the DNN weights (applied by the optimizer, optim._apply_regularizers); dense_emb is a full Linear(13 -> 13*D).
 """
 from __future__ import annotations
 
@@ -74,7 +74,8 @@ class DNNLayer(tnn.Module):
         sizes = [self.input_size] + list(layer_sizes)
         self._mlp_layers = []
         for i in range(len(layer_sizes)):
-            linear = bnn.Linear(sizes[i], sizes[i + 1], weight_std=1.0 / math.sqrt(sizes[i]))
+            linear = bnn.Linear(sizes[i], sizes[i + 1], weight_std=1.0 / math.sqrt(sizes[i]),
+                                weight_l2_decay=1e-7)   # L2Decay(1e-7), net.py:166-168
             self.add_module("linear_%d" % i, linear)
             self._mlp_layers.append(linear)
             act = tnn.ReLU()

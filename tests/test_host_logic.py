@@ -121,3 +121,27 @@ def test_oracle_optimizer_rules_against_torch():
     ids = np.array([3, 5, 3, 0, 5, 5])
     u, merged = oo.merge_rows(ids, np.ones((6, 2)), padding_idx=0)
     assert u.tolist() == [3, 5] and merged[:, 0].tolist() == [2.0, 3.0]
+
+
+def test_l2_decay_regularizer_is_added_after_clipping():
+    """ParamAttr(regularizer=L2Decay(c)) (dcn_v2/net.py:166-168): grad <- clip(grad) + c*w."""
+    from paddlerec_b200 import nn as bnn, optim
+
+    torch.manual_seed(0)
+    lin = bnn.Linear(4, 3, weight_std=0.5, weight_l2_decay=0.25)
+    assert lin.weight.l2_decay == 0.25 and not hasattr(lin.bias, "l2_decay")
+    w0, b0 = lin.weight.detach().clone(), lin.bias.detach().clone()
+    gw, gb = torch.randn(4, 3) * 5, torch.randn(3) * 5
+    lin.weight.grad, lin.bias.grad = gw.clone(), gb.clone()
+    opt = optim.SGD(0.1, lin.parameters(), grad_clip=optim.ClipGradByGlobalNorm(1.0))
+    opt.step()
+    from oracle import optim as ooptim
+
+    ow, ob = ooptim.clip_then_l2([gw.numpy(), gb.numpy()], [w0.numpy(), b0.numpy()], [0.25, 0.0], 1.0)
+    assert np.allclose(lin.weight.detach().numpy(), w0.numpy() - 0.1 * ow, atol=1e-6)
+    assert np.allclose(lin.bias.detach().numpy(), b0.numpy() - 0.1 * ob, atol=1e-6)
+    # the DCN-V2 tower carries the reference's coefficient
+    from paddlerec_b200.rank.dcn_v2 import net as dcn_net
+
+    dnn = dcn_net.DNNLayer(4, 13, 26, [8, 8])
+    assert [getattr(p, "l2_decay", 0.0) for n, p in dnn.named_parameters() if n.endswith("weight")] == [1e-7, 1e-7]
