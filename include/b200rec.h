@@ -239,6 +239,34 @@ int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V,
                             int64_t* perm, int32_t* inv_perm, int64_t* counts, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* ---- K6: DLRM dot interaction (models/rank/dlrm/net.py:98-113) -----------------------------------
+ * T [B, N, d]: the num_field embedding rows followed by the bottom-MLP output x as the LAST row.
+ * R [B, d + P]: R[:, :d] = x; R[:, d+p] = <T_i, T_j> over the upper triangle in row-major order,
+ * P = N(N-1)/2, or N(N+1)/2 with self_interaction — whose diagonal entries are 0, as the
+ * reference's triu(Z,1)+tril(MIN_FLOAT,-1)+masked_select evaluates (net.py:104-111).
+ * Backward: dT from dR (includes dR[:, :d] flowing into the x row).  N*(d+1)+N*N floats of shared
+ * memory per sample in flight must fit (N <= 128, d <= 256 checked). */
+int b200rec_dot_interact_fwd(const float* T, float* R, int64_t B, int N, int d, int self_interaction,
+                             void* stream);
+int b200rec_dot_interact_bwd(const float* T, const float* dR, float* dT, int64_t B, int N, int d,
+                             int self_interaction, void* stream);
+
+/* ---- uint64 feasigns -> table rows ----------------------------------------------------------------
+ * The PS / GPUBox path of the reference keys its sparse table by raw uint64 feasigns
+ * (tools/static_gpubox_trainer.py:152-159; `sparse_embedding` ignores its nominal size,
+ * models/rank/dnn/benchmark_gpubox.yaml); the dygraph path folds tokens into [0, V) on the host with
+ * a per-slot salted hash (models/rank/dnn/benchmark_reader.py:50-52).  This is that fold on the
+ * device, so a dense [V, D] HBM table can serve hashed keys with no host pass:
+ *   z      = keys[i] ^ ((slot_of_key ? slot_of_key[i] + 1 : 0) * 0x9E3779B97F4A7C15)
+ *   z      = splitmix64-finaliser(z)     (z ^= z>>30; z *= 0xBF58476D1CE4E5B9; z ^= z>>27;
+ *                                          z *= 0x94D049BB133111EB; z ^= z>>31)
+ *   rows[i]= reserve_zero ? (keys[i] == 0 ? 0 : 1 + z mod (V-1)) : z mod V
+ * reserve_zero keeps row 0 for "no feature" (feasign 0 is the padding key of the readers,
+ * models/rank/deepfm/criteo_reader.py:48,86-88).  Collisions share a row, exactly like the
+ * reference's `% hash_dim`.  HBM-bound: 16 (+4) bytes per key. */
+int b200rec_hash_keys(const uint64_t* keys, const int32_t* slot_of_key, int64_t n, int64_t V,
+                      int reserve_zero, int64_t* rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

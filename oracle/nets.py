@@ -188,3 +188,63 @@ def cvm(emb_with_show_click: torch.Tensor, use_cvm: bool) -> torch.Tensor:
     show = torch.log(emb_with_show_click[:, 0:1] + 1.0)
     click = torch.log(emb_with_show_click[:, 1:2] + 1.0) - show
     return torch.cat([show, click, emb_with_show_click[:, 2:]], 1)
+
+
+# ---- DLRM (models/rank/dlrm/net.py) ---------------------------------------------------------------
+def batch_norm_train(x, weight, bias, eps=1e-5):
+    """paddle.nn.BatchNorm1D in train mode (public API docs): per-feature batch mean and BIASED
+    batch variance, y = (x - mu) / sqrt(var + eps) * weight + bias."""
+    mu = x.mean(0, keepdim=True)
+    var = ((x - mu) ** 2).mean(0, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * weight + bias
+
+
+def batch_norm_running(mean, var, x, momentum=0.9):
+    """Running statistics after one train step: moving = moving*momentum + batch*(1-momentum), with
+    the biased batch variance (paddle.nn.BatchNorm1D docs)."""
+    mu = x.mean(0)
+    bv = ((x - mu) ** 2).mean(0)
+    return mean * momentum + mu * (1 - momentum), var * momentum + bv * (1 - momentum)
+
+
+def dlrm_mlp(p: Params, prefix: str, x, n_layers: int):
+    """MLPLayer.forward — dlrm/net.py:122-169.  The guard `i != len(units_list) - 1` (:136) is true
+    for every i of enumerate(units_list[:-1]), so EVERY layer, the last included, is
+    Linear -> ReLU -> BatchNorm1D and the `else` branch (:153-166) never runs."""
+    for i in range(n_layers):
+        x = linear(x, p["%sdense_%d.weight" % (prefix, i)], p["%sdense_%d.bias" % (prefix, i)])
+        x = torch.relu(x)
+        x = batch_norm_train(x, p["%snorm_%d.weight" % (prefix, i)], p["%snorm_%d.bias" % (prefix, i)])
+    return x
+
+
+def dot_interact(T, self_interaction: bool = False):
+    """net.py:104-113 on T [B, N, d] (x = last row): Z = T T^T; the strict upper triangle in
+    row-major order — with self_interaction the diagonal positions are selected too but hold 0,
+    because triu(Z, 1) has already zeroed them (:106-111); R = concat([x, Zflat])."""
+    B, N, d = T.shape
+    Z = torch.bmm(T, T.transpose(1, 2))
+    iu = torch.triu_indices(N, N, 0 if self_interaction else 1)
+    flat = Z[:, iu[0], iu[1]]
+    if self_interaction:
+        flat = torch.where((iu[0] == iu[1]).unsqueeze(0), torch.zeros((), dtype=T.dtype), flat)
+    return torch.cat([T[:, N - 1, :], flat], 1)
+
+
+def dlrm_forward(p: Params, sparse_inputs, dense_inputs, *, n_bot: int, n_top: int,
+                 self_interaction: bool = False):
+    """DLRMLayer.forward — dlrm/net.py:84-116.  Returns the raw [B, 2] scores (train mode)."""
+    x = dlrm_mlp(p, "bot_mlp.", dense_inputs, n_bot)                               # :93
+    d = x.shape[1]
+    embs = [embedding(p["embedding.weight"], s).reshape(-1, d) for s in sparse_inputs]  # :96-101
+    T = torch.cat(embs + [x], 1).reshape(x.shape[0], len(embs) + 1, d)             # :104-107
+    R = dot_interact(T, self_interaction)                                          # :110-123
+    return dlrm_mlp(p, "top_mlp.", R, n_top)                                       # :125
+
+
+def softmax_cross_entropy(logits, label):
+    """paddle.nn.functional.cross_entropy(input, label) with hard int64 labels [B,1], mean
+    (dlrm/dygraph_model.py:57-61)."""
+    lse = torch.logsumexp(logits, 1)
+    picked = logits.gather(1, label.reshape(-1, 1).to(torch.int64)).squeeze(1)
+    return (lse - picked).mean()

@@ -168,6 +168,31 @@ class Dropout(Layer):
         return tnn.functional.dropout(x, self.p, self.training)
 
 
+class BatchNorm1D(Layer):
+    """paddle.nn.BatchNorm1D(num_features, momentum=0.9, epsilon=1e-05): state `weight`, `bias`,
+    `_mean`, `_variance`; train mode normalises with the batch mean and the biased batch variance
+    and moves the running statistics by (1 - momentum)."""
+
+    def __init__(self, num_features, momentum=0.9, epsilon=1e-05, **kw):
+        super().__init__()
+        self.weight = tnn.Parameter(torch.ones(num_features))
+        self.bias = tnn.Parameter(torch.zeros(num_features))
+        self.register_buffer("_mean", torch.zeros(num_features))
+        self.register_buffer("_variance", torch.ones(num_features))
+        self._momentum, self._epsilon = momentum, epsilon
+
+    def forward(self, x):
+        if self.training:
+            mu = x.mean(0)
+            var = ((x - mu) ** 2).mean(0)
+            with torch.no_grad():
+                self._mean.mul_(self._momentum).add_(mu.detach() * (1 - self._momentum))
+                self._variance.mul_(self._momentum).add_(var.detach() * (1 - self._momentum))
+        else:
+            mu, var = self._mean, self._variance
+        return (x - mu) / torch.sqrt(var + self._epsilon) * self.weight + self.bias
+
+
 class LayerList(tnn.ModuleList):
     pass
 
@@ -216,7 +241,8 @@ def install():
     paddle.framework, paddle.regularizer, paddle.io = framework, regularizer, io
     paddle.distributed, paddle.static = dist, static
 
-    for cls in (Layer, Embedding, Linear, ReLU, Sigmoid, Dropout, LayerList, ParameterList):
+    for cls in (Layer, Embedding, Linear, ReLU, Sigmoid, Dropout, LayerList, ParameterList,
+                BatchNorm1D):
         setattr(nn, cls.__name__, cls)
     nn.Conv1D = type("Conv1D", (Layer,), {})  # imported (never used) by din/net.py:13
     for cls in (TruncatedNormal, Normal, Constant, Uniform, XavierUniform, XavierNormal):
@@ -243,6 +269,13 @@ def install():
     paddle.cast = lambda x, dtype: x.to(dtype)
     paddle.mean = lambda x: x.mean()
     paddle.to_tensor = torch.as_tensor
+    # dlrm/net.py:104-111
+    paddle.bmm = torch.bmm
+    paddle.triu = lambda x, diagonal=0: torch.triu(x, diagonal)
+    paddle.tril = lambda x, diagonal=0: torch.tril(x, diagonal)
+    paddle.ones_like = torch.ones_like
+    paddle.greater_than = lambda x, y: x > y
+    paddle.masked_select = lambda x, mask: torch.masked_select(x, mask)
     F.sigmoid = torch.sigmoid
     F.softmax = _softmax
     F.relu = torch.relu

@@ -166,3 +166,28 @@ def multislot_lines(lines: Sequence[str], slot_is_float: Sequence[bool]):
         assert at == len(toks)
         out.append(row)
     return out
+
+
+# ---- device-side feasign fold (include/b200rec.h: b200rec_hash_keys) --------------------------------
+def hash_keys(keys: np.ndarray, V: int, slot_of_key=None, reserve_zero: bool = True) -> np.ndarray:
+    """numpy restatement of the uint64 feasign -> row fold: splitmix64 finaliser of
+    key ^ (slot+1)*golden, then `% (V-1) + 1` (row 0 reserved for feasign 0, the readers' padding
+    key — criteo_reader.py:48,86-88) or `% V`.  The reference folds on the host with
+    xxh32(str(slot)+token) % hash_dim (benchmark_reader.py:50-52); this is the same contract
+    (deterministic, slot-salted, uniform over rows) with a 64-bit mixer that needs no string."""
+    k = np.asarray(keys).astype(np.uint64)
+    z = k.copy()
+    if slot_of_key is not None:
+        salt = (np.asarray(slot_of_key).astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = z ^ salt
+    z ^= z >> np.uint64(30)
+    z *= np.uint64(0xBF58476D1CE4E5B9)
+    z ^= z >> np.uint64(27)
+    z *= np.uint64(0x94D049BB133111EB)
+    z ^= z >> np.uint64(31)
+    if reserve_zero:
+        r = np.uint64(1) + z % np.uint64(V - 1)
+        r = np.where(k == 0, np.uint64(0), r)
+    else:
+        r = z % np.uint64(V)
+    return r.astype(np.int64)

@@ -107,6 +107,9 @@ _SIG = {
     "b200rec_tower_relu_bwd_split": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "b200rec_tower_prep_weight": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "b200rec_tower_fold_dw": (c_int, [_P, _P, c_int, c_int, _P]),
+    "b200rec_dot_interact_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "b200rec_dot_interact_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "b200rec_hash_keys": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "b200rec_shard_bucketize_workspace_bytes": (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     "b200rec_shard_bucketize": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, c_size_t,
                                         _P]),

@@ -12,6 +12,8 @@
 #include "shard.cuh"
 #include "tower.cuh"
 #include "cvm.cuh"
+#include "hash_keys.cuh"
+#include "dot_interact.cuh"
 #include "din_attn.cuh"
 
 namespace b200rec {
@@ -306,6 +308,52 @@ int b200rec_cvm_bwd(const float* dy, const float* show_click, float* dx, int64_t
   const int64_t total = N * (D + 2);
   const unsigned grid = (unsigned)min((total + 255) / 256, (int64_t)sm_count() * 16);
   cvm_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(dy, show_click, dx, N, D, use_cvm);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static int dot_interact_launch(bool bwd, const float* T, const float* dR, float* out, int64_t B, int N,
+                               int d, int self_interaction, void* stream) {
+  B200_REQUIRE(B >= 0 && N >= 2 && N <= 128 && d >= 1 && d <= 256, "dot_interact: bad sizes");
+  if (B == 0) return B200REC_OK;
+  NOT_NULL(T); NOT_NULL(out);
+  const DotShape s(N, d, self_interaction ? 1 : 0);
+  const size_t smem = kDotWarps * sizeof(float) * (bwd ? s.smem_floats_bwd() : s.smem_floats_fwd());
+  B200_REQUIRE(smem <= 200 * 1024, "dot_interact: N*d too large for shared memory");
+  const int64_t ctas = (B + kDotWarps - 1) / kDotWarps;
+  const unsigned grid = (unsigned)min(ctas, (int64_t)sm_count() * 8);
+  if (bwd) {
+    NOT_NULL(dR);
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(dot_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dot_interact_bwd_kernel<<<grid, kDotWarps * 32, smem, ST(stream)>>>(T, dR, out, B, s);
+  } else {
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(dot_interact_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dot_interact_fwd_kernel<<<grid, kDotWarps * 32, smem, ST(stream)>>>(T, out, B, s);
+  }
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_dot_interact_fwd(const float* T, float* R, int64_t B, int N, int d, int self_interaction,
+                             void* stream) {
+  return dot_interact_launch(false, T, nullptr, R, B, N, d, self_interaction, stream);
+}
+
+int b200rec_dot_interact_bwd(const float* T, const float* dR, float* dT, int64_t B, int N, int d,
+                             int self_interaction, void* stream) {
+  return dot_interact_launch(true, T, dR, dT, B, N, d, self_interaction, stream);
+}
+
+int b200rec_hash_keys(const uint64_t* keys, const int32_t* slot_of_key, int64_t n, int64_t V,
+                      int reserve_zero, int64_t* rows, void* stream) {
+  B200_REQUIRE(n >= 0, "hash_keys: n < 0");
+  B200_REQUIRE(V >= (reserve_zero ? 2 : 1), "hash_keys: table too small for the requested fold");
+  if (n == 0) return B200REC_OK;
+  NOT_NULL(keys); NOT_NULL(rows);
+  const unsigned grid = (unsigned)min((n + 255) / 256, (int64_t)sm_count() * 16);
+  hash_keys_kernel<<<grid, 256, 0, ST(stream)>>>(keys, slot_of_key, n, (uint64_t)V, reserve_zero, rows);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

@@ -1,0 +1,120 @@
+// K6 — DLRM dot interaction (models/rank/dlrm/net.py:98-113), forward and backward.
+//
+//   T [B, N, d]   N = num_field + 1 feature vectors per sample: the 26 embedding rows, then the
+//                 bottom-MLP output x as the LAST row (net.py:98-101)
+//   R [B, d + P]  R[:, :d] = x  (the concat of net.py:113 fused in),
+//                 R[:, d + p] = <T_i, T_j> for the pairs (i, j) of the upper triangle in row-major
+//                 order; P = N(N-1)/2 (i < j), or N(N+1)/2 with self_interaction, where — exactly
+//                 as the reference's triu(Z,1) + tril(MIN_FLOAT,-1) + masked_select evaluates —
+//                 the diagonal entries are selected but carry 0, not <T_i, T_i> (net.py:104-111).
+//
+// One warp per sample, persistent grid.  The sample's N*d floats are staged in shared memory with a
+// row pitch of d+1 (consecutive pairs differ in j, so lanes hit consecutive rows: pitch d+1 is
+// conflict-free, the shared i row is a broadcast); lanes then own pairs p = lane, lane+32, ... and
+// write R coalesced.  Backward stages T the same way, mirrors dZ into a full N x N matrix
+// with a zero diagonal, and lane (i, c) accumulates dT[i][c] = sum_j dZ[i][j] * T[j][c]
+// (+ dR[:, c] for the x row) — no atomics, deterministic.  HBM-bound: algorithmic bytes per sample 4*(N*d + d + P) forward (3 196 B at
+// N=27, d=16) and 4*(2*N*d + d + P) backward.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200rec {
+
+constexpr int kDotWarps = 4;  // samples in flight per CTA
+
+struct DotShape {
+  int N, d, self, P, pitch;
+  __host__ __device__ DotShape(int N_, int d_, int self_)
+      : N(N_), d(d_), self(self_), P(self_ ? N_ * (N_ + 1) / 2 : N_ * (N_ - 1) / 2), pitch(d_ + 1) {}
+  // first output index of row i of the (strict / with-diagonal) upper triangle
+  __host__ __device__ int row_start(int i) const {
+    return self ? i * N - i * (i - 1) / 2 : i * (N - 1) - i * (i - 1) / 2;
+  }
+  __host__ __device__ int row_len(int i) const { return self ? N - i : N - 1 - i; }
+  // output index of the pair (i, j), i < j (or i <= j with self)
+  __host__ __device__ int pair(int i, int j) const { return row_start(i) + (self ? j - i : j - i - 1); }
+  __host__ __device__ size_t smem_floats_fwd() const { return (size_t)N * pitch; }
+  __host__ __device__ size_t smem_floats_bwd() const { return (size_t)N * pitch + (size_t)N * N; }
+};
+
+__device__ __forceinline__ void dot_stage_rows(const float* __restrict__ src, float* __restrict__ dst,
+                                               const DotShape& s, int lane) {
+  const int total = s.N * s.d;
+  for (int e = lane; e < total; e += 32) {
+    const int r = e / s.d, c = e - r * s.d;
+    dst[r * s.pitch + c] = __ldg(src + e);
+  }
+}
+
+__global__ void __launch_bounds__(kDotWarps * 32)
+dot_interact_fwd_kernel(const float* __restrict__ T, float* __restrict__ R, int64_t B, DotShape s) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = smem + (size_t)warp * s.smem_floats_fwd();
+  const int out_w = s.d + s.P;
+  for (int64_t b = (int64_t)blockIdx.x * kDotWarps + warp; b < B; b += (int64_t)gridDim.x * kDotWarps) {
+    dot_stage_rows(T + b * s.N * s.d, tile, s, lane);
+    __syncwarp();
+    float* out = R + b * out_w;
+    for (int c = lane; c < s.d; c += 32) __stcs(out + c, tile[(s.N - 1) * s.pitch + c]);
+    // walk the triangle: (i, j) of this lane's first pair, then advance by 32 pairs each round
+    int i = 0, off = lane;  // off = position inside row i
+    for (int p = lane; p < s.P; p += 32) {
+      while (off >= s.row_len(i)) { off -= s.row_len(i); ++i; }
+      const int j = s.self ? i + off : i + 1 + off;
+      float acc = 0.f;
+      if (j != i) {
+        const float* a = tile + i * s.pitch;
+        const float* bb = tile + j * s.pitch;
+#pragma unroll 4
+        for (int c = 0; c < s.d; ++c) acc = fmaf(a[c], bb[c], acc);
+      }
+      __stcs(out + s.d + p, acc);
+      off += 32;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kDotWarps * 32)
+dot_interact_bwd_kernel(const float* __restrict__ T, const float* __restrict__ dR,
+                        float* __restrict__ dT, int64_t B, DotShape s) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = smem + (size_t)warp * s.smem_floats_bwd();
+  float* dzf = tile + (size_t)s.N * s.pitch;  // dZ mirrored into a full N x N matrix, zero diagonal
+  const int out_w = s.d + s.P;
+  for (int64_t b = (int64_t)blockIdx.x * kDotWarps + warp; b < B; b += (int64_t)gridDim.x * kDotWarps) {
+    dot_stage_rows(T + b * s.N * s.d, tile, s, lane);
+    const float* g = dR + b * out_w;
+    for (int i = lane; i < s.N; i += 32) dzf[i * s.N + i] = 0.f;
+    {
+      int i = 0, off = lane;
+      for (int p = lane; p < s.P; p += 32) {
+        while (off >= s.row_len(i)) { off -= s.row_len(i); ++i; }
+        const int j = s.self ? i + off : i + 1 + off;
+        if (j != i) {
+          const float v = __ldg(g + s.d + p);
+          dzf[i * s.N + j] = v;
+          dzf[j * s.N + i] = v;
+        }
+        off += 32;
+      }
+    }
+    __syncwarp();
+    float* out = dT + b * s.N * s.d;
+    const int total = s.N * s.d;
+    for (int e = lane; e < total; e += 32) {
+      const int i = e / s.d, c = e - i * s.d;
+      float acc = (i == s.N - 1) ? __ldg(g + c) : 0.f;   // x is both the last row of T and R[:, :d]
+      const float* zr = dzf + i * s.N;
+#pragma unroll 3
+      for (int j = 0; j < s.N; ++j) acc = fmaf(zr[j], tile[j * s.pitch + c], acc);
+      __stcs(out + e, acc);                                // the diagonal carries no gradient
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace b200rec

@@ -65,3 +65,35 @@ def auc_from_stats(pos: np.ndarray, neg: np.ndarray) -> float:
         tot_neg += neg[idx]
         auc += abs(tot_neg - tot_neg_prev) * (tot_pos + tot_pos_prev) / 2.0
     return auc / tot_pos / tot_neg if tot_pos > 0.0 and tot_neg > 0.0 else 0.0
+
+
+def softmax_cross_entropy(logits: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """paddle.nn.functional.cross_entropy(input, label) with hard labels [B,1] (per-sample, no
+    reduction; models/rank/dlrm/dygraph_model.py:57-61 takes the mean)."""
+    return torch.nn.functional.cross_entropy(logits, label.reshape(-1).to(torch.int64),
+                                             reduction="none").unsqueeze(1)
+
+
+class Accuracy:
+    """paddle.metric.Accuracy() top-1: `compute(pred, label)` -> per-sample correctness,
+    `update(correct)` accumulates, `accumulate()` -> running accuracy.  Counters stay on the device
+    until accumulate()."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self._correct = None
+        self._total = 0
+
+    def compute(self, pred: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+        return (pred.argmax(dim=1, keepdim=True) == label.reshape(-1, 1).to(pred.device)).to(torch.float32)
+
+    def update(self, correct: torch.Tensor):
+        c = correct.detach().sum()
+        self._correct = c if self._correct is None else self._correct + c
+        self._total += correct.shape[0]
+        return self
+
+    def accumulate(self) -> float:
+        return float(self._correct) / self._total if self._total else 0.0

@@ -85,7 +85,8 @@ class Linear(tnn.Module):
     """paddle.nn.Linear: weight is [in_features, out_features] (transposed w.r.t. torch)."""
 
     def __init__(self, in_features: int, out_features: int, weight_std: Optional[float] = None,
-                 xavier: bool = False, bias: bool = True, weight_l2_decay: float = 0.0):
+                 xavier: bool = False, bias: bool = True, weight_l2_decay: float = 0.0,
+                 truncated: bool = False):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.weight = tnn.Parameter(torch.empty(in_features, out_features))
@@ -97,6 +98,8 @@ class Linear(tnn.Module):
         if xavier:  # paddle XavierUniform: U(-sqrt(6/(fan_in+fan_out)), +)
             lim = math.sqrt(6.0 / (in_features + out_features))
             tnn.init.uniform_(self.weight, -lim, lim)
+        elif weight_std is not None and truncated:  # paddle TruncatedNormal(std): resample beyond 2 sigma
+            tnn.init.trunc_normal_(self.weight, 0.0, weight_std, -2.0 * weight_std, 2.0 * weight_std)
         elif weight_std is not None:
             tnn.init.normal_(self.weight, 0.0, weight_std)
         else:  # paddle.nn.Linear default: XavierUniform as well
@@ -107,6 +110,34 @@ class Linear(tnn.Module):
         lead = x.shape[:-1]
         y = _LinearFn.apply(x.reshape(-1, self.in_features), self.weight, self.bias)
         return y.reshape(*lead, self.out_features)
+
+
+class BatchNorm1D(tnn.Module):
+    """paddle.nn.BatchNorm1D(num_features, momentum=0.9, epsilon=1e-5) on [B, C] activations: state
+    `weight`, `bias`, `_mean`, `_variance` (the reference's checkpoint names).  Train mode
+    normalises with the batch mean and the biased batch variance (library kernel:
+    torch.nn.functional.batch_norm) and moves the running statistics by (1 - momentum) with the
+    BIASED variance, which is Paddle's rule — torch's own running update uses the unbiased one, so
+    the buffers are updated here, not by the library call."""
+
+    def __init__(self, num_features: int, momentum: float = 0.9, epsilon: float = 1e-5):
+        super().__init__()
+        self.weight = tnn.Parameter(torch.ones(num_features))
+        self.bias = tnn.Parameter(torch.zeros(num_features))
+        self.register_buffer("_mean", torch.zeros(num_features))
+        self.register_buffer("_variance", torch.ones(num_features))
+        self.momentum, self.epsilon = momentum, epsilon
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.training:
+            return torch.nn.functional.batch_norm(x, self._mean, self._variance, self.weight,
+                                                  self.bias, False, 0.0, self.epsilon)
+        with torch.no_grad():
+            var, mu = torch.var_mean(x, dim=0, unbiased=False)
+            self._mean.mul_(self.momentum).add_(mu, alpha=1.0 - self.momentum)
+            self._variance.mul_(self.momentum).add_(var, alpha=1.0 - self.momentum)
+        return torch.nn.functional.batch_norm(x, None, None, self.weight, self.bias, True, 0.0,
+                                              self.epsilon)
 
 
 _HOOKS = {}

@@ -43,7 +43,7 @@ KERNELS_PER_CALL = {
     "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
     "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
-    "tower_prep_weight": 1, "tower_fold_dw": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1,
+    "tower_prep_weight": 1, "tower_fold_dw": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
 EVENTS = None
@@ -559,6 +559,83 @@ class _CrossV2(torch.autograd.Function):
             dxl = dout + ctx.mm(dxw, W.t())
             dW = ctx.mm(xl.t(), dxw)
         return dx0, dxl, dW, dbias, None, None
+
+
+# ---- K6: DLRM dot interaction --------------------------------------------------------------------
+def dot_interact_width(N: int, d: int, self_interaction: bool = False) -> int:
+    return d + (N * (N + 1) // 2 if self_interaction else N * (N - 1) // 2)
+
+
+def raw_dot_interact_fwd(T: torch.Tensor, self_interaction: bool = False) -> torch.Tensor:
+    """T [B, N, d] (x is the last row) -> R [B, d + P] = [x | upper-triangle dots]."""
+    lib = _lib.load()
+    T = _req(T, torch.float32, "T")
+    B, N, d = T.shape
+    R = torch.empty(B, dot_interact_width(N, d, self_interaction), dtype=torch.float32,
+                    device=T.device)
+    check(lib.b200rec_dot_interact_fwd(ptr(T), ptr(R), B, N, d, int(bool(self_interaction)),
+                                       _stream()), "dot_interact_fwd")
+    _count("dot_interact_fwd")
+    return R
+
+
+def raw_dot_interact_bwd(T: torch.Tensor, dR: torch.Tensor, self_interaction: bool = False) -> torch.Tensor:
+    lib = _lib.load()
+    T = _req(T, torch.float32, "T")
+    dR = _req(dR, torch.float32, "dR")
+    B, N, d = T.shape
+    if dR.shape != (B, dot_interact_width(N, d, self_interaction)):
+        raise ValueError("dot_interact_bwd: dR has shape %s" % (tuple(dR.shape),))
+    dT = torch.empty_like(T)
+    check(lib.b200rec_dot_interact_bwd(ptr(T), ptr(dR), ptr(dT), B, N, d,
+                                       int(bool(self_interaction)), _stream()), "dot_interact_bwd")
+    _count("dot_interact_bwd")
+    return dT
+
+
+class _DotInteract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, T, self_interaction):
+        T = T.contiguous()
+        ctx.save_for_backward(T)
+        ctx.self_interaction = self_interaction
+        return raw_dot_interact_fwd(T, self_interaction)
+
+    @staticmethod
+    def backward(ctx, dR):
+        (T,) = ctx.saved_tensors
+        return raw_dot_interact_bwd(T, dR.contiguous(), ctx.self_interaction), None
+
+
+def dot_interact(T: torch.Tensor, self_interaction: bool = False) -> torch.Tensor:
+    """DLRM's pairwise-dot feature interaction with the `concat([x, Zflat])` fused in
+    (models/rank/dlrm/net.py:98-113); T = [26 embedding rows ..., x]."""
+    return _DotInteract.apply(T, self_interaction)
+
+
+# ---- uint64 feasigns -> rows ---------------------------------------------------------------------
+def raw_hash_keys(keys: torch.Tensor, V: int, slot_of_key: Optional[torch.Tensor] = None,
+                  reserve_zero: bool = True) -> torch.Tensor:
+    """keys: uint64 (or int64 holding the same bits) feasigns, any shape -> int64 rows in [0, V) of
+    the same shape; slot_of_key: int32 per key (salts the hash per slot) or None."""
+    lib = _lib.load()
+    if keys.dtype not in (torch.uint64, torch.int64):
+        raise TypeError("hash_keys: keys must be uint64 or int64, got %s" % keys.dtype)
+    if not keys.is_cuda:
+        raise _lib.B200RecError("hash_keys: keys must be a CUDA tensor (no CPU fallback)")
+    keys = keys.contiguous()
+    if slot_of_key is not None:
+        slot_of_key = _req(slot_of_key, torch.int32, "slot_of_key")
+        if slot_of_key.numel() != keys.numel():
+            raise ValueError("hash_keys: slot_of_key must have one entry per key")
+    rows = torch.empty(keys.shape, dtype=torch.int64, device=keys.device)
+    check(lib.b200rec_hash_keys(ptr(keys), ptr(slot_of_key), keys.numel(), int(V),
+                                int(bool(reserve_zero)), ptr(rows), _stream()), "hash_keys")
+    _count("hash_keys")
+    return rows
+
+
+hash_keys = raw_hash_keys
 
 
 # ---- continuous_value_model ---------------------------------------------------------------------

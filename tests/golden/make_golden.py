@@ -154,6 +154,29 @@ def make_wide_deep():
          grads_of(loss, named))
 
 
+def make_dlrm(self_interaction, tag):
+    """dlrm/net.py in TRAIN mode (BatchNorm uses batch statistics); also stores the running
+    statistics after the step under `buf/<name>`-style params (`_mean`, `_variance`)."""
+    ref = paddle_shim.import_reference_net("dlrm")
+    torch.manual_seed(777)
+    V, D, F, Dn, bot, top = 257, 8, 26, 13, [32, 16, 8], [32, 16, 2]
+    layer = ref.DLRMLayer(Dn, bot, V, D, top, F, self_interaction=self_interaction)
+    layer.train()
+    g = torch.Generator().manual_seed(99)
+    ids, dense, label = criteo_batch(g, 11, V)  # no padding_idx: id 0 is a real row
+    sparse_inputs = [ids[:, i:i + 1] for i in range(F)]
+    named = dict(layer.named_parameters())
+    pred = layer(sparse_inputs, dense)           # raw [B, 2] scores
+    loss = nets.softmax_cross_entropy(pred, label)
+    check_oracle("dlrm_" + tag, pred, nets.dlrm_forward(named, sparse_inputs, dense, n_bot=len(bot),
+                                                        n_top=len(top),
+                                                        self_interaction=self_interaction))
+    params = dict(named)
+    params.update({k: v for k, v in layer.named_buffers()})   # running stats AFTER this step
+    save("dlrm_" + tag, params, {"ids": ids, "dense": dense, "label": label}, pred, loss,
+         grads_of(loss, named))
+
+
 if __name__ == "__main__":
     torch.set_default_dtype(torch.float64)
     make_deepfm(9, "d9")      # the reference's own D (config.yaml:51): scalar row path
@@ -162,3 +185,5 @@ if __name__ == "__main__":
     make_dcn_v2(True, False, "mix_parallel")
     make_din()
     make_wide_deep()
+    make_dlrm(False, "pairs")
+    make_dlrm(True, "self")

@@ -478,3 +478,110 @@ def test_gather_pool_sum_lod(D):
     (out * gout.to(DEV)).sum().backward()
     (ref * gout.double()).sum().backward()
     assert rel_err(emb.grad_rows.to_dense(), Wr.grad) < 3e-6
+
+
+# ---- uint64 feasigns -> rows (E2 / §8(f) row 2) ---------------------------------------------------
+@pytest.mark.parametrize("V,reserve_zero", [(1000001, True), (2, True), (1, False), (10**8, False),
+                                            ((1 << 40) + 7, True)])
+def test_hash_keys_bit_exact(V, reserve_zero):
+    from oracle import readers
+
+    ops = _ops()
+    rng = np.random.default_rng(V % 97)
+    n = 100003
+    keys = rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    keys[:5] = np.array([0, 1, (1 << 64) - 1, 1 << 63, 0], np.uint64)
+    slots = rng.integers(0, 26, n).astype(np.int32)
+    for sl in (None, slots):
+        want = readers.hash_keys(keys, V, sl, reserve_zero)
+        got = ops.raw_hash_keys(torch.from_numpy(keys).to(DEV), V,
+                                None if sl is None else torch.from_numpy(sl).to(DEV), reserve_zero)
+        assert got.dtype == torch.int64 and got.shape == (n,)
+        assert np.array_equal(got.cpu().numpy(), want)
+        assert want.min() >= 0 and want.max() < V
+        if reserve_zero:
+            assert (want[keys == 0] == 0).all() and (want[keys != 0] >= 1).all()
+    # int64 tensors holding the same bits give the same rows; shape is preserved
+    as_i64 = torch.from_numpy(keys.view(np.int64)).to(DEV).reshape(-1, 1)[: n - 3]
+    got2 = ops.raw_hash_keys(as_i64, V, None, reserve_zero)
+    assert got2.shape == as_i64.shape
+    assert np.array_equal(got2.cpu().numpy()[:, 0], readers.hash_keys(keys[: n - 3], V, None, reserve_zero))
+
+
+def test_hash_keys_feeds_the_gather_and_spreads_uniformly():
+    """Hashed multi-slot lookup end to end: parse -> fold on the device -> gather; and the fold's
+    occupancy over V rows is that of a uniform hash (no slot aliasing)."""
+    from oracle import readers
+
+    ops = _ops()
+    V, D, n = 4096, 16, 1 << 18
+    rng = np.random.default_rng(7)
+    raw = rng.integers(1, 5000, n).astype(np.uint64)          # small raw ids, as in real logs
+    slots = rng.integers(0, 26, n).astype(np.int32)
+    rows = ops.raw_hash_keys(torch.from_numpy(raw).to(DEV), V, torch.from_numpy(slots).to(DEV), True)
+    assert np.array_equal(rows.cpu().numpy(), readers.hash_keys(raw, V, slots, True))
+    counts = torch.bincount(rows, minlength=V).double()[1:]
+    distinct = len(set(zip(raw.tolist(), slots.tolist())))
+    # balls-in-bins: expected empty fraction exp(-distinct/(V-1)); none here, and max load bounded
+    assert (counts == 0).float().mean() < 0.01 and counts.max() < 12 * n / (V - 1)
+    assert distinct > 100000
+    W = torch.randn(V, D, device=DEV)
+    W[0] = 0
+    out = ops.raw_gather(W, rows, 0)
+    assert torch.equal(out, W[rows])
+
+
+def test_hash_keys_rejects_bad_arguments():
+    ops = _ops()
+    from paddlerec_b200._lib import B200RecError
+
+    k = torch.zeros(4, dtype=torch.uint64, device=DEV)
+    with pytest.raises(B200RecError, match="too small"):
+        ops.raw_hash_keys(k, 1, None, True)
+    with pytest.raises(TypeError):
+        ops.raw_hash_keys(k.to(torch.float32), 10)
+    with pytest.raises(B200RecError, match="CUDA"):
+        ops.raw_hash_keys(torch.zeros(4, dtype=torch.int64), 10)
+    assert ops.raw_hash_keys(k[:0], 10).numel() == 0
+
+
+# ---- K6: DLRM dot interaction ----------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,d", [(1, 2, 1), (5, 5, 3), (33, 27, 16), (1000, 27, 16), (7, 27, 9),
+                                   (64, 40, 64), (9, 27, 128), (3, 128, 4)])
+@pytest.mark.parametrize("self_interaction", [False, True])
+def test_dot_interact_fwd_bwd(B, N, d, self_interaction):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + N * 10 + d)
+    T = torch.randn(B, N, d, generator=g, dtype=torch.float64)
+    Tref = T.clone().requires_grad_(True)
+    Rref = nets.dot_interact(Tref, self_interaction)
+    dR = torch.randn(Rref.shape, generator=g, dtype=torch.float64)
+    Rref.backward(dR)
+    Tg = T.to(torch.float32).to(DEV).requires_grad_(True)
+    R = ops.dot_interact(Tg, self_interaction)
+    assert R.shape == Rref.shape == (B, ops.dot_interact_width(N, d, self_interaction))
+    R.backward(dR.to(torch.float32).to(DEV))
+    # d-term fp32 dot products vs float64: 2e-6 of the largest magnitude
+    assert rel_err(R, Rref) < 2e-6
+    assert rel_err(Tg.grad, Tref.grad) < 2e-6
+    assert torch.equal(R[:, :d], Tg.detach()[:, N - 1])          # the x block is a copy
+    if self_interaction:
+        iu = torch.triu_indices(N, N, 0)
+        assert (R[:, d:][:, (iu[0] == iu[1]).to(DEV)] == 0).all()  # the reference's zero diagonal
+    # deterministic: no atomics anywhere
+    R2 = ops.raw_dot_interact_fwd(Tg.detach(), self_interaction)
+    dT2 = ops.raw_dot_interact_bwd(Tg.detach(), dR.to(torch.float32).to(DEV), self_interaction)
+    assert torch.equal(R2, R.detach()) and torch.equal(dT2, Tg.grad)
+
+
+def test_dot_interact_rejects_bad_shapes():
+    ops = _ops()
+    from paddlerec_b200._lib import B200RecError
+
+    with pytest.raises(B200RecError, match="bad sizes"):
+        ops.raw_dot_interact_fwd(torch.zeros(2, 1, 4, device=DEV))            # N < 2
+    with pytest.raises(B200RecError, match="bad sizes"):
+        ops.raw_dot_interact_fwd(torch.zeros(2, 129, 4, device=DEV))
+    with pytest.raises(ValueError):
+        ops.raw_dot_interact_bwd(torch.zeros(2, 3, 4, device=DEV), torch.zeros(2, 5, device=DEV))
+    assert ops.raw_dot_interact_fwd(torch.zeros(0, 3, 4, device=DEV)).shape == (0, 7)

@@ -134,6 +134,45 @@ def test_wide_deep_golden(precision):
         bnn.set_matmul_precision("fp32")
 
 
+@pytest.mark.parametrize("name,self_interaction", [("dlrm_pairs", False), ("dlrm_self", True)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_dlrm_golden(name, self_interaction, precision):
+    """Train-mode forward (BatchNorm on batch statistics), softmax cross-entropy, every gradient and
+    the running statistics after the step, against the reference's own dlrm/net.py (golden)."""
+    from paddlerec_b200 import functional as BF
+    from paddlerec_b200 import nn as bnn
+    from paddlerec_b200.rank.dlrm import net
+    g = load_golden(name)
+    V, D = g["param"]["embedding.weight"].shape
+    bot = [g["param"]["bot_mlp.dense_%d.weight" % i].shape[1] for i in range(3)]
+    top = [g["param"]["top_mlp.dense_%d.weight" % i].shape[1] for i in range(3)]
+    stats = {k: v for k, v in g["param"].items() if k.endswith("._mean") or k.endswith("._variance")}
+    g2 = dict(g)
+    g2["param"] = {k: v for k, v in g["param"].items() if k not in stats}
+    bnn.set_matmul_precision(precision)
+    try:
+        layer = load_state(net.DLRMLayer(13, bot, V, D, top, 26, self_interaction=self_interaction), g2)
+        layer.train()
+        ids, dense, label = _criteo_inputs(g)
+        pred = layer([ids[:, i:i + 1] for i in range(26)], dense)
+        assert pred.shape == (ids.shape[0], 2)
+        loss = BF.softmax_cross_entropy(pred, label.to(torch.int64)).mean()
+        loss.backward()
+        check(g2, pred, loss, grads_of(layer))
+        sd = layer.state_dict()
+        for k, v in stats.items():          # Paddle's rule: biased batch variance, momentum 0.9
+            assert rel_err(sd[k], v) < TOL, k
+        assert np.abs(grads_of(layer)["embedding.weight"][0]).max() > 0   # id 0 is a real row
+        # eval mode runs on the running statistics and is deterministic
+        layer.eval()
+        with torch.no_grad():
+            e1 = layer(ids, dense)
+            e2 = layer(ids, dense)
+        assert torch.equal(e1, e2) and not torch.allclose(e1, pred.detach())
+    finally:
+        bnn.set_matmul_precision("fp32")
+
+
 @pytest.mark.parametrize("tiled", [True, False])
 def test_din_golden(tiled):
     import torch.nn.functional as F

@@ -6,7 +6,7 @@ import pytest
 from tests.util import load_golden, oracle_run
 
 CASES = [("deepfm", "deepfm_d9"), ("deepfm", "deepfm_d16"), ("dcn_v2", "dcn_v2_v2_stacked"),
-         ("dcn_v2", "dcn_v2_mix_parallel"), ("din", "din"), ("wide_deep", "wide_deep")]
+         ("dcn_v2", "dcn_v2_mix_parallel"), ("din", "din"), ("wide_deep", "wide_deep"), ("dlrm", "dlrm_pairs"), ("dlrm", "dlrm_self")]
 
 
 @pytest.mark.parametrize("model,name", CASES)
@@ -37,3 +37,23 @@ def test_din_attention_grads_present():
     receive gradients; the golden file carries them under att.*"""
     g = load_golden("din")
     assert "att.linear_0.weight" in g["grad"] and np.abs(g["grad"]["att.linear_0.weight"]).max() > 0
+
+
+def test_dlrm_self_interaction_diagonal_is_zero_not_the_self_dot():
+    """dlrm/net.py:106-111: triu(Z,1) zeroes the diagonal BEFORE the MIN_FLOAT mask is added, so with
+    self_interaction=True the N extra positions are selected but hold 0 — the golden (minted from the
+    reference's code) pins that; a "correct" <T_i,T_i> would change the prediction."""
+    import torch
+
+    from oracle import nets
+
+    T = torch.randn(3, 5, 4, dtype=torch.float64)
+    R = nets.dot_interact(T, True)
+    assert R.shape == (3, 4 + 15)
+    iu = torch.triu_indices(5, 5, 0)
+    diag = (iu[0] == iu[1])
+    assert (R[:, 4:][:, diag] == 0).all() and (R[:, 4:][:, ~diag] != 0).all()
+    assert torch.equal(R[:, :4], T[:, 4])
+    g = load_golden("dlrm_self")
+    stats = [k for k in g["param"] if k.endswith("._variance")]
+    assert stats and all((g["param"][k] != 1).any() for k in stats)   # running stats moved

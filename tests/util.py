@@ -58,6 +58,18 @@ def oracle_run(model, g, dtype=torch.float64):
         dense = torch.tensor(i["dense"], dtype=dtype)
         pred = nets.wide_deep_forward(p, slots(i["ids"]), dense, n_fc(p, "") - 1)
         loss = nets.log_loss(pred, torch.tensor(i["label"], dtype=dtype)).mean()
+    elif model == "dlrm":
+        dense = torch.tensor(i["dense"], dtype=dtype)
+        n_bot = len([k for k in p if k.startswith("bot_mlp.dense_") and k.endswith(".weight")])
+        n_top = len([k for k in p if k.startswith("top_mlp.dense_") and k.endswith(".weight")])
+        N = i["ids"].shape[1] + 1
+        d = p["embedding.weight"].shape[1]
+        self_int = p["top_mlp.dense_0.weight"].shape[0] == d + N * (N + 1) // 2
+        # the golden's `_mean` / `_variance` are the running statistics AFTER the step: not inputs
+        stats = {k: p.pop(k) for k in list(p) if k.endswith("._mean") or k.endswith("._variance")}
+        pred = nets.dlrm_forward(p, slots(i["ids"]), dense, n_bot=n_bot, n_top=n_top,
+                                 self_interaction=self_int)
+        loss = nets.softmax_cross_entropy(pred, torch.tensor(i["label"]))
     else:
         raise ValueError(model)
     gs = torch.autograd.grad(loss, list(p.values()), allow_unused=True)
