@@ -21,7 +21,7 @@
 
 namespace b200rec {
 
-constexpr int kDotWarps = 4;  // samples in flight per CTA
+constexpr int kDotWarps = 4;  // samples in flight per CTA (fewer when N*N floats would not fit)
 
 struct DotShape {
   int N, d, self, P, pitch;
@@ -53,7 +53,8 @@ dot_interact_fwd_kernel(const float* __restrict__ T, float* __restrict__ R, int6
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* tile = smem + (size_t)warp * s.smem_floats_fwd();
   const int out_w = s.d + s.P;
-  for (int64_t b = (int64_t)blockIdx.x * kDotWarps + warp; b < B; b += (int64_t)gridDim.x * kDotWarps) {
+  const int warps = blockDim.x >> 5;
+  for (int64_t b = (int64_t)blockIdx.x * warps + warp; b < B; b += (int64_t)gridDim.x * warps) {
     dot_stage_rows(T + b * s.N * s.d, tile, s, lane);
     __syncwarp();
     float* out = R + b * out_w;
@@ -85,7 +86,8 @@ dot_interact_bwd_kernel(const float* __restrict__ T, const float* __restrict__ d
   float* tile = smem + (size_t)warp * s.smem_floats_bwd();
   float* dzf = tile + (size_t)s.N * s.pitch;  // dZ mirrored into a full N x N matrix, zero diagonal
   const int out_w = s.d + s.P;
-  for (int64_t b = (int64_t)blockIdx.x * kDotWarps + warp; b < B; b += (int64_t)gridDim.x * kDotWarps) {
+  const int warps = blockDim.x >> 5;
+  for (int64_t b = (int64_t)blockIdx.x * warps + warp; b < B; b += (int64_t)gridDim.x * warps) {
     dot_stage_rows(T + b * s.N * s.d, tile, s, lane);
     const float* g = dR + b * out_w;
     for (int i = lane; i < s.N; i += 32) dzf[i * s.N + i] = 0.f;
