@@ -138,7 +138,12 @@ def test_wide_deep_golden(precision):
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_dlrm_golden(name, self_interaction, precision):
     """Train-mode forward (BatchNorm on batch statistics), softmax cross-entropy, every gradient and
-    the running statistics after the step, against the reference's own dlrm/net.py (golden)."""
+    the running statistics after the step, against the reference's own dlrm/net.py (golden).
+
+    Tolerance: 1e-4 in fp32 (the package default).  In the opt-in 'bf16x3' GEMM mode the six
+    BatchNorm layers divide by a standard deviation estimated from this golden's 11 samples, which
+    amplifies the ~2^-16 relative error of the dropped lo*lo products: a CPU emulation of the split
+    GEMMs gives 5e-5 on the scores and up to 4e-4 on the gradients, so that mode is held to 2e-3."""
     from paddlerec_b200 import functional as BF
     from paddlerec_b200 import nn as bnn
     from paddlerec_b200.rank.dlrm import net
@@ -158,10 +163,11 @@ def test_dlrm_golden(name, self_interaction, precision):
         assert pred.shape == (ids.shape[0], 2)
         loss = BF.softmax_cross_entropy(pred, label.to(torch.int64)).mean()
         loss.backward()
-        check(g2, pred, loss, grads_of(layer))
+        tol = TOL if precision == "fp32" else 2e-3
+        check(g2, pred, loss, grads_of(layer), tol=tol)
         sd = layer.state_dict()
         for k, v in stats.items():          # Paddle's rule: biased batch variance, momentum 0.9
-            assert rel_err(sd[k], v) < TOL, k
+            assert rel_err(sd[k], v) < tol, k
         assert np.abs(grads_of(layer)["embedding.weight"][0]).max() > 0   # id 0 is a real row
         # eval mode runs on the running statistics and is deterministic
         layer.eval()

@@ -103,7 +103,9 @@ def test_packed_reader_trains_identically_to_the_dataloader(tmp_path):
         losses, metric_values, _ = runner.train(cfg, max_steps=5, save=False)
         runs.append((losses, metric_values["auc"]))
     assert len(runs[0][0]) == 5
-    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1]
+    # same batches in the same order => the same trajectory (different batches differ at 1e-1)
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5, atol=0)
+    assert abs(runs[0][1] - runs[1][1]) < 1e-6
 
 
 def test_dlrm_model_dir_trains(tmp_path):
