@@ -9,6 +9,7 @@ rank-model surface (models/rank/*/net.py, DygraphModel).  See DESIGN.md.
   sharded.py       row-cyclic table sharding over NCCL all-to-all
   rank/<model>/    net.py + dygraph_model.py mirrors of the reference's plugin directories
   dataio.py        native text parsers (include/b200rec_io.h) + PackedBatchReader
+  checkpoint.py    rec.pdparams in paddle.save's pickle layout, rec.pdopt for resume
   runner.py        tools/trainer.py-shaped loop and yaml loader
 """
 __version__ = "0.1.0"

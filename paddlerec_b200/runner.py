@@ -18,6 +18,8 @@ import numpy as np
 import torch
 import yaml
 
+from . import checkpoint
+
 logging.basicConfig(format="%(asctime)s - %(levelname)s - %(message)s", level=logging.INFO)
 logger = logging.getLogger("paddlerec_b200")
 
@@ -123,15 +125,23 @@ def create_data_loader(config, mode="train", rank=0, world_size=1):
 
 # ---- checkpoint (save_load.py:25-46) ------------------------------------------------------------
 def save_model(net, optimizer, model_path, epoch_id, prefix="rec"):
+    """<model_path>/<epoch>/rec.pdparams (+ rec.pdopt) — the layout of save_load.py:25-31, the
+    .pdparams in paddle.save's state_dict pickle format (checkpoint.py)."""
     path = os.path.join(model_path, str(epoch_id))
     os.makedirs(path, exist_ok=True)
-    torch.save(net.state_dict(), os.path.join(path, prefix + ".pdparams"))
+    checkpoint.save_pdparams(net.state_dict(), os.path.join(path, prefix + ".pdparams"))
+    if optimizer is not None:
+        checkpoint.save_pdopt(optimizer, net, os.path.join(path, prefix + ".pdopt"))
     logger.info("Already save model in %s", path)
 
 
-def load_model(model_path, net, prefix="rec"):
-    state = torch.load(os.path.join(model_path, prefix + ".pdparams"), map_location="cuda")
-    net.load_state_dict(state)
+def load_model(model_path, net, prefix="rec", optimizer=None):
+    """save_load.py:41-46; with `optimizer`, also restores rec.pdopt when it is there (resume)."""
+    logger.info("start load model from %s", model_path)
+    checkpoint.set_state_dict(net, checkpoint.load_pdparams(os.path.join(model_path, prefix + ".pdparams")))
+    opt_path = os.path.join(model_path, prefix + ".pdopt")
+    if optimizer is not None and os.path.exists(opt_path):
+        checkpoint.load_pdopt(optimizer, net, opt_path)
 
 
 # ---- the loop (trainer.py:49-223) ---------------------------------------------------------------
@@ -158,9 +168,9 @@ def train(config: dict, max_steps=None, save=True):
     model_init_path = config.get("runner.model_init_path", None)
 
     dy_model = dy_model_class.create_model(config)
-    if model_init_path is not None:
-        load_model(model_init_path, dy_model)
     optimizer = dy_model_class.create_optimizer(dy_model, config)
+    if model_init_path is not None:     # warm start (trainer.py:106-107); also resumes rec.pdopt
+        load_model(model_init_path, dy_model, optimizer=optimizer)
     train_dataloader = create_data_loader(config, "train")
 
     losses = []
