@@ -110,3 +110,16 @@ def raw_embed_fm_bwd(feat, S, dfeat_dnn, gy1, gy2, dense, seg, pos, num, F, fuse
         fusedW[:, D] = dW1
         return fusedW, None, ddense_w, ddense_w1
     return dW, dW1, ddense_w, ddense_w1
+
+
+def raw_dot_interact_fwd(T, self_interaction=False):
+    from oracle import nets
+    return nets.dot_interact(T, self_interaction)
+
+
+def raw_dot_interact_bwd(T, dR, self_interaction=False):
+    from oracle import nets
+    with torch.enable_grad():
+        Tq = T.detach().clone().requires_grad_(True)
+        nets.dot_interact(Tq, self_interaction).backward(dR)
+    return Tq.grad

@@ -178,3 +178,69 @@ def test_shard_embeddings_generic_lookup(tmp_path):
                                    rtol=2e-5, atol=1e-6)
         np.testing.assert_allclose(r["dW"], p["embedding.weight"].grad.numpy()[rank::world],
                                    rtol=2e-4, atol=1e-7)
+
+
+def _dlrm_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import ops, sharded
+        from paddlerec_b200.rank.dlrm import net
+        from tests.util import load_golden
+        # K6 is CUDA-only: the stand-in takes its place for this choreography test
+        ops.raw_dot_interact_fwd = cpu_kernels.raw_dot_interact_fwd
+        ops.raw_dot_interact_bwd = cpu_kernels.raw_dot_interact_bwd
+        g = load_golden("dlrm_pairs")
+        Vg, Dg = g["param"]["embedding.weight"].shape
+        model = net.DLRMLayer(13, [32, 16, 8], Vg, Dg, [32, 16, 2], 26, device="cpu")
+        sd = model.state_dict()
+        with torch.no_grad():
+            for k, v in g["param"].items():
+                if not (k.endswith("._mean") or k.endswith("._variance")):
+                    sd[k].copy_(torch.tensor(v, dtype=torch.float32))
+        sharded.shard_embeddings(model, rank, world, kernels=cpu_kernels)
+        model.train()
+        ids = torch.tensor(g["in"]["ids"])
+        dense = torch.tensor(g["in"]["dense"], dtype=torch.float32)
+        label = torch.tensor(g["in"]["label"])
+        Bg = ids.shape[0] // world * world
+        per = Bg // world
+        sl = slice(rank * per, (rank + 1) * per)
+        pred = model(ids[sl], dense[sl])
+        loss = BF.softmax_cross_entropy(pred, label[sl]).sum() / Bg
+        loss.backward()
+        np.savez(os.path.join(out_dir, "dlrm%d.npz" % rank), pred=pred.detach().numpy(),
+                 dW=model.embedding.grad_rows.to_dense().numpy(),
+                 dtop=model.top_mlp.dense_0.weight.grad.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_dlrm_matches_per_rank_oracle(tmp_path):
+    """DLRM on a row-sharded table (generic exchange + K6 stand-in).  BatchNorm normalises with each
+    rank's LOCAL batch statistics — as the reference's collective mode does — so the oracle is run on
+    each rank's slice; the table gradient of an owner is the sum of both ranks' contributions."""
+    from tests.util import load_golden, to_params, slots
+    world = 2
+    mp.spawn(_dlrm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = load_golden("dlrm_pairs")
+    ids = torch.tensor(g["in"]["ids"])
+    Bg = ids.shape[0] // world * world
+    per = Bg // world
+    dW = 0
+    for rank in range(world):
+        p = to_params({k: v for k, v in g["param"].items()
+                       if not (k.endswith("._mean") or k.endswith("._variance"))})
+        sl = slice(rank * per, (rank + 1) * per)
+        pred = nets.dlrm_forward(p, slots(ids[sl]), torch.tensor(g["in"]["dense"])[sl], n_bot=3, n_top=3)
+        lse = torch.logsumexp(pred, 1) - pred.gather(1, torch.tensor(g["in"]["label"])[sl]).squeeze(1)
+        (lse.sum() / Bg).backward()
+        r = np.load(os.path.join(str(tmp_path), "dlrm%d.npz" % rank))
+        np.testing.assert_allclose(r["pred"], pred.detach().numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(r["dtop"], p["top_mlp.dense_0.weight"].grad.numpy(), rtol=2e-3, atol=1e-6)
+        dW = dW + p["embedding.weight"].grad.numpy()
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "dlrm%d.npz" % rank))
+        np.testing.assert_allclose(r["dW"], dW[rank::world], rtol=2e-3, atol=1e-6)
