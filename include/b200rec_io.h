@@ -59,6 +59,19 @@ int b200rec_io_parse_slot_text(const char* text, size_t len, const char* label_s
                                int64_t* ids, float* dense, int64_t cap, int64_t* n_out,
                                int n_threads);
 
+/* Same, with the two per-model variations of the reference's readers selected by `flags`:
+ *   B200REC_IO_DENSE_LOG1P        dense value = log(v + 1), evaluated in double before narrowing to
+ *                                 float32 (models/rank/dcn_v2/reader.py:60-61)
+ *   B200REC_IO_SKIP_EMPTY_SPARSE  a sparse token with an empty value (`7:`) is ignored instead of
+ *                                 being an error (dcn_v2/reader.py:53-55) */
+#define B200REC_IO_DENSE_LOG1P 1
+#define B200REC_IO_SKIP_EMPTY_SPARSE 2
+int b200rec_io_parse_slot_text_ex(const char* text, size_t len, const char* label_slot,
+                                  const char* const* sparse_slots, int n_sparse,
+                                  const char* dense_slot, int dense_dim, int flags, int64_t* label,
+                                  int64_t* ids, float* dense, int64_t cap, int64_t* n_out,
+                                  int n_threads);
+
 /* ---- slot text, variable length (doc/custom_reader.md:15-24) -------------------------------------
  * Same tokens; every (sample, sparse slot) pair is a bag of >= 1 keys: bag b = n*n_sparse + f holds
  * keys[offsets[b] .. offsets[b+1]); a missing slot is the bag {0} like the padded reader.

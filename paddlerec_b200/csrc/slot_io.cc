@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <charconv>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -368,7 +369,20 @@ int b200rec_io_parse_slot_text(const char* text, size_t len, const char* label_s
                                const char* dense_slot, int dense_dim, int64_t* label,
                                int64_t* ids, float* dense, int64_t cap, int64_t* n_out,
                                int n_threads) {
+  return b200rec_io_parse_slot_text_ex(text, len, label_slot, sparse_slots, n_sparse, dense_slot,
+                                       dense_dim, 0, label, ids, dense, cap, n_out, n_threads);
+}
+
+int b200rec_io_parse_slot_text_ex(const char* text, size_t len, const char* label_slot,
+                                  const char* const* sparse_slots, int n_sparse,
+                                  const char* dense_slot, int dense_dim, int flags, int64_t* label,
+                                  int64_t* ids, float* dense, int64_t cap, int64_t* n_out,
+                                  int n_threads) {
   if ((!text && len) || !n_out) return fail(B200REC_IO_ERR_ARG, "null argument");
+  if (flags & ~(B200REC_IO_DENSE_LOG1P | B200REC_IO_SKIP_EMPTY_SPARSE))
+    return fail(B200REC_IO_ERR_ARG, "unknown flags 0x%x", flags);
+  const bool log1p_dense = (flags & B200REC_IO_DENSE_LOG1P) != 0;
+  const bool skip_empty = (flags & B200REC_IO_SKIP_EMPTY_SPARSE) != 0;
   SlotSchema sc;
   if (int rc = make_schema(sc, label_slot, sparse_slots, n_sparse, dense_slot, dense_dim)) return rc;
   if ((sc.has_label && !label) || (n_sparse > 0 && !ids) || (sc.has_dense && !dense))
@@ -394,9 +408,10 @@ int b200rec_io_parse_slot_text(const char* text, size_t len, const char* label_s
           double v;
           if (!parse_f64(val, &v)) { st.set(B200REC_IO_ERR_PARSE, n, "bad float in", tok); return false; }
           if (n_dense >= Dn) { st.set(B200REC_IO_ERR_RAGGED, n, "too many dense values at", tok); return false; }
-          drow[n_dense++] = float(v);
+          drow[n_dense++] = float(log1p_dense ? std::log(v + 1.0) : v);
           return true;
         }
+        if (skip_empty && val.empty()) return true;
         int64_t v;
         if (!parse_i64(val, &v)) { st.set(B200REC_IO_ERR_PARSE, n, "bad integer in", tok); return false; }
         uint8_t& s = seen[kind == -2 ? size_t(F) : size_t(kind)];

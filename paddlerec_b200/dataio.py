@@ -48,6 +48,9 @@ _SIG = {
     "b200rec_io_count_lines": (c_int, [_P, c_size_t, POINTER(c_int64)]),
     "b200rec_io_parse_slot_text": (c_int, [_P, c_size_t, c_char_p, POINTER(c_char_p), c_int, c_char_p,
                                            c_int, _P, _P, _P, c_int64, POINTER(c_int64), c_int]),
+    "b200rec_io_parse_slot_text_ex": (c_int, [_P, c_size_t, c_char_p, POINTER(c_char_p), c_int, c_char_p,
+                                              c_int, c_int, _P, _P, _P, c_int64, POINTER(c_int64),
+                                              c_int]),
     "b200rec_io_parse_slot_text_lod": (c_int, [_P, c_size_t, c_char_p, POINTER(c_char_p), c_int,
                                                c_char_p, c_int, _P, _P, _P, _P, c_int64, c_int64,
                                                POINTER(c_int64), POINTER(c_int64), c_int]),
@@ -148,6 +151,12 @@ class SlotSchema:
     label_slot: Optional[str] = "click"
     dense_slot: Optional[str] = "dense_feature"
     dense_dim: int = 13
+    dense_log1p: bool = False          # dense = log(v + 1)   (models/rank/dcn_v2/reader.py:60-61)
+    skip_empty_sparse: bool = False    # ignore `slot:` with no value (dcn_v2/reader.py:53-55)
+
+    @property
+    def flags(self) -> int:
+        return (1 if self.dense_log1p else 0) | (2 if self.skip_empty_sparse else 0)
 
     @property
     def n_sparse(self) -> int:
@@ -155,6 +164,7 @@ class SlotSchema:
 
 
 CRITEO = SlotSchema()
+CRITEO_DCN_V2 = SlotSchema(dense_log1p=True, skip_empty_sparse=True)
 
 
 def _line_bound(data) -> int:
@@ -191,10 +201,10 @@ def parse_slot_text(data, schema: SlotSchema = CRITEO, out=None, threads: int = 
     cap = out[1].shape[0] if out is not None else _line_bound(data)
     label, ids, dense = _alloc(cap, schema, out)
     n = c_int64(0)
-    _check(load().b200rec_io_parse_slot_text(
+    _check(load().b200rec_io_parse_slot_text_ex(
         p, nbytes, schema.label_slot.encode() if schema.label_slot else None,
         _names(schema.sparse_slots), schema.n_sparse,
-        schema.dense_slot.encode() if schema.dense_slot else None, schema.dense_dim,
+        schema.dense_slot.encode() if schema.dense_slot else None, schema.dense_dim, schema.flags,
         _np_ptr(label), _np_ptr(ids), _np_ptr(dense), cap, ctypes.byref(n), threads))
     k = n.value
     return (label[:k] if label is not None else None, ids[:k], dense[:k] if dense is not None else None)

@@ -109,8 +109,12 @@ def create_data_loader(config, mode="train", rank=0, world_size=1):
         from . import dataio
 
         fmt = config.get("runner.packed_format", "slot_text")
+        schemas = {"criteo": dataio.CRITEO, "criteo_dcn_v2": dataio.CRITEO_DCN_V2}
+        schema_name = config.get("runner.packed_schema", "criteo")
+        if schema_name not in schemas:
+            raise ValueError("runner.packed_schema %r is not one of %s" % (schema_name, sorted(schemas)))
         return dataio.PackedBatchReader(
-            file_list, batch_size=batch_size, fmt=fmt, drop_last=True,
+            file_list, batch_size=batch_size, fmt=fmt, schema=schemas[schema_name], drop_last=True,
             threads=int(config.get("runner.reader_threads", 0)),
             pin_memory=torch.cuda.is_available(), rank=rank, world_size=world_size,
             shard_files=bool(config.get("runner.use_fleet", False)))
@@ -155,10 +159,14 @@ def parse_args(argv=None):
     return args
 
 
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("paddlerec_b200 runs on a CUDA device only (no CPU fallback)")
+
+
 def train(config: dict, max_steps=None, save=True):
     """Returns a list of per-step python floats (loss) and the final metric values."""
-    if not torch.cuda.is_available():
-        raise RuntimeError("paddlerec_b200 trains on a CUDA device only (no CPU fallback)")
+    _require_cuda()
     dy_model_class = load_dy_model_class(config["config_abs_dir"])
     seed = int(config.get("runner.seed", 12345))
     torch.manual_seed(seed)
@@ -196,7 +204,7 @@ def train(config: dict, max_steps=None, save=True):
                 # the only host sync of the loop
                 metric_str = "".join("%s:%.6f, " % (n, m.accumulate())
                                      for n, m in zip(metric_list_name, metric_list))
-                tensor_str = "".join("%s:%s," % (k, str(float(v))) for k, v in
+                tensor_str = "".join("%s:%s," % (k, str(float(v.detach() if hasattr(v, "detach") else v))) for k, v in
                                      (tensor_print_dict or {}).items())
                 train_run_cost += time.time() - train_start
                 logger.info(
@@ -226,7 +234,61 @@ def train(config: dict, max_steps=None, save=True):
     return [float(l) for l in losses], metric_values, dy_model
 
 
-def main(argv=None):
+def infer(config: dict, max_steps=None):
+    """tools/infer.py:48-197: for every saved epoch in [infer_start_epoch, infer_end_epoch) load
+    <infer_load_path>/<epoch>/rec.pdparams, run infer_forward over the test data in eval mode and
+    report the metrics; the metric objects are created once and reset after every epoch only when
+    `runner.use_auc` is set (infer.py:180-181).  Returns {epoch: {metric: value}}."""
+    _require_cuda()
+    dy_model_class = load_dy_model_class(config["config_abs_dir"])
+    torch.manual_seed(12345)
+    print_interval = int(config.get("runner.print_interval", 10))
+    load_path = config.get("runner.infer_load_path", "model_output")
+    if not os.path.isabs(load_path):
+        load_path = os.path.join(config["config_abs_dir"], load_path)
+    start_epoch = int(config.get("runner.infer_start_epoch", 0))
+    end_epoch = int(config.get("runner.infer_end_epoch", 10))
+    dy_model = dy_model_class.create_model(config)
+    test_dataloader = create_data_loader(config, "test")
+    metric_list, metric_list_name = dy_model_class.create_metrics()
+    results, step_num = {}, 0
+    for epoch_id in range(start_epoch, end_epoch):
+        logger.info("load model epoch %d", epoch_id)
+        load_model(os.path.join(load_path, str(epoch_id)), dy_model)
+        dy_model.eval()
+        seen = 0
+        interval_begin = time.time()
+        for batch_id, batch in enumerate(test_dataloader):
+            batch_size = len(batch[0])
+            metric_list, tensor_print_dict = dy_model_class.infer_forward(dy_model, metric_list, batch,
+                                                                          config)
+            seen += batch_size
+            if batch_id % print_interval == 0:
+                metric_str = "".join("%s: %.6f," % (n, m.accumulate())
+                                     for n, m in zip(metric_list_name, metric_list))
+                tensor_str = "".join("%s:%s," % (k, str(float(v.detach() if hasattr(v, "detach") else v))) for k, v in
+                                     (tensor_print_dict or {}).items())
+                logger.info("epoch: %d, batch_id: %d, %s%s ips: %.2f ins/s", epoch_id, batch_id,
+                            metric_str, tensor_str,
+                            print_interval * batch_size / (time.time() + 0.0001 - interval_begin))
+                interval_begin = time.time()
+            step_num += 1
+            if max_steps is not None and step_num >= max_steps:
+                break
+        if seen == 0:
+            raise RuntimeError("test_dataloader is null, please ensure batch size < dataset size!")
+        results[epoch_id] = {n: m.accumulate() for n, m in zip(metric_list_name, metric_list)}
+        logger.info("epoch: %d done, %s", epoch_id,
+                    ", ".join("%s: %.6f" % kv for kv in results[epoch_id].items()))
+        if config.get("runner.use_auc", False):
+            for m in metric_list:
+                m.reset()
+        if max_steps is not None and step_num >= max_steps:
+            break
+    return results
+
+
+def main(argv=None, mode="train"):
     args = parse_args(argv)
     config = load_yaml(args.config_yaml)
     config["yaml_path"] = args.config_yaml
@@ -235,7 +297,7 @@ def main(argv=None):
     logger.info("**************common.configs**********")
     for k in ("runner.use_gpu", "runner.train_batch_size", "runner.epochs", "runner.print_interval"):
         logger.info("%s: %s", k, config.get(k))
-    train(config)
+    return train(config) if mode == "train" else infer(config)
 
 
 if __name__ == "__main__":

@@ -123,3 +123,56 @@ def raw_dot_interact_bwd(T, dR, self_interaction=False):
         Tq = T.detach().clone().requires_grad_(True)
         nets.dot_interact(Tq, self_interaction).backward(dR)
     return Tq.grad
+
+
+# ---- row-wise optimizers / densify (stand-ins for b200rec_sparse_* and b200rec_rows_to_dense) -------
+def _valid(sr):
+    U = int(sr.num[0])
+    return sr.rows[:U], sr.value[:U, :sr.cols]
+
+
+def raw_rows_to_dense(sr, dW):
+    rows, g = _valid(sr)
+    dW[rows, :g.shape[1]] += g
+
+
+def raw_sparse_sgd(W, sr, lr):
+    rows, g = _valid(sr)
+    W[rows, :g.shape[1]] -= lr * g
+
+
+def raw_sparse_adam(W, m, v, sr, lr, beta1, beta2, eps, beta1_pow, beta2_pow):
+    """Paddle's adam op on the touched rows: lr_t = lr*sqrt(1-b2^t)/(1-b1^t),
+    w -= lr_t * m / (sqrt(v) + eps*sqrt(1-b2^t))."""
+    rows, g = _valid(sr)
+    C = g.shape[1]
+    m[rows, :C] = beta1 * m[rows, :C] + (1 - beta1) * g
+    v[rows, :C] = beta2 * v[rows, :C] + (1 - beta2) * g * g
+    c2 = (1 - beta2_pow) ** 0.5
+    W[rows, :C] -= lr * c2 / (1 - beta1_pow) * m[rows, :C] / (v[rows, :C].sqrt() + eps * c2)
+
+
+KERNEL_NAMES = ("raw_gather", "raw_embed_fm_fwd", "raw_embed_fm_bwd", "raw_segment_reduce",
+                "raw_rows_to_dense", "raw_sparse_sgd", "raw_sparse_adam", "raw_dot_interact_fwd",
+                "raw_dot_interact_bwd")
+
+
+def install(monkeypatch, ops):
+    """Patch the stand-ins over paddlerec_b200.ops for a CPU test of HOST logic (trainer / infer
+    loops, checkpoints, readers).  Never used by the product or by the GPU parity tests."""
+    import sys
+
+    me = sys.modules[__name__]
+    for name in KERNEL_NAMES:
+        fn = getattr(me, name)
+        if name == "raw_segment_reduce":
+            monkeypatch.setattr(ops, name, lambda dOut, seg, pos, num, n, row_of_pos=None:
+                                raw_segment_reduce(dOut, seg, pos, num, n))
+        else:
+            monkeypatch.setattr(ops, name, fn)
+
+    def group(ids, V, pad):
+        g = raw_group_ids(ids, V, pad)
+        return ops.IdGroups(g.unique_ids, g.seg_offsets, g.sorted_pos, g.num, g.n, V)
+
+    monkeypatch.setattr(ops, "raw_group_ids", group)

@@ -29,7 +29,7 @@ def _read(name, mode="rb"):
 def test_library_exports_every_declared_symbol():
     lib = dataio.load()
     declared = dataio.declared_symbols()
-    assert len(declared) == 9 and set(declared) == set(dataio._SIG)
+    assert len(declared) == 10 and set(declared) == set(dataio._SIG)
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.b200rec_io_abi_version() == dataio.IO_ABI_VERSION

@@ -145,3 +145,53 @@ def test_l2_decay_regularizer_is_added_after_clipping():
 
     dnn = dcn_net.DNNLayer(4, 13, 26, [8, 8])
     assert [getattr(p, "l2_decay", 0.0) for n, p in dnn.named_parameters() if n.endswith("weight")] == [1e-7, 1e-7]
+
+
+@pytest.mark.parametrize("model", ["deepfm", "dcn_v2", "wide_deep", "dlrm", "din"])
+def test_every_model_directory_is_a_complete_plugin(model):
+    """doc/model_develop.md:3-45: a model directory holds net.py, dygraph_model.py (class
+    DygraphModel with the seven methods), a reader and a yaml whose data paths resolve."""
+    d = os.path.join(PKG, "rank", model)
+    cfg = runner.load_yaml(os.path.join(d, "config.yaml"))
+    cfg["config_abs_dir"] = d
+    dm = runner.load_dy_model_class(d)
+    for meth in ("create_model", "create_feeds", "create_loss", "create_optimizer", "create_metrics",
+                 "train_forward", "infer_forward"):
+        assert callable(getattr(dm, meth)), meth
+    for mode in ("train", "test"):
+        batch = next(iter(runner.create_data_loader(cfg, mode)))
+        bs = cfg["runner.train_batch_size" if mode == "train" else "runner.infer_batch_size"]
+        assert len(batch[0]) == bs
+    if model == "din":
+        assert len(batch) == 8 and batch[5].dtype == torch.int64 and batch[5].shape[2] == 1
+        assert batch[0].shape == batch[6].shape                    # target ids tiled to [B, L]
+    else:
+        assert len(batch) == 28 and batch[27].shape == (bs, 13)
+
+
+def test_dcn_v2_reader_log_transform_and_native_schema():
+    """dcn_v2/reader.py:53-61: dense = log(v+1), `slot:` with an empty value is skipped — the Python
+    mirror and the native parser (dataio.CRITEO_DCN_V2) agree bit for bit."""
+    from paddlerec_b200 import dataio
+    from paddlerec_b200.rank.dcn_v2 import reader
+
+    lines = ["click:1 dense_feature:0.5 dense_feature:0 " + " ".join("dense_feature:%r" % (i * 0.37) for i in range(11))
+             + " 1:7 2: 3:9", "click:0 4:5 26:11"]
+    ds = reader.RecDataset([], config={})
+    rows = [ds.parse_line(l) for l in lines]
+    assert rows[0][2][0] == 0 and rows[0][3][0] == 9                  # `2:` skipped -> padding id
+    assert rows[0][27][0] == np.float32(np.log(1.5)) and rows[0][27][1] == 0
+    assert rows[1][27].tolist() == [0.0] * 13
+    label, ids, dense = dataio.parse_slot_text("\n".join(lines), dataio.CRITEO_DCN_V2)
+    assert np.array_equal(ids, np.stack([np.concatenate(r[1:27]) for r in rows]))
+    assert np.array_equal(dense, np.stack([r[27] for r in rows]))
+    assert label[:, 0].tolist() == [1, 0]
+    with pytest.raises(dataio.B200RecIOError, match="bad integer"):
+        dataio.parse_slot_text(lines[0], dataio.CRITEO)               # plain schema: `2:` is an error
+    cfg = {"runner.train_data_dir": "../deepfm/data/sample_data/train", "runner.train_batch_size": 16,
+           "runner.train_reader_path": "reader", "config_abs_dir": os.path.join(PKG, "rank", "dcn_v2")}
+    plain = list(runner.create_data_loader(cfg))
+    packed = list(runner.create_data_loader({**cfg, "runner.reader_type": "PackedReader",
+                                             "runner.packed_schema": "criteo_dcn_v2"}))
+    for a, b in zip(plain, packed):
+        assert torch.equal(b[1], torch.cat(a[1:27], 1)) and torch.equal(b[2], a[27])
