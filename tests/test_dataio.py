@@ -35,6 +35,36 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200rec_io_abi_version() == dataio.IO_ABI_VERSION
 
 
+def test_plain_and_ex_entry_points_agree_through_raw_ctypes():
+    """The Python binding always calls the _ex entry point; the plain one must stay equivalent
+    (flags = 0) for C callers that bind the shorter signature."""
+    import ctypes
+    lib = dataio.load()
+    text = _read("slot_text_sample.txt")
+    n_lines = dataio.count_lines(text)
+    names = (ctypes.c_char_p * 26)(*[str(i).encode() for i in range(1, 27)])
+    outs = []
+    for ex in (False, True):
+        label = np.empty((n_lines, 1), np.int64)
+        ids = np.empty((n_lines, 26), np.int64)
+        dense = np.empty((n_lines, 13), np.float32)
+        n = ctypes.c_int64()
+        args = [text, len(text), b"click", names, 26, b"dense_feature", 13]
+        if ex:
+            args.append(0)
+        args += [label.ctypes.data, ids.ctypes.data, dense.ctypes.data, n_lines, ctypes.byref(n), 2]
+        fn = lib.b200rec_io_parse_slot_text_ex if ex else lib.b200rec_io_parse_slot_text
+        assert fn(*args) == 0, lib.b200rec_io_last_error()
+        outs.append((n.value, label.copy(), ids.copy(), dense.copy()))
+    assert outs[0][0] == outs[1][0] == 48
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][1:], outs[1][1:]))
+    bad = ctypes.c_int64()
+    assert lib.b200rec_io_parse_slot_text_ex(text, len(text), b"click", names, 26, b"dense_feature", 13,
+                                             64, None, outs[0][2].ctypes.data, None, 48,
+                                             ctypes.byref(bad), 1) == -1          # unknown flag
+    assert b"unknown flags" in lib.b200rec_io_last_error()
+
+
 # ---- hashes ---------------------------------------------------------------------------------------
 def test_xxh32_published_vectors():
     # test vectors of the xxHash specification / reference implementation (seed 0 and a prime seed)
