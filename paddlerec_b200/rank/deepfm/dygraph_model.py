@@ -27,6 +27,8 @@ class DygraphModel:
     device = "cuda"
 
     def create_model(self, config):
+        """The yaml's hyper_parameters -> DeepFMLayer on `self.device` (reference :25-38).  The label
+        occupies one of `sparse_inputs_slots`, hence the -1."""
         sparse_feature_number = config.get("hyper_parameters.sparse_feature_number")
         sparse_feature_dim = config.get("hyper_parameters.sparse_feature_dim")
         fc_sizes = config.get("hyper_parameters.fc_sizes")
@@ -53,17 +55,24 @@ class DygraphModel:
         return label, ids, dense
 
     def create_loss(self, pred, label):
+        """Mean log-loss with Paddle's epsilon 1e-4 on the sigmoid output (reference :53-58)."""
         cost = BF.log_loss(pred, label.to(torch.float32))
         return cost.mean()
 
     def create_optimizer(self, dy_model, config):
+        """Adam over every parameter; the two tables are updated row-wise from their SelectedRows
+        gradients (lazy_mode — the reference's dygraph Adam :61-65 is non-lazy, its static twin
+        static_model.py:101-103 lazy; a non-lazy pass over V=1e8 rows would move 77 GB per step)."""
         lr = config.get("hyper_parameters.optimizer.learning_rate", 0.001)
         return optim.Adam(learning_rate=lr, parameters=dy_model.parameters(), lazy_mode=True)
 
     def create_metrics(self):
+        """One ROC-AUC metric named "auc" (reference :68-72); its histograms live on the device."""
         return [BF.Auc("ROC")], ["auc"]
 
     def train_forward(self, dy_model, metrics_list, batch_data, config):
+        """-> (loss, metrics_list, print_dict) as doc/model_develop.md:35-39 requires; the metric
+        update reads the detached prediction without leaving the device (reference :75-87)."""
         label, sparse_tensor, dense_tensor = self.create_feeds(batch_data, config)
         pred = dy_model.forward(sparse_tensor, dense_tensor)
         loss = self.create_loss(pred, label)
@@ -72,6 +81,7 @@ class DygraphModel:
         return loss, metrics_list, {"loss": loss}
 
     def infer_forward(self, dy_model, metrics_list, batch_data, config):
+        """-> (metrics_list, None): forward under no_grad + metric update (reference :89-98)."""
         label, sparse_tensor, dense_tensor = self.create_feeds(batch_data, config)
         with torch.no_grad():
             pred = dy_model.forward(sparse_tensor, dense_tensor)
