@@ -110,6 +110,17 @@ int b200rec_io_parse_criteo_tsv(const char* text, size_t len, int hash_kind, int
                                 int64_t* ids, float* dense, int64_t cap, int64_t* n_out,
                                 int64_t* n_skipped_out, int n_threads);
 
+/* ---- DIN behaviour logs (models/rank/din/dinReader.py:61-70) ---------------------------------------
+ * Line: `hist_items;hist_cats;target_item;target_cat;label` — the two histories are blank-separated
+ * id lists of equal length, label is a float.  Lines with fewer than 5 `;` fields are skipped
+ * (dinReader.py:64-65) and counted.  Output is LoD: sample n owns hist_items / hist_cats
+ * [offsets[n], offsets[n+1]).  Grouping by length, padding and the mask (dinReader.py:75-140) are
+ * batch-level and live in the caller (paddlerec_b200/dataio.py: DinBatchReader). */
+int b200rec_io_parse_din(const char* text, size_t len, int64_t* hist_items, int64_t* hist_cats,
+                         int64_t* offsets, int64_t* target_item, int64_t* target_cat, float* label,
+                         int64_t cap, int64_t keys_cap, int64_t* n_out, int64_t* n_keys_out,
+                         int64_t* n_skipped_out, int n_threads);
+
 /* The two string hashes, exposed for tests and for callers that hash elsewhere. */
 uint64_t b200rec_io_hash_std_string(const char* s, size_t len);
 uint32_t b200rec_io_xxh32(const char* s, size_t len, uint32_t seed);

@@ -655,4 +655,94 @@ int b200rec_io_parse_criteo_tsv(const char* text, size_t len, int hash_kind, int
   return B200REC_IO_OK;
 }
 
+int b200rec_io_parse_din(const char* text, size_t len, int64_t* hist_items, int64_t* hist_cats,
+                         int64_t* offsets, int64_t* target_item, int64_t* target_cat, float* label,
+                         int64_t cap, int64_t keys_cap, int64_t* n_out, int64_t* n_keys_out,
+                         int64_t* n_skipped_out, int n_threads) {
+  if ((!text && len) || !n_out || !n_keys_out || !offsets || !target_item || !target_cat || !label ||
+      (keys_cap > 0 && (!hist_items || !hist_cats)))
+    return fail(B200REC_IO_ERR_ARG, "null argument");
+  const Partition pt = partition_lines(text, len, true, n_threads, [](const Line& ln) {
+    int semis = 0;
+    for (const char* q = ln.p; q < ln.e; ++q) semis += (*q == ';');
+    return semis >= 4;
+  });
+  *n_out = *n_keys_out = 0;
+  if (n_skipped_out) *n_skipped_out = pt.total_skipped;
+  if (int64_t(pt.total) > cap)
+    return fail(B200REC_IO_ERR_CAPACITY, "%zu samples but cap = %lld", pt.total, (long long)cap);
+  struct Local { std::vector<int64_t> items, cats; std::vector<int32_t> lens; };
+  std::vector<Local> local((size_t)pt.T);
+  int rc = parallel_lines(pt, [&](int t, const std::vector<Line>& lines, size_t base, Status& st) {
+    Local& L = local[size_t(t)];
+    L.lens.reserve(lines.size());
+    for (size_t i = 0; i < lines.size() && st.code == B200REC_IO_OK; ++i) {
+      const int64_t n = int64_t(base + i);
+      const char* p = lines[i].p;
+      const char* const e = lines[i].e;
+      std::string_view field[5];
+      for (int f = 0; f < 5; ++f) {      // the first five `;`-separated fields; the rest is ignored
+        const char* semi = static_cast<const char*>(memchr(p, ';', size_t(e - p)));
+        const char* fe = (semi && f < 4) ? semi : (semi ? semi : e);
+        field[f] = std::string_view(p, size_t(fe - p));
+        p = semi ? semi + 1 : e;
+      }
+      auto id_list = [&](std::string_view s, std::vector<int64_t>& out) -> int {  // str.split()
+        int cnt = 0;
+        const char* q = s.data();
+        const char* const qe = q + s.size();
+        while (q < qe) {
+          while (q < qe && is_space(*q)) ++q;
+          if (q >= qe) break;
+          const char* a = q;
+          while (q < qe && !is_space(*q)) ++q;
+          int64_t v;
+          if (!parse_i64(std::string_view(a, size_t(q - a)), &v)) {
+            st.set(B200REC_IO_ERR_PARSE, n, "bad id", std::string_view(a, size_t(q - a)));
+            return -1;
+          }
+          out.push_back(v);
+          ++cnt;
+        }
+        return cnt;
+      };
+      const int ni = id_list(field[0], L.items);
+      if (ni < 0) break;
+      const int nc = id_list(field[1], L.cats);
+      if (nc < 0) break;
+      if (ni != nc) { st.set(B200REC_IO_ERR_RAGGED, n, "item and category histories differ in length:", field[1]); break; }
+      auto strip = [](std::string_view s) {
+        while (!s.empty() && is_space(s.front())) s.remove_prefix(1);
+        while (!s.empty() && is_space(s.back())) s.remove_suffix(1);
+        return s;
+      };
+      double lab;
+      if (!parse_i64(strip(field[2]), &target_item[n])) { st.set(B200REC_IO_ERR_PARSE, n, "bad target item", field[2]); break; }
+      if (!parse_i64(strip(field[3]), &target_cat[n])) { st.set(B200REC_IO_ERR_PARSE, n, "bad target category", field[3]); break; }
+      if (!parse_f64(strip(field[4]), &lab)) { st.set(B200REC_IO_ERR_PARSE, n, "bad label", field[4]); break; }
+      label[n] = float(lab);
+      L.lens.push_back(int32_t(ni));
+    }
+  });
+  if (rc) return rc;
+  int64_t total = 0;
+  for (auto& L : local) total += int64_t(L.items.size());
+  if (total > keys_cap)
+    return fail(B200REC_IO_ERR_CAPACITY, "%lld ids but keys_cap = %lld", (long long)total, (long long)keys_cap);
+  int64_t at = 0;
+  for (int t = 0; t < pt.T; ++t) {
+    Local& L = local[size_t(t)];
+    int64_t* off = offsets + int64_t(pt.base[size_t(t)]);
+    for (size_t i = 0; i < L.lens.size(); ++i) { off[i] = at; at += L.lens[i]; }
+    if (!L.items.empty()) {
+      memcpy(hist_items + (at - int64_t(L.items.size())), L.items.data(), L.items.size() * sizeof(int64_t));
+      memcpy(hist_cats + (at - int64_t(L.cats.size())), L.cats.data(), L.cats.size() * sizeof(int64_t));
+    }
+  }
+  offsets[int64_t(pt.total)] = at;
+  *n_out = int64_t(pt.total);
+  *n_keys_out = total;
+  return B200REC_IO_OK;
+}
+
 }  // extern "C"

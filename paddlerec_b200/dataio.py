@@ -60,6 +60,8 @@ _SIG = {
     "b200rec_io_parse_criteo_tsv": (c_int, [_P, c_size_t, c_int, c_int64, POINTER(c_double),
                                             POINTER(c_double), _P, _P, _P, c_int64, POINTER(c_int64),
                                             POINTER(c_int64), c_int]),
+    "b200rec_io_parse_din": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
+                                     POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), c_int]),
     "b200rec_io_hash_std_string": (c_uint64, [c_char_p, c_size_t]),
     "b200rec_io_xxh32": (c_uint32, [c_char_p, c_size_t, c_uint32]),
 }
@@ -266,6 +268,90 @@ def parse_criteo_tsv(data, hash_kind: int = HASH_STD, hash_dim: int = 1000001, c
                                               ctypes.byref(skipped), threads))
     k = n.value
     return label[:k], ids[:k], dense[:k], skipped.value
+
+
+def parse_din(data, threads: int = 0):
+    """DIN behaviour-log lines -> dict(hist_items, hist_cats int64[K], offsets int64[n+1],
+    target_item, target_cat int64[n], label float32[n], n_skipped)."""
+    p, nbytes, _keep = _buf(data)
+    cap = count_lines(data)
+    keys_cap = max(1, nbytes // 2)
+    items = np.empty(keys_cap, np.int64)
+    cats = np.empty(keys_cap, np.int64)
+    offsets = np.empty(cap + 1, np.int64)
+    ti, tc = np.empty(cap, np.int64), np.empty(cap, np.int64)
+    label = np.empty(cap, np.float32)
+    n, nk, skipped = c_int64(0), c_int64(0), c_int64(0)
+    _check(load().b200rec_io_parse_din(p, nbytes, _np_ptr(items), _np_ptr(cats), _np_ptr(offsets),
+                                       _np_ptr(ti), _np_ptr(tc), _np_ptr(label), cap, keys_cap,
+                                       ctypes.byref(n), ctypes.byref(nk), ctypes.byref(skipped), threads))
+    k = n.value
+    return {"hist_items": items[:nk.value].copy(), "hist_cats": cats[:nk.value].copy(),
+            "offsets": offsets[:k + 1].copy(), "target_item": ti[:k].copy(), "target_cat": tc[:k].copy(),
+            "label": label[:k].copy(), "n_skipped": skipped.value}
+
+
+class DinBatchReader:
+    """Batches of the reference's DIN reader (models/rank/din/dinReader.py:44-144) built from the
+    natively parsed LoD arrays with numpy instead of per-sample Python: records are taken in file
+    order in groups of 20*batch_size, each group is stably sorted by history length, cut into
+    batches, and every batch is padded with id 0 to ITS OWN max length; the mask is 0 / -1e9 stored
+    as int64 [B, L, 1]; the target ids are tiled L times; the tail group drops its incomplete
+    batch.  Yields the 8-tuple the DataLoader collate of that reader produces:
+    (hist_item[B,L], hist_cat[B,L], target_item[B], target_cat[B], label[B] f32, mask[B,L,1] i64,
+     target_item_seq[B,L], target_cat_seq[B,L])."""
+
+    def __init__(self, file_list: Sequence[str], batch_size: int, threads: int = 0,
+                 as_torch: bool = True, pin_memory: bool = False):
+        self.file_list = sorted(file_list)
+        self.batch_size = int(batch_size)
+        self.group_size = self.batch_size * 20
+        self.threads, self.as_torch, self.pin_memory = threads, as_torch, pin_memory
+
+    def _records(self):
+        parts = []
+        for path in self.file_list:
+            with open(path, "rb") as fh:
+                parts.append(parse_din(fh.read(), self.threads))
+        lens = np.concatenate([np.diff(p["offsets"]) for p in parts]) if parts else np.zeros(0, np.int64)
+        cat = lambda k: np.concatenate([p[k] for p in parts]) if parts else np.zeros(0, np.int64)  # noqa: E731
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        return cat("hist_items"), cat("hist_cats"), offsets, cat("target_item"), cat("target_cat"), cat("label")
+
+    def _batch(self, rec, idx):
+        items, cats, offsets, ti, tc, label = rec
+        lens = (offsets[idx + 1] - offsets[idx]).astype(np.int64)
+        B, L = idx.size, int(lens.max())
+        col = np.arange(L, dtype=np.int64)[None, :]
+        valid = col < lens[:, None]
+        src = (offsets[idx][:, None] + col)[valid]
+        hist_item = np.zeros((B, L), np.int64)
+        hist_cat = np.zeros((B, L), np.int64)
+        hist_item[valid] = items[src]
+        hist_cat[valid] = cats[src]
+        mask = np.where(valid, 0, int(-1e9)).astype(np.int64).reshape(B, L, 1)
+        out = (hist_item, hist_cat, ti[idx], tc[idx], label[idx].astype(np.float32), mask,
+               np.repeat(ti[idx][:, None], L, 1), np.repeat(tc[idx][:, None], L, 1))
+        if not self.as_torch:
+            return out
+        import torch
+
+        ts = tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in out)
+        if self.pin_memory and torch.cuda.is_available():
+            ts = tuple(t.pin_memory() for t in ts)
+        return ts
+
+    def __iter__(self):
+        rec = self._records()
+        n = rec[3].size
+        lens = np.diff(rec[2])
+        B, G = self.batch_size, self.group_size
+        for g0 in range(0, n, G):
+            g1 = min(n, g0 + G)
+            order = g0 + np.argsort(lens[g0:g1], kind="stable")
+            end = (g1 - g0) if g1 - g0 == G else (g1 - g0) - (g1 - g0) % B
+            for i in range(0, end, B):
+                yield self._batch(rec, order[i:i + B])
 
 
 def hash_std_string(s: bytes) -> int:

@@ -109,6 +109,10 @@ def create_data_loader(config, mode="train", rank=0, world_size=1):
         from . import dataio
 
         fmt = config.get("runner.packed_format", "slot_text")
+        if fmt == "din":     # behaviour logs: length-grouped, per-batch padding (dinReader.py)
+            return dataio.DinBatchReader(file_list, batch_size=batch_size,
+                                         threads=int(config.get("runner.reader_threads", 0)),
+                                         pin_memory=torch.cuda.is_available())
         schemas = {"criteo": dataio.CRITEO, "criteo_dcn_v2": dataio.CRITEO_DCN_V2}
         schema_name = config.get("runner.packed_schema", "criteo")
         if schema_name not in schemas:

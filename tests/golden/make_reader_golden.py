@@ -9,6 +9,11 @@
   slot_text_criteo_reader.npz  what the reference's models/rank/deepfm/criteo_reader.py yields for
                                them (imported from /root/reference on top of oracle/paddle_shim.py)
 
+  din_sample.txt               synthetic DIN behaviour logs (`hist;cats;target;cat;label`)
+  din_reader_batches.npz       what the reference's models/rank/din/dinReader.py yields for them at
+                               batch_size 3 (one full 60-record group + a 17-record tail), stacked
+                               per batch the way the DataLoader collates them
+
 usage: python tests/golden/make_reader_golden.py
 """
 import os
@@ -72,6 +77,45 @@ def make_slot_text(rng, n=48):
     return "\n".join(lines) + "\n"
 
 
+def make_din(rng, n=77):
+    lines = []
+    for i in range(n):
+        k = min(40, max(1, int(rng.expovariate(1 / 6.0)) + 1))
+        hist = " ".join(str(rng.randint(1, 63000)) for _ in range(k))
+        cats = " ".join(str(rng.randint(1, 800)) for _ in range(k))
+        lines.append("%s;%s;%d;%d;%d" % (hist, cats, rng.randint(1, 63000), rng.randint(1, 800),
+                                        rng.randint(0, 1)))
+    lines.insert(9, "1 2 3;4 5 6;7")          # fewer than 5 fields: skipped (dinReader.py:64-65)
+    return "\n".join(lines) + "\n"
+
+
+def din_golden(path):
+    import importlib.util
+    import tempfile
+
+    from oracle import paddle_shim
+
+    paddle_shim.install()
+    spec = importlib.util.spec_from_file_location("ref_din_reader", "/root/reference/models/rank/din/dinReader.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())              # the reference writes ./tmp.txt as a side effect
+    try:
+        ds = mod.RecDataset([path], {"runner.train_batch_size": 3})
+        samples = list(ds)
+    finally:
+        os.chdir(cwd)
+    out = {}
+    names = ["hist_item", "hist_cat", "target_item", "target_cat", "label", "mask", "target_item_seq",
+             "target_cat_seq"]
+    for b in range(len(samples) // 3):
+        for j, name in enumerate(names):
+            out["b%d/%s" % (b, name)] = np.stack([np.asarray(s[j]) for s in samples[3 * b:3 * b + 3]])
+    np.savez_compressed(os.path.join(HERE, "din_reader_batches.npz"), **out)
+    return len(samples)
+
+
 def main():
     rng = random.Random(12345)
     tsv = make_tsv(rng)
@@ -99,6 +143,10 @@ def main():
     ids = np.stack([np.concatenate(s[:27]) for s in samples]).astype(np.int64)
     dense = np.stack([s[27] for s in samples]).astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "slot_text_criteo_reader.npz"), ids=ids, dense=dense)
+    din_path = os.path.join(HERE, "din_sample.txt")
+    with open(din_path, "w") as fh:
+        fh.write(make_din(rng))
+    print("din: %d samples from the reference reader" % din_golden(din_path))
     print("tsv: %d lines -> %d parsed by parser.cpp; slot text: %d samples" %
           (tsv.count("\n"), out.count(b"\n"), len(samples)))
 

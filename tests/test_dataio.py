@@ -29,7 +29,7 @@ def _read(name, mode="rb"):
 def test_library_exports_every_declared_symbol():
     lib = dataio.load()
     declared = dataio.declared_symbols()
-    assert len(declared) == 10 and set(declared) == set(dataio._SIG)
+    assert len(declared) == 11 and set(declared) == set(dataio._SIG)
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.b200rec_io_abi_version() == dataio.IO_ABI_VERSION
@@ -363,3 +363,69 @@ def test_dygraph_model_consumes_packed_batches(tmp_path):
     label, ids, dense = dm.create_feeds(batch, cfg)
     assert label.shape == (32, 1) and dense.shape == (32, 13) and dense.dtype == torch.float32
     assert ids.shape == (32, 26) and torch.equal(ids, batch[1])
+
+
+# ---- DIN behaviour logs vs the reference's dinReader.py ---------------------------------------------
+DIN_FIELDS = ["hist_item", "hist_cat", "target_item", "target_cat", "label", "mask", "target_item_seq",
+              "target_cat_seq"]
+
+
+def test_din_batches_match_golden_from_reference_reader():
+    gold = np.load(os.path.join(GOLD, "din_reader_batches.npz"))
+    rd = dataio.DinBatchReader([os.path.join(GOLD, "din_sample.txt")], batch_size=3, as_torch=False)
+    batches = list(rd)
+    assert len(batches) == 25                      # 60-record group + 17-record tail minus 2
+    for b, batch in enumerate(batches):
+        for j, name in enumerate(DIN_FIELDS):
+            want = gold["b%d/%s" % (b, name)]
+            assert batch[j].shape == want.shape and batch[j].dtype == want.dtype, (b, name)
+            assert np.array_equal(batch[j], want), (b, name)
+    # lengths are sorted inside a group, every batch is padded to its own maximum
+    Ls = [b[0].shape[1] for b in batches]
+    assert Ls[:20] == sorted(Ls[:20]) and Ls[20:] == sorted(Ls[20:]) and Ls[19] > Ls[20]
+    assert batches[0][5].min() in (0, int(-1e9)) and batches[-1][5].dtype == np.int64
+
+
+def test_din_native_reader_matches_python_reader_through_the_dataloader():
+    import torch
+
+    from paddlerec_b200 import runner
+
+    d = os.path.join(ROOT, "paddlerec_b200", "rank", "din")
+    cfg = runner.load_yaml(os.path.join(d, "config.yaml"))
+    cfg["config_abs_dir"] = d
+    for bs in (32, 2):                             # bs=2: 100 records = 2 full groups + a tail of 20
+        cfg["runner.train_batch_size"] = bs
+        plain = list(runner.create_data_loader(cfg))
+        native = list(dataio.DinBatchReader([os.path.join(d, "data", "train_data", "sample_data.txt")], bs))
+        assert len(plain) == len(native) == 100 // bs
+        for a, b in zip(plain, native):
+            for j in range(8):
+                assert torch.equal(a[j], b[j]) and a[j].dtype == b[j].dtype, j
+
+
+def test_din_parse_edge_cases():
+    r = dataio.parse_din("1 2;3 4;5;6;1\nbroken;line\n\n 7 ; 8 ;9; 10 ;0.5;extra;fields\n")
+    assert r["n_skipped"] == 1 and r["offsets"].tolist() == [0, 2, 3]
+    assert r["hist_items"].tolist() == [1, 2, 7] and r["hist_cats"].tolist() == [3, 4, 8]
+    assert r["target_item"].tolist() == [5, 9] and r["target_cat"].tolist() == [6, 10]
+    assert r["label"].tolist() == [1.0, 0.5]
+    with pytest.raises(dataio.B200RecIOError, match="differ in length") as e:
+        dataio.parse_din("1 2 3;4 5;6;7;1\n")
+    assert e.value.code == -4
+    with pytest.raises(dataio.B200RecIOError, match="line 2: bad id"):
+        dataio.parse_din("1;2;3;4;1\n1 x;2 3;3;4;0\n")
+    with pytest.raises(dataio.B200RecIOError, match="bad label"):
+        dataio.parse_din("1;2;3;4;yes\n")
+    # thread count does not change the result
+    rng = np.random.default_rng(8)
+    lines = []
+    for _ in range(4000):
+        k = int(rng.integers(1, 30))
+        lines.append("%s;%s;%d;%d;%d" % (" ".join(map(str, rng.integers(1, 10**6, k))),
+                                        " ".join(map(str, rng.integers(1, 800, k))),
+                                        rng.integers(1, 10**6), rng.integers(1, 800), rng.integers(0, 2)))
+    text = "\n".join(lines)
+    a, b = dataio.parse_din(text, threads=1), dataio.parse_din(text, threads=8)
+    assert all(np.array_equal(a[k], b[k]) for k in a if k != "n_skipped")
+    assert a["offsets"][-1] == a["hist_items"].size == a["hist_cats"].size

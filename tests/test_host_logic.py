@@ -169,6 +169,17 @@ def test_every_model_directory_is_a_complete_plugin(model):
         assert len(batch) == 28 and batch[27].shape == (bs, 13)
 
 
+def test_din_packed_reader_type():
+    d = os.path.join(PKG, "rank", "din")
+    cfg = runner.load_yaml(os.path.join(d, "config.yaml"))
+    cfg["config_abs_dir"] = d
+    plain = list(runner.create_data_loader(cfg))
+    native = list(runner.create_data_loader({**cfg, "runner.reader_type": "PackedReader",
+                                             "runner.packed_format": "din"}))
+    assert len(plain) == len(native) == 3
+    assert all(torch.equal(x, y) for a, b in zip(plain, native) for x, y in zip(a, b))
+
+
 def test_dcn_v2_reader_log_transform_and_native_schema():
     """dcn_v2/reader.py:53-61: dense = log(v+1), `slot:` with an empty value is skipped — the Python
     mirror and the native parser (dataio.CRITEO_DCN_V2) agree bit for bit."""
