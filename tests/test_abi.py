@@ -73,3 +73,55 @@ def test_every_entry_point_has_a_torch_wrapper():
                  "din_attention", "continuous_value_model", "raw_shard_bucketize", "SelectedRows",
                  "raw_sparse_adam", "raw_sparse_sgd", "raw_sparse_adagrad", "raw_tower_split"):
         assert hasattr(ops, attr), attr
+
+
+def _prototypes(header):
+    """{name: [category per parameter]} parsed from a C header; category in ptr / i64 / i32 / f64 / f32."""
+    import re
+
+    text = open(os.path.join(_lib.INCLUDE_DIR, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|uint64_t|uint32_t|const char\s*\*)\s+(b200rec_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;",
+                         text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        cats = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    cats.append("ptr")
+                elif re.search(r"\b(int64_t|uint64_t|size_t)\b", a):
+                    cats.append("i64")
+                elif re.search(r"\bdouble\b", a):
+                    cats.append("f64")
+                elif re.search(r"\bfloat\b", a):
+                    cats.append("f32")
+                elif re.search(r"\b(int|uint32_t|int32_t)\b", a):
+                    cats.append("i32")
+                else:
+                    raise AssertionError("unparsed parameter %r of %s" % (a, name))
+        protos[name] = cats
+    return protos
+
+
+def _ctype_category(t):
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, ctypes._Pointer):
+        return "ptr"
+    return {ctypes.c_int64: "i64", ctypes.c_size_t: "i64", ctypes.c_uint64: "i64", ctypes.c_int: "i32",
+            ctypes.c_uint32: "i32", ctypes.c_double: "f64", ctypes.c_float: "f32"}[t]
+
+
+@pytest.mark.parametrize("header,module", [("b200rec.h", "_lib"), ("b200rec_io.h", "dataio")])
+def test_ctypes_signatures_match_the_header_prototypes(header, module):
+    """Arity and the width/kind of every parameter of every bound function — a wrong ctypes
+    signature corrupts arguments silently (an int64 passed as int loses its upper half)."""
+    import importlib
+
+    mod = importlib.import_module("paddlerec_b200." + module)
+    protos = _prototypes(header)
+    assert set(protos) == set(mod._SIG)
+    for name, (_res, argtypes) in mod._SIG.items():
+        got = [_ctype_category(t) for t in argtypes]
+        assert got == protos[name], "%s: header %s, ctypes %s" % (name, protos[name], got)
