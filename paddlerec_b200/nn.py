@@ -216,6 +216,11 @@ class Embedding(tnn.Module):
         return ops.gather_pool_sum(self.weight, keys, offsets, self.pad, self,
                                    _autograd_hook(keys.device))
 
+    def forward_seqpool_cvm(self, keys, offsets, n_slots: int, show_click, use_cvm: bool):
+        """All multi-hot slots of a batch at once: sum-pool + CVM (ops.fused_seqpool_cvm)."""
+        return ops.fused_seqpool_cvm(self.weight, keys, offsets, n_slots, show_click, use_cvm,
+                                     self.pad, self, _autograd_hook(keys.device))
+
     def clear_grad(self) -> None:
         self.weight.grad_rows = None
 

@@ -681,6 +681,30 @@ def continuous_value_model(x, show_click, use_cvm):
     return _CVM.apply(x, show_click, use_cvm)
 
 
+def fused_seqpool_cvm(W, keys, offsets, n_slots: int, show_click, use_cvm: bool, padding_idx, sink,
+                      hook):
+    """`fused_seqpool_cvm(embs, "sum", show_clk, use_cvm)` of the PS/GPUBox models
+    (tools/utils/static_ps/model_util.py:411-415; slot_dnn/net.py:63-75 spells it as
+    sequence_pool(sum) + continuous_value_model): for every (sample, slot) bag the rows of its
+    variable-length key list are summed, then the two leading show/click columns are transformed
+    (use_cvm) or dropped; backward writes `show_click` into those two gradient columns so the table
+    accumulates the statistics.
+
+    ALL slots go through ONE pooled gather and ONE CVM launch: `keys`/`offsets` hold the bags in
+    sample-major order, bag b = n*n_slots + f — the layout dataio.parse_slot_text_lod emits.
+    W: [V, D+2]; show_click: [B, 2].  Returns [B, n_slots, D+2 if use_cvm else D]."""
+    n_bags = offsets.numel() - 1
+    if n_bags % n_slots:
+        raise ValueError("fused_seqpool_cvm: %d bags is not a multiple of n_slots=%d" % (n_bags, n_slots))
+    B = n_bags // n_slots
+    if show_click.shape != (B, 2):
+        raise ValueError("fused_seqpool_cvm: show_click must be [%d, 2], got %s" % (B, tuple(show_click.shape)))
+    pooled = gather_pool_sum(W, keys, offsets, padding_idx, sink, hook)            # [B*F, D+2]
+    per_bag = show_click.to(torch.float32).repeat_interleave(n_slots, dim=0)         # [B*F, 2]
+    out = continuous_value_model(pooled, per_bag, use_cvm)
+    return out.reshape(B, n_slots, out.shape[1])
+
+
 # ---- K4: DIN attention pooling ------------------------------------------------------------------
 HAVE_DIN_ATTN = True
 

@@ -154,7 +154,7 @@ def raw_sparse_adam(W, m, v, sr, lr, beta1, beta2, eps, beta1_pow, beta2_pow):
 
 KERNEL_NAMES = ("raw_gather", "raw_embed_fm_fwd", "raw_embed_fm_bwd", "raw_segment_reduce",
                 "raw_rows_to_dense", "raw_sparse_sgd", "raw_sparse_adam", "raw_dot_interact_fwd",
-                "raw_dot_interact_bwd")
+                "raw_dot_interact_bwd", "raw_gather_pool_sum", "raw_cvm_fwd", "raw_cvm_bwd")
 
 
 def install(monkeypatch, ops):
@@ -166,8 +166,11 @@ def install(monkeypatch, ops):
     for name in KERNEL_NAMES:
         fn = getattr(me, name)
         if name == "raw_segment_reduce":
-            monkeypatch.setattr(ops, name, lambda dOut, seg, pos, num, n, row_of_pos=None:
-                                raw_segment_reduce(dOut, seg, pos, num, n))
+            def seg_reduce(dOut, seg, pos, num, n, row_of_pos=None):
+                if row_of_pos is not None:      # pooled lookup: position p contributes dOut[bag(p)]
+                    dOut = dOut[row_of_pos[:n].long()]
+                return raw_segment_reduce(dOut, seg, pos, num, n)
+            monkeypatch.setattr(ops, name, seg_reduce)
         else:
             monkeypatch.setattr(ops, name, fn)
 
@@ -176,3 +179,24 @@ def install(monkeypatch, ops):
         return ops.IdGroups(g.unique_ids, g.seg_offsets, g.sorted_pos, g.num, g.n, V)
 
     monkeypatch.setattr(ops, "raw_group_ids", group)
+
+
+# ---- LoD pooling + CVM stand-ins -------------------------------------------------------------------
+def raw_gather_pool_sum(W, keys, offsets, padding_idx, D=None):
+    W = W if D is None else W[:, :D]
+    keys, offsets = keys.reshape(-1), offsets.reshape(-1)
+    n_bags = offsets.numel() - 1
+    lens = offsets[1:] - offsets[:-1]
+    bag = torch.repeat_interleave(torch.arange(n_bags), lens)
+    rows = raw_gather(W, keys, padding_idx)
+    out = torch.zeros(n_bags, W.shape[1]).index_add(0, bag, rows)
+    return out, bag.to(torch.int32)
+
+
+def raw_cvm_fwd(x, use_cvm):
+    from oracle import nets
+    return nets.cvm(x, use_cvm)
+
+
+def raw_cvm_bwd(dy, show_click, D, use_cvm):
+    return torch.cat([show_click[:, :2], dy[:, 2:] if use_cvm else dy], 1)

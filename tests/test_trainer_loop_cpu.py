@@ -105,3 +105,57 @@ def test_the_product_refuses_to_run_without_cuda(tmp_path):
         runner.train(cfg)
     with pytest.raises(RuntimeError, match="CUDA device only"):
         runner.infer(cfg)
+
+
+@pytest.mark.parametrize("use_cvm", [False, True])
+def test_fused_seqpool_cvm_from_parsed_lod_text(cpu_engine, use_cvm):
+    """Multi-hot path end to end on the host side: variable-length `slot:value` text -> native LoD
+    parser -> ONE pooled lookup + ONE CVM for all slots (ops.fused_seqpool_cvm), forward and the
+    table gradient (show/click written into the two leading columns) against the oracle."""
+    from oracle import nets
+    from paddlerec_b200 import dataio, nn as bnn
+
+    rng = np.random.default_rng(11)
+    slots = ["s%d" % i for i in range(4)]
+    V, D, B = 50, 6, 9
+    lines = []
+    for _ in range(B):
+        toks = ["y:%d" % rng.integers(0, 2)]
+        for s in slots:
+            toks += ["%s:%d" % (s, rng.integers(0, V)) for _ in range(rng.integers(0, 5))]
+        lines.append(" ".join(toks))
+    sch = dataio.SlotSchema(sparse_slots=tuple(slots), label_slot="y", dense_slot=None)
+    label, keys, offsets, _ = dataio.parse_slot_text_lod("\n".join(lines), sch)
+    emb = bnn.Embedding(V, D + 2, padding_idx=0, init_std=0.5, device="cpu")
+    with torch.no_grad():
+        emb.weight[:, :2] = torch.rand(V, 2) * 5          # accumulated show / click statistics
+        emb.weight[0] = 0
+    show_click = torch.rand(B, 2) * 3
+    out = emb.forward_seqpool_cvm(torch.from_numpy(keys), torch.from_numpy(offsets), len(slots),
+                                  show_click, use_cvm)
+    assert out.shape == (B, len(slots), D + 2 if use_cvm else D)
+    # oracle: per bag sum of rows (padding key 0 -> zeros), then the CVM column transform
+    W = emb.weight.detach().double().requires_grad_(True)
+    ref = []
+    for b in range(B * len(slots)):
+        ks = torch.from_numpy(keys[offsets[b]:offsets[b + 1]])
+        ref.append((W[ks] * (ks != 0).unsqueeze(1)).sum(0))
+    ref = nets.cvm(torch.stack(ref), use_cvm).reshape(out.shape)
+    assert torch.allclose(out.double(), ref, rtol=1e-6, atol=1e-6)
+    gout = torch.randn(out.shape)
+    (out * gout).sum().backward()
+    (ref * gout.double()).sum().backward()
+    dW = emb.grad_rows.to_dense().double()
+    touched = np.unique(keys[keys != 0])
+    # embedding columns: the oracle's autograd; show/click columns: the batch's show_click, summed
+    # over the bags a key occurs in (Paddle's cvm_grad semantics), not d(log)/d(show)
+    assert torch.allclose(dW[touched][:, 2:], W.grad[touched][:, 2:], rtol=1e-5, atol=1e-6)
+    want_sc = torch.zeros(V, 2, dtype=torch.float64)
+    for b in range(B * len(slots)):
+        for k in keys[offsets[b]:offsets[b + 1]]:
+            if k != 0:
+                want_sc[k] += show_click[b // len(slots)].double()
+    assert torch.allclose(dW[:, :2], want_sc, rtol=1e-6, atol=1e-6)
+    assert not dW[0].any()
+    with pytest.raises(ValueError, match="multiple of n_slots"):
+        emb.forward_seqpool_cvm(torch.from_numpy(keys), torch.from_numpy(offsets), 5, show_click, use_cvm)
