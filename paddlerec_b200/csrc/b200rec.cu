@@ -318,23 +318,27 @@ static int dot_interact_launch(bool bwd, const float* T, const float* dR, float*
   if (B == 0) return B200REC_OK;
   NOT_NULL(T); NOT_NULL(out);
   const DotShape s(N, d, self_interaction ? 1 : 0);
-  const size_t per_warp = sizeof(float) * (bwd ? s.smem_floats_bwd() : s.smem_floats_fwd());
+  // B200REC_K6_V2=1 selects the experimental float4 / cp.async variant (dot_interact.cuh); read per
+  // call so that a test can compare both paths in one process
+  const char* v2_env = getenv("B200REC_K6_V2");
+  const bool v2 = v2_env && atoi(v2_env) != 0 && d % 4 == 0;
+  const size_t per_warp = sizeof(float) * (v2 ? dot_v2_smem_floats(s, bwd)
+                                              : (bwd ? s.smem_floats_bwd() : s.smem_floats_fwd()));
   int warps = kDotWarps;  // samples in flight per CTA; shrink until the tiles fit
   while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
   const size_t smem = warps * per_warp;
   B200_REQUIRE(smem <= 200 * 1024, "dot_interact: N*d too large for shared memory");
   const int64_t ctas = (B + warps - 1) / warps;
   const unsigned grid = (unsigned)min(ctas, (int64_t)sm_count() * 8);
-  if (bwd) {
-    NOT_NULL(dR);
-    if (smem > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(dot_interact_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dot_interact_bwd_kernel<<<grid, warps * 32, smem, ST(stream)>>>(T, dR, out, B, s);
-  } else {
-    if (smem > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(dot_interact_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dot_interact_fwd_kernel<<<grid, warps * 32, smem, ST(stream)>>>(T, out, B, s);
+  if (bwd) NOT_NULL(dR);
+  auto fwd_k = v2 ? dot_interact_fwd_v2_kernel : dot_interact_fwd_kernel;
+  auto bwd_k = v2 ? dot_interact_bwd_v2_kernel : dot_interact_bwd_kernel;
+  if (smem > 48 * 1024) {
+    if (bwd) B200_CUDA(cudaFuncSetAttribute(bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else B200_CUDA(cudaFuncSetAttribute(fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  if (bwd) bwd_k<<<grid, warps * 32, smem, ST(stream)>>>(T, dR, out, B, s);
+  else fwd_k<<<grid, warps * 32, smem, ST(stream)>>>(T, out, B, s);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

@@ -585,3 +585,25 @@ def test_dot_interact_rejects_bad_shapes():
     with pytest.raises(ValueError):
         ops.raw_dot_interact_bwd(torch.zeros(2, 3, 4, device=DEV), torch.zeros(2, 5, device=DEV))
     assert ops.raw_dot_interact_fwd(torch.zeros(0, 3, 4, device=DEV)).shape == (0, 7)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200REC_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental K6 v2 kernels: opt in with B200REC_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B,N,d", [(1, 2, 4), (33, 27, 16), (1000, 27, 16), (64, 40, 64), (9, 27, 128),
+                                   (3, 128, 4), (5000, 27, 8)])
+@pytest.mark.parametrize("self_interaction", [False, True])
+def test_dot_interact_v2_matches_v1(B, N, d, self_interaction, monkeypatch):
+    """The float4 / cp.async variant (B200REC_K6_V2=1) against the validated default: forward
+    bit-identical (same products in the same order), backward too (same j order per output)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + N + d)
+    T = torch.randn(B, N, d, generator=g).to(DEV)
+    dR = torch.randn(B, ops.dot_interact_width(N, d, self_interaction), generator=g).to(DEV)
+    monkeypatch.delenv("B200REC_K6_V2", raising=False)
+    R1 = ops.raw_dot_interact_fwd(T, self_interaction)
+    dT1 = ops.raw_dot_interact_bwd(T, dR, self_interaction)
+    monkeypatch.setenv("B200REC_K6_V2", "1")
+    R2 = ops.raw_dot_interact_fwd(T, self_interaction)
+    dT2 = ops.raw_dot_interact_bwd(T, dR, self_interaction)
+    assert torch.equal(R1, R2)
+    assert torch.equal(dT1, dT2)

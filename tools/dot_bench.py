@@ -32,7 +32,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=65536)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--v2", action="store_true", help="time the experimental B200REC_K6_V2 kernels")
     a = ap.parse_args()
+    if a.v2:
+        os.environ["B200REC_K6_V2"] = "1"
     dev = "cuda"
     peak = None
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -55,7 +58,7 @@ def main():
             return torch.cat([Ts[i][:, N - 1], Z[:, iu[0], iu[1]]], 1)
         ms_l = timed(lib_fwd, ring, a.iters)
         bf, bb = 4 * (N * d + d + P) * a.B, 4 * (2 * N * d + d + P) * a.B
-        row = {"kernel": "dot_interact", "B": a.B, "N": N, "d": d, "fwd_ms": round(ms_f, 4),
+        row = {"kernel": "dot_interact_v2" if a.v2 else "dot_interact", "B": a.B, "N": N, "d": d, "fwd_ms": round(ms_f, 4),
                "bwd_ms": round(ms_b, 4), "fwd_GBps": round(bf / ms_f / 1e6, 1),
                "bwd_GBps": round(bb / ms_b / 1e6, 1), "library_fwd_ms": round(ms_l, 4),
                "fwd_bytes": bf, "bwd_bytes": bb}
