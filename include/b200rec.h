@@ -239,11 +239,11 @@ int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V,
                             int64_t* perm, int32_t* inv_perm, int64_t* counts, void* workspace,
                             size_t workspace_bytes, void* stream);
 
-/* ---- K6: DLRM dot interaction (models/rank/dlrm/net.py:98-113) -----------------------------------
+/* ---- K6: DLRM dot interaction (models/rank/dlrm/net.py:97-115) -----------------------------------
  * T [B, N, d]: the num_field embedding rows followed by the bottom-MLP output x as the LAST row.
  * R [B, d + P]: R[:, :d] = x; R[:, d+p] = <T_i, T_j> over the upper triangle in row-major order,
  * P = N(N-1)/2, or N(N+1)/2 with self_interaction — whose diagonal entries are 0, as the
- * reference's triu(Z,1)+tril(MIN_FLOAT,-1)+masked_select evaluates (net.py:104-111).
+ * reference's triu(Z,1)+tril(MIN_FLOAT,-1)+masked_select evaluates (net.py:105-113).
  * Backward: dT from dR (includes dR[:, :d] flowing into the x row).  N*(d+1)+N*N floats of shared
  * memory per sample in flight must fit (N <= 128, d <= 256 checked). */
 int b200rec_dot_interact_fwd(const float* T, float* R, int64_t B, int N, int d, int self_interaction,

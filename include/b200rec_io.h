@@ -61,9 +61,9 @@ int b200rec_io_parse_slot_text(const char* text, size_t len, const char* label_s
 
 /* Same, with the two per-model variations of the reference's readers selected by `flags`:
  *   B200REC_IO_DENSE_LOG1P        dense value = log(v + 1), evaluated in double before narrowing to
- *                                 float32 (models/rank/dcn_v2/reader.py:60-61)
+ *                                 float32 (models/rank/dcn_v2/reader.py:63-64)
  *   B200REC_IO_SKIP_EMPTY_SPARSE  a sparse token with an empty value (`7:`) is ignored instead of
- *                                 being an error (dcn_v2/reader.py:53-55) */
+ *                                 being an error (dcn_v2/reader.py:55-57) */
 #define B200REC_IO_DENSE_LOG1P 1
 #define B200REC_IO_SKIP_EMPTY_SPARSE 2
 int b200rec_io_parse_slot_text_ex(const char* text, size_t len, const char* label_slot,
@@ -97,11 +97,11 @@ int b200rec_io_parse_multislot(const char* text, size_t len, const int* slot_is_
 /* ---- raw Criteo TSV -------------------------------------------------------------------------------
  * Column 0 label, 1..13 integer features, 14..39 categorical tokens, tab separated.
  * dense[n, j] = column empty ? 0 : (value - cont_min[j]) / cont_diff[j], computed in double
- * (parser.cpp:58-64, benchmark_reader.py:43-49); NULL cont_min/cont_diff = the constants both
+ * (parser.cpp:55-63, benchmark_reader.py:43-49); NULL cont_min/cont_diff = the constants both
  * reference readers hard-code.  ids[n, f] = hash(column 14+f) mod hash_dim with
- *   hash_kind 0: 64-bit libstdc++ std::hash<std::string> of the token   (parser.cpp:71)
+ *   hash_kind 0: 64-bit libstdc++ std::hash<std::string> of the token   (parser.cpp:68)
  *   hash_kind 1: xxHash32(seed 0) of str(column index) + token           (benchmark_reader.py:50-52)
- * Lines that do not have exactly 40 columns are skipped and counted (parser.cpp:50-52); with
+ * Lines that do not have exactly 40 columns are skipped and counted (parser.cpp:49-51); with
  * hash_kind 1 a short line is an error (the Python reader raises) and extra columns are ignored. */
 #define B200REC_IO_HASH_STD 0
 #define B200REC_IO_HASH_XXH32 1
@@ -110,11 +110,11 @@ int b200rec_io_parse_criteo_tsv(const char* text, size_t len, int hash_kind, int
                                 int64_t* ids, float* dense, int64_t cap, int64_t* n_out,
                                 int64_t* n_skipped_out, int n_threads);
 
-/* ---- DIN behaviour logs (models/rank/din/dinReader.py:61-70) ---------------------------------------
+/* ---- DIN behaviour logs (models/rank/din/dinReader.py:45-57) ---------------------------------------
  * Line: `hist_items;hist_cats;target_item;target_cat;label` — the two histories are blank-separated
  * id lists of equal length, label is a float.  Lines with fewer than 5 `;` fields are skipped
- * (dinReader.py:64-65) and counted.  Output is LoD: sample n owns hist_items / hist_cats
- * [offsets[n], offsets[n+1]).  Grouping by length, padding and the mask (dinReader.py:75-140) are
+ * (dinReader.py:52-53) and counted.  Output is LoD: sample n owns hist_items / hist_cats
+ * [offsets[n], offsets[n+1]).  Grouping by length, padding and the mask (dinReader.py:61-144) are
  * batch-level and live in the caller (paddlerec_b200/dataio.py: DinBatchReader). */
 int b200rec_io_parse_din(const char* text, size_t len, int64_t* hist_items, int64_t* hist_cats,
                          int64_t* offsets, int64_t* target_item, int64_t* target_cat, float* label,

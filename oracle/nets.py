@@ -54,7 +54,7 @@ def deepfm_fm(p: Params, sparse_inputs: Sequence[torch.Tensor], dense_inputs: to
     dense_embeddings = dense_inputs.unsqueeze(2) * p["fm.dense_w"]                # :118-119
     feat = torch.cat([sparse_embeddings, dense_embeddings], 1)                    # :120 [B,39,D]
     summed = feat.sum(1)                                                          # :123
-    summed_sq = summed.square()                                                   # :125
+    summed_sq = summed.square()                                                   # :117
     sq_sum = feat.square().sum(1)                                                 # :129-132
     y_second_order = 0.5 * (summed_sq - sq_sum).sum(1, keepdim=True)              # :134-137
     return y_first_order, y_second_order, feat
@@ -208,9 +208,9 @@ def batch_norm_running(mean, var, x, momentum=0.9):
 
 
 def dlrm_mlp(p: Params, prefix: str, x, n_layers: int):
-    """MLPLayer.forward — dlrm/net.py:122-169.  The guard `i != len(units_list) - 1` (:136) is true
+    """MLPLayer.forward — dlrm/net.py:121-171.  The guard `i != len(units_list) - 1` (:135) is true
     for every i of enumerate(units_list[:-1]), so EVERY layer, the last included, is
-    Linear -> ReLU -> BatchNorm1D and the `else` branch (:153-166) never runs."""
+    Linear -> ReLU -> BatchNorm1D and the `else` branch (:152-165) never runs."""
     for i in range(n_layers):
         x = linear(x, p["%sdense_%d.weight" % (prefix, i)], p["%sdense_%d.bias" % (prefix, i)])
         x = torch.relu(x)
@@ -219,9 +219,9 @@ def dlrm_mlp(p: Params, prefix: str, x, n_layers: int):
 
 
 def dot_interact(T, self_interaction: bool = False):
-    """net.py:104-113 on T [B, N, d] (x = last row): Z = T T^T; the strict upper triangle in
+    """net.py:103-115 on T [B, N, d] (x = last row): Z = T T^T; the strict upper triangle in
     row-major order — with self_interaction the diagonal positions are selected too but hold 0,
-    because triu(Z, 1) has already zeroed them (:106-111); R = concat([x, Zflat])."""
+    because triu(Z, 1) has already zeroed them (:105-113); R = concat([x, Zflat]) (:115)."""
     B, N, d = T.shape
     Z = torch.bmm(T, T.transpose(1, 2))
     iu = torch.triu_indices(N, N, 0 if self_interaction else 1)
@@ -233,18 +233,18 @@ def dot_interact(T, self_interaction: bool = False):
 
 def dlrm_forward(p: Params, sparse_inputs, dense_inputs, *, n_bot: int, n_top: int,
                  self_interaction: bool = False):
-    """DLRMLayer.forward — dlrm/net.py:84-116.  Returns the raw [B, 2] scores (train mode)."""
-    x = dlrm_mlp(p, "bot_mlp.", dense_inputs, n_bot)                               # :93
+    """DLRMLayer.forward — dlrm/net.py:76-118.  Returns the raw [B, 2] scores (train mode)."""
+    x = dlrm_mlp(p, "bot_mlp.", dense_inputs, n_bot)                               # :86
     d = x.shape[1]
-    embs = [embedding(p["embedding.weight"], s).reshape(-1, d) for s in sparse_inputs]  # :96-101
-    T = torch.cat(embs + [x], 1).reshape(x.shape[0], len(embs) + 1, d)             # :104-107
-    R = dot_interact(T, self_interaction)                                          # :110-123
-    return dlrm_mlp(p, "top_mlp.", R, n_top)                                       # :125
+    embs = [embedding(p["embedding.weight"], s).reshape(-1, d) for s in sparse_inputs]  # :89-94
+    T = torch.cat(embs + [x], 1).reshape(x.shape[0], len(embs) + 1, d)             # :97-100
+    R = dot_interact(T, self_interaction)                                          # :103-115
+    return dlrm_mlp(p, "top_mlp.", R, n_top)                                       # :117
 
 
 def softmax_cross_entropy(logits, label):
     """paddle.nn.functional.cross_entropy(input, label) with hard int64 labels [B,1], mean
-    (dlrm/dygraph_model.py:57-61)."""
+    (dlrm/dygraph_model.py:58-62)."""
     lse = torch.logsumexp(logits, 1)
     picked = logits.gather(1, label.reshape(-1, 1).to(torch.int64)).squeeze(1)
     return (lse - picked).mean()

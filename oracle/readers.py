@@ -19,15 +19,15 @@ import numpy as np
 M64 = (1 << 64) - 1
 M32 = (1 << 32) - 1
 
-CONT_MIN = [0, -3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]           # parser.cpp:38, benchmark_reader.py:23
-CONT_DIFF = [20, 603, 100, 50, 64000, 500, 100, 50, 500, 10, 10, 10, 50]  # parser.cpp:40, :25
-HASH_DIM = 1000001                                             # parser.cpp:41, benchmark_reader.py:26
+CONT_MIN = [0, -3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]           # parser.cpp:37, benchmark_reader.py:23
+CONT_DIFF = [20, 603, 100, 50, 64000, 500, 100, 50, 500, 10, 10, 10, 50]  # parser.cpp:39, :25
+HASH_DIM = 1000001                                             # parser.cpp:40, benchmark_reader.py:26
 
 
 # ---- models/rank/deepfm/criteo_reader.py:61-103 ---------------------------------------------------
 def slot_text_lines(lines: Sequence[str], sparse_slots: Sequence[str], dense_slot: str, dense_dim: int):
     """One entry per line: ([values of sparse slot 0], ..., [dense values]).  Follows the reader
-    statement by statement: strip + split(" ") (:66), split(":") and take [0]/[1] (:69-70), skip
+    statement by statement: strip + split(" ") (:67), split(":") and take [0]/[1] (:70-71), skip
     unknown slots (:72-73), int()/float() (:74-77), pad a slot that did not appear with [0] or
     [0]*dense_dim (:80-89).  Blank lines are skipped (the packed readers' one documented
     difference: the reference would emit an all-padding sample)."""
@@ -59,7 +59,7 @@ def slot_text_packed(lines, sparse_slots, dense_slot, dense_dim):
     return ids, dense
 
 
-# ---- libstdc++ std::hash<std::string> (what parser.cpp:71 calls) ----------------------------------
+# ---- libstdc++ std::hash<std::string> (what parser.cpp:68 calls) ----------------------------------
 def std_hash_string(s: bytes) -> int:
     """64-bit std::_Hash_bytes of libstdc++ (MurmurHash64A-style, seed 0xc70f6907)."""
     mul = ((0xc6a4a793 << 32) + 0x5bd1e995) & M64
@@ -83,7 +83,7 @@ def std_hash_string(s: bytes) -> int:
     return h
 
 
-# ---- xxHash32 (benchmark_reader.py:50 calls xxhash.xxh32(..).intdigest()) --------------------------
+# ---- xxHash32 (benchmark_reader.py:52 calls xxhash.xxh32(..).intdigest()) --------------------------
 def xxh32(s: bytes, seed: int = 0) -> int:
     P1, P2, P3, P4, P5 = 2654435761, 2246822519, 3266489917, 668265263, 374761393
     rotl = lambda x, r: ((x << r) | (x >> (32 - r))) & M32
@@ -114,12 +114,12 @@ def xxh32(s: bytes, seed: int = 0) -> int:
     return h
 
 
-# ---- tools/dataset/parser.cpp:47-77 and models/rank/dnn/benchmark_reader.py:39-56 -------------------
+# ---- tools/dataset/parser.cpp:43-77 and models/rank/dnn/benchmark_reader.py:39-56 -------------------
 def criteo_tsv_lines(lines: Sequence[str], hash_kind: str = "std", hash_dim: int = HASH_DIM
                      ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
     """(label[n], ids[n,26], dense[n,13] float32, n_skipped).  hash_kind "std": parser.cpp — lines
-    without exactly 40 tab-separated columns are skipped (:50-52), dense = (stod(x)-min)/diff or 0
-    for an empty column (:58-64), id = std::hash<string>(column) % hash_dim (:71).  "xxh32":
+    without exactly 40 tab-separated columns are skipped (:49-51), dense = (stod(x)-min)/diff or 0
+    for an empty column (:55-63), id = std::hash<string>(column) % hash_dim (:68).  "xxh32":
     benchmark_reader.line_process — id = xxh32(str(idx) + column) % hash_dim (:50-52)."""
     label, ids, dense, skipped = [], [], [], 0
     for l in lines:

@@ -1,12 +1,12 @@
-// K6 — DLRM dot interaction (models/rank/dlrm/net.py:98-113), forward and backward.
+// K6 — DLRM dot interaction (models/rank/dlrm/net.py:97-115), forward and backward.
 //
 //   T [B, N, d]   N = num_field + 1 feature vectors per sample: the 26 embedding rows, then the
-//                 bottom-MLP output x as the LAST row (net.py:98-101)
-//   R [B, d + P]  R[:, :d] = x  (the concat of net.py:113 fused in),
+//                 bottom-MLP output x as the LAST row (net.py:97-100)
+//   R [B, d + P]  R[:, :d] = x  (the concat of net.py:115 fused in),
 //                 R[:, d + p] = <T_i, T_j> for the pairs (i, j) of the upper triangle in row-major
 //                 order; P = N(N-1)/2 (i < j), or N(N+1)/2 with self_interaction, where — exactly
 //                 as the reference's triu(Z,1) + tril(MIN_FLOAT,-1) + masked_select evaluates —
-//                 the diagonal entries are selected but carry 0, not <T_i, T_i> (net.py:104-111).
+//                 the diagonal entries are selected but carry 0, not <T_i, T_i> (net.py:105-113).
 //
 // One warp per sample, persistent grid.  The sample's N*d floats are staged in shared memory with a
 // row pitch of d+1 (consecutive pairs differ in j, so lanes hit consecutive rows: pitch d+1 is

@@ -483,7 +483,7 @@ int b200rec_io_parse_slot_text_lod(const char* text, size_t len, const char* lab
         st.set(B200REC_IO_ERR_RAGGED, n, "dense slot is shorter than dense_dim:", sc.dense);
       for (int f = 0; f < F; ++f) {
         auto& b = bags[size_t(f)];
-        if (b.empty()) b.push_back(0);  // padded like criteo_reader.py:86-88
+        if (b.empty()) b.push_back(0);  // padded like criteo_reader.py:88-89
         L.bag_len.push_back(int32_t(b.size()));
         L.keys.insert(L.keys.end(), b.begin(), b.end());
       }

@@ -153,8 +153,8 @@ class SlotSchema:
     label_slot: Optional[str] = "click"
     dense_slot: Optional[str] = "dense_feature"
     dense_dim: int = 13
-    dense_log1p: bool = False          # dense = log(v + 1)   (models/rank/dcn_v2/reader.py:60-61)
-    skip_empty_sparse: bool = False    # ignore `slot:` with no value (dcn_v2/reader.py:53-55)
+    dense_log1p: bool = False          # dense = log(v + 1)   (models/rank/dcn_v2/reader.py:63-64)
+    skip_empty_sparse: bool = False    # ignore `slot:` with no value (dcn_v2/reader.py:55-57)
 
     @property
     def flags(self) -> int:
@@ -292,7 +292,7 @@ def parse_din(data, threads: int = 0):
 
 
 class DinBatchReader:
-    """Batches of the reference's DIN reader (models/rank/din/dinReader.py:44-144) built from the
+    """Batches of the reference's DIN reader (models/rank/din/dinReader.py:45-144) built from the
     natively parsed LoD arrays with numpy instead of per-sample Python: records are taken in file
     order in groups of 20*batch_size, each group is stably sorted by history length, cut into
     batches, and every batch is padded with id 0 to ITS OWN max length; the mask is 0 / -1e9 stored

@@ -69,7 +69,7 @@ def auc_from_stats(pos: np.ndarray, neg: np.ndarray) -> float:
 
 def softmax_cross_entropy(logits: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     """paddle.nn.functional.cross_entropy(input, label) with hard labels [B,1] (per-sample, no
-    reduction; models/rank/dlrm/dygraph_model.py:57-61 takes the mean)."""
+    reduction; models/rank/dlrm/dygraph_model.py:58-62 takes the mean)."""
     return torch.nn.functional.cross_entropy(logits, label.reshape(-1).to(torch.int64),
                                              reduction="none").unsqueeze(1)
 

@@ -609,7 +609,7 @@ class _DotInteract(torch.autograd.Function):
 
 def dot_interact(T: torch.Tensor, self_interaction: bool = False) -> torch.Tensor:
     """DLRM's pairwise-dot feature interaction with the `concat([x, Zflat])` fused in
-    (models/rank/dlrm/net.py:98-113); T = [26 embedding rows ..., x]."""
+    (models/rank/dlrm/net.py:97-115); T = [26 embedding rows ..., x]."""
     return _DotInteract.apply(T, self_interaction)
 
 

@@ -1,6 +1,6 @@
 """DCN-V2 reader — the reference's models/rank/dcn_v2/reader.py:21-89: the Criteo `slot:value`
-format of DeepFM with two differences: dense values are log(v + 1) (:60-61) and a sparse token with
-an empty value is skipped (:53-55).  Native equivalent: dataio.CRITEO_DCN_V2."""
+format of DeepFM with two differences: dense values are log(v + 1) (:63-64) and a sparse token with
+an empty value is skipped (:55-57).  Native equivalent: dataio.CRITEO_DCN_V2."""
 from __future__ import annotations
 
 import numpy as np

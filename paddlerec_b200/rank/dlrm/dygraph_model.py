@@ -22,7 +22,7 @@ class DygraphModel(_CriteoBase):
             num_field=g("hyper_parameters.num_field"), self_interaction=False, device=self.device)
 
     def create_loss(self, raw_predict_2d, label):
-        return BF.softmax_cross_entropy(raw_predict_2d, label).mean()            # :57-61
+        return BF.softmax_cross_entropy(raw_predict_2d, label).mean()            # :58-62
 
     def create_optimizer(self, dy_model, config):
         lr = config.get("hyper_parameters.optimizer.learning_rate", 0.001)
@@ -32,7 +32,7 @@ class DygraphModel(_CriteoBase):
         return [BF.Auc("ROC"), BF.Accuracy()], ["auc", "accuracy"]
 
     def _update_metrics(self, metrics_list, raw_pred_2d, label):
-        predict_2d = torch.softmax(raw_pred_2d.detach(), dim=1)                  # :86
+        predict_2d = torch.softmax(raw_pred_2d.detach(), dim=1)                  # :88
         if metrics_list:
             metrics_list[0].update(preds=predict_2d, labels=label)
             metrics_list[1].update(metrics_list[1].compute(pred=predict_2d, label=label))

@@ -1,13 +1,13 @@
 """DLRM network — same classes / constructor arguments / state_dict names as the reference's
-models/rank/dlrm/net.py (DLRMLayer :23-116, MLPLayer :119-169).
+models/rank/dlrm/net.py (DLRMLayer :23-118, MLPLayer :121-171).
 
 CUDA path: the 26 per-slot lookups into the one table (no padding_idx, TruncatedNormal) are a single
 b200rec_gather over [B,26]; `bmm(T, T^T)` + triu/tril/masked_select + `concat([x, Zflat])`
-(net.py:104-113) is ONE kernel, b200rec_dot_interact (K6), that never materialises the [B,27,27]
+(net.py:103-115) is ONE kernel, b200rec_dot_interact (K6), that never materialises the [B,27,27]
 product; the two MLPs are library GEMMs with torch's batch-norm.
 Quirks kept: MLPLayer's guard `i != len(units_list) - 1` is always true, so EVERY layer — the last
-one producing the 2 class scores included — is Linear -> ReLU -> BatchNorm1D (net.py:133-152);
-with self_interaction=True the extra diagonal positions hold 0, not <e_i, e_i> (net.py:106-111).
+one producing the 2 class scores included — is Linear -> ReLU -> BatchNorm1D (net.py:134-151);
+with self_interaction=True the extra diagonal positions hold 0, not <e_i, e_i> (net.py:105-113).
 """
 from __future__ import annotations
 
@@ -68,10 +68,10 @@ class DLRMLayer(tnn.Module):
                                        init="truncated_normal", init_std=1.0, device=device)
 
     def forward(self, sparse_inputs, dense_inputs):
-        x = self.bot_mlp(dense_inputs)                                            # net.py:93
+        x = self.bot_mlp(dense_inputs)                                            # net.py:86
         ids = (torch.cat(list(sparse_inputs), dim=1) if isinstance(sparse_inputs, (list, tuple))
                else sparse_inputs)
-        emb = self.embedding(ids)                                                 # [B, 26, d]  :96-101
-        T = torch.cat([emb, x.unsqueeze(1)], dim=1)                               # :104-107
-        R = ops.dot_interact(T, self.self_interaction)                            # :110-123 (K6)
-        return self.top_mlp(R)                                                    # :125
+        emb = self.embedding(ids)                                                 # [B, 26, d]  :89-94
+        T = torch.cat([emb, x.unsqueeze(1)], dim=1)                               # :97-100
+        R = ops.dot_interact(T, self.self_interaction)                            # :103-115 (K6)
+        return self.top_mlp(R)                                                    # :117

@@ -85,7 +85,7 @@ def make_din(rng, n=77):
         cats = " ".join(str(rng.randint(1, 800)) for _ in range(k))
         lines.append("%s;%s;%d;%d;%d" % (hist, cats, rng.randint(1, 63000), rng.randint(1, 800),
                                         rng.randint(0, 1)))
-    lines.insert(9, "1 2 3;4 5 6;7")          # fewer than 5 fields: skipped (dinReader.py:64-65)
+    lines.insert(9, "1 2 3;4 5 6;7")          # fewer than 5 fields: skipped (dinReader.py:52-53)
     return "\n".join(lines) + "\n"
 
 

@@ -181,7 +181,7 @@ def test_din_packed_reader_type():
 
 
 def test_dcn_v2_reader_log_transform_and_native_schema():
-    """dcn_v2/reader.py:53-61: dense = log(v+1), `slot:` with an empty value is skipped — the Python
+    """dcn_v2/reader.py:55-64: dense = log(v+1), `slot:` with an empty value is skipped — the Python
     mirror and the native parser (dataio.CRITEO_DCN_V2) agree bit for bit."""
     from paddlerec_b200 import dataio
     from paddlerec_b200.rank.dcn_v2 import reader

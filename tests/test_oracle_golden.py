@@ -40,7 +40,7 @@ def test_din_attention_grads_present():
 
 
 def test_dlrm_self_interaction_diagonal_is_zero_not_the_self_dot():
-    """dlrm/net.py:106-111: triu(Z,1) zeroes the diagonal BEFORE the MIN_FLOAT mask is added, so with
+    """dlrm/net.py:105-113: triu(Z,1) zeroes the diagonal BEFORE the MIN_FLOAT mask is added, so with
     self_interaction=True the N extra positions are selected but hold 0 — the golden (minted from the
     reference's code) pins that; a "correct" <T_i,T_i> would change the prediction."""
     import torch
