@@ -429,3 +429,41 @@ def test_din_parse_edge_cases():
     a, b = dataio.parse_din(text, threads=1), dataio.parse_din(text, threads=8)
     assert all(np.array_equal(a[k], b[k]) for k in a if k != "n_skipped")
     assert a["offsets"][-1] == a["hist_items"].size == a["hist_cats"].size
+
+
+def test_pack_dataset_tool_and_packed_training_input(tmp_path):
+    """tools/pack_dataset.py: text -> .b2r once; the packed reader then yields the same batches as
+    the text reader, and runner.create_data_loader accepts `packed_format: packed`."""
+    import importlib.util
+
+    import torch
+
+    from paddlerec_b200 import runner
+
+    spec = importlib.util.spec_from_file_location("pack_dataset", os.path.join(ROOT, "tools", "pack_dataset.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    paths, _ = _write_files(tmp_path)
+    cache = tmp_path / "cache"
+    assert tool.main(["--out", str(cache)] + paths) == 700 + 1 + 333
+    packed = sorted(str(p) for p in cache.iterdir())
+    assert [os.path.basename(p) for p in packed] == ["part-0.txt.b2r", "part-1.txt.b2r", "part-2.txt.b2r"]
+    a = list(dataio.PackedBatchReader(paths, batch_size=64, prefetch=0))
+    b = list(dataio.PackedBatchReader(packed, batch_size=64, fmt="packed", prefetch=0))
+    assert len(a) == len(b) == (700 + 1 + 333) // 64
+    assert all(torch.equal(x, y) for p, q in zip(a, b) for x, y in zip(p, q))
+    # raw TSV (parser.cpp semantics: the two malformed lines of the sample are skipped)
+    tsv = tmp_path / "day_0"
+    tsv.write_bytes(_read("criteo_tsv_sample.tsv"))
+    assert tool.main(["--out", str(cache), "--format", "criteo_tsv", str(tsv)]) == 62
+    lab, ids, dense = dataio.read_packed(str(cache / "day_0.b2r"))
+    rl, rid, _ = _parser_cpp_output(_read("criteo_tsv_parser_cpp.txt"))
+    assert np.array_equal(ids, rid) and np.array_equal(lab[:, 0], rl)
+    with pytest.raises(dataio.B200RecIOError, match="fewer than 40 columns"):   # benchmark_reader raises
+        tool.main(["--out", str(cache), "--format", "criteo_tsv", "--hash", "xxh32", str(tsv)])
+    # through the runner: a data dir of .b2r files
+    cfg = {"runner.train_data_dir": str(cache), "runner.train_batch_size": 100, "config_abs_dir": "/",
+           "runner.reader_type": "PackedReader", "runner.packed_format": "packed"}
+    (cache / "day_0.b2r").unlink()
+    batches = list(runner.create_data_loader(cfg))
+    assert len(batches) == 10 and batches[0][1].shape == (100, 26)
