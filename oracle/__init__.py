@@ -26,6 +26,7 @@ Files
   paddle_shim.py  the stand-in used to run the reference's net.py here
   readers.py      the reference's text readers (slot:value, raw Criteo TSV, multislot) + the two
                   string hashes they use, pure Python
+  interact_ref.c  plain-C restatement of the DLRM dot interaction (fwd/bwd) and the feasign fold
   fm_ref.c        plain-C restatement of the fused FM forward/backward (double accumulation),
                   built by oracle/Makefile into oracle/_build/libfm_ref.so
 """
