@@ -422,6 +422,7 @@ class PackedBatchReader:
     world_size: int = 1
     shard_files: bool = False
     _files: List[str] = field(default_factory=list, init=False, repr=False)
+    _scratch_bufs: Optional[tuple] = field(default=None, init=False, repr=False)
 
     def __post_init__(self):
         files = sorted(self.file_list)
@@ -436,7 +437,7 @@ class PackedBatchReader:
     # -- parsing -----------------------------------------------------------------------------------
     def _scratch(self, n: int):
         """Grow-only parse buffers, reused across chunks (fresh arrays would page-fault every time)."""
-        cur = getattr(self, "_scratch_bufs", None)
+        cur = self._scratch_bufs
         if cur is None or cur[1].shape[0] < n:
             cap = max(n, int(1.25 * (cur[1].shape[0] if cur is not None else 0)))
             F, Dn = self.schema.n_sparse, (self.schema.dense_dim if self.schema.dense_slot else 0)
@@ -444,7 +445,7 @@ class PackedBatchReader:
                 F, Dn = 26, 13
             cur = (np.empty((cap, 1), np.int64), np.empty((cap, F), np.int64),
                    np.empty((cap, Dn), np.float32))
-            object.__setattr__(self, "_scratch_bufs", cur)
+            self._scratch_bufs = cur
         return cur
 
     def _parse(self, chunk):
