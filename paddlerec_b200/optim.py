@@ -58,6 +58,18 @@ class _Base:
         self._lr = learning_rate
         self._clip: Optional[ClipGradByGlobalNorm] = grad_clip
         self.step_count = 0
+        # set by sharded.DistributedOptimizer: sums the squared norm of the LOCAL table-shard
+        # gradients over the ranks (the dense gradients are already all-reduced, i.e. identical)
+        self.sparse_sq_reduce = None
+
+    #: Paddle's optimizer.step() never advances an LRScheduler and the reference loop
+    #: (tools/trainer.py:151-153) never calls scheduler.step(), so the reference DIN run stays at
+    #: values[0] forever.  Faithful default: do not step; set True for per-step decay.
+    lr_auto_step = False
+
+    def _maybe_step_lr(self) -> None:
+        if self.lr_auto_step and hasattr(self._lr, "step"):
+            self._lr.step()
 
     def get_lr(self) -> float:
         return float(self._lr()) if callable(self._lr) else float(self._lr)
@@ -71,15 +83,23 @@ class _Base:
     zero_grad = clear_grad
 
     def global_grad_norm(self) -> torch.Tensor:
-        sq = []
+        """sqrt(sum of squares over EVERY gradient) — ClipGradByGlobalNorm's norm
+        (models/rank/dcn_v2/dygraph_model.py:81-88).  With row-sharded tables each rank holds only
+        its shard's SelectedRows, so that part is summed over the ranks (one scalar all-reduce)
+        before the sqrt; every replica then applies the same scale."""
+        dev = (self._dense + self._sparse)[0].device
+        dense_sq = torch.zeros((), device=dev)
         for p in self._dense:
             if p.grad is not None:
-                sq.append(p.grad.float().square().sum())
+                dense_sq = dense_sq + p.grad.float().square().sum()
+        sparse_sq = torch.zeros((), device=dev)
         for p in self._sparse:
             sr = getattr(p, "grad_rows", None)
             if sr is not None:
-                sq.append(_valid_rows(sr).square().sum())
-        return torch.stack(sq).sum().sqrt()
+                sparse_sq = sparse_sq + _valid_rows(sr).square().sum()
+        if self.sparse_sq_reduce is not None:
+            sparse_sq = self.sparse_sq_reduce(sparse_sq)
+        return (dense_sq + sparse_sq).sqrt()
 
     def _apply_clip(self) -> None:
         if self._clip is None:
@@ -127,8 +147,7 @@ class SGD(_Base):
             if sr is not None:
                 ops.raw_sparse_sgd(p.data, sr, lr)
         self.step_count += 1
-        if hasattr(self._lr, "step"):
-            self._lr.step()
+        self._maybe_step_lr()
 
 
 class Adam(_Base):
@@ -176,8 +195,7 @@ class Adam(_Base):
             if sr is not None:
                 m, v = self.moments(p)
                 ops.raw_sparse_adam(p.data, m, v, sr, lr, self.beta1, self.beta2, self.eps, b1p, b2p)
-        if hasattr(self._lr, "step"):
-            self._lr.step()
+        self._maybe_step_lr()
 
 
 class SparseAdaGrad(_Base):

@@ -400,6 +400,16 @@ class DistributedOptimizer:
     def __init__(self, inner, model: tnn.Module, world: int, group=None):
         self.inner, self.world, self.group = inner, world, group
         self._dense = [p for p in dense_parameters(model) if p.requires_grad]
+        if world > 1 and hasattr(inner, "sparse_sq_reduce"):
+            # ClipGradByGlobalNorm (DCN-V2): the table gradients live on their owners, so the
+            # squared norm of that part is one scalar all-reduce; the dense part is identical on
+            # every rank after the bucket all-reduce below.
+            inner.sparse_sq_reduce = self._sum_over_ranks
+
+    def _sum_over_ranks(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.clone()
+        dist.all_reduce(t, group=self.group)
+        return t
 
     def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
         return loss / self.world

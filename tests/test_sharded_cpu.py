@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _full_problem():
+def _full_problem(B=B):
     g = torch.Generator().manual_seed(2468)
     p = {"fm.embedding.weight": torch.randn(V, D, generator=g) * 0.1,
          "fm.embedding_one.weight": torch.randn(V, 1, generator=g) * 0.1,
@@ -244,3 +244,72 @@ def test_sharded_dlrm_matches_per_rank_oracle(tmp_path):
     for rank in range(world):
         r = np.load(os.path.join(str(tmp_path), "dlrm%d.npz" % rank))
         np.testing.assert_allclose(r["dW"], dW[rank::world], rtol=2e-3, atol=1e-6)
+
+
+def _clip_worker(rank, world, port, out_dir):
+    """One SGD step with ClipGradByGlobalNorm under DistributedOptimizer on a row-sharded
+    Wide&Deep: the clip scale must come from the GLOBAL gradient norm (dense + every shard)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import ops, optim, sharded
+        from paddlerec_b200.rank.wide_deep import net
+        from tests.util import load_golden
+        ops.raw_sparse_sgd = cpu_kernels.raw_sparse_sgd
+        g = load_golden("wide_deep")
+        Vg, Dg = g["param"]["embedding.weight"].shape
+        fc = [g["param"]["linear_%d.weight" % i].shape[1] for i in range(2)]
+        model = net.WideDeepLayer(Vg, Dg, 13, 26, fc, device="cpu")
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(torch.tensor(g["param"][k], dtype=torch.float32))
+        sharded.shard_embeddings(model, rank, world, kernels=cpu_kernels)
+        ids = torch.tensor(g["in"]["ids"])
+        dense = torch.tensor(g["in"]["dense"], dtype=torch.float32)
+        label = torch.tensor(g["in"]["label"], dtype=torch.float32)
+        Bg = ids.shape[0] // world * world
+        per = Bg // world
+        sl = slice(rank * per, (rank + 1) * per)
+        inner = optim.SGD(0.5, model.parameters(), grad_clip=optim.ClipGradByGlobalNorm(CLIP))
+        opt = sharded.DistributedOptimizer(inner, model, world)
+        pred = model(ids[sl], dense[sl])
+        loss = BF.log_loss(pred, label[sl]).mean()
+        opt.scale_loss(loss).backward()
+        opt.step()
+        out = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+        np.savez(os.path.join(out_dir, "clip%d.npz" % rank), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+CLIP = 0.02
+
+
+def test_sharded_global_norm_clip_is_global(tmp_path):
+    """the clip scale under sharding must use the norm over ALL shards (one scalar
+    all-reduce), otherwise the replicated dense parameters diverge between ranks."""
+    from tests.util import load_golden, to_params, slots
+    world = 2
+    mp.spawn(_clip_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = load_golden("wide_deep")
+    p = to_params(g["param"])
+    ids = torch.tensor(g["in"]["ids"])
+    Bg = ids.shape[0] // world * world
+    dense = torch.tensor(g["in"]["dense"], dtype=torch.float64)[:Bg]
+    label = torch.tensor(g["in"]["label"], dtype=torch.float64)[:Bg]
+    pred = nets.wide_deep_forward(p, slots(ids[:Bg]), dense, 2)
+    nets.log_loss(pred, label).mean().backward()
+    norm = float(sum((v.grad ** 2).sum() for v in p.values() if v.grad is not None) ** 0.5)
+    assert norm > 2 * CLIP          # the clip is active, so a rank-local norm would show
+    scale = CLIP / max(norm, CLIP)
+    r = [np.load(os.path.join(str(tmp_path), "clip%d.npz" % k)) for k in range(world)]
+    for k, v in p.items():
+        want = (v.detach() - 0.5 * scale * v.grad).numpy()
+        if k == "embedding.weight":
+            for rank in range(world):
+                np.testing.assert_allclose(r[rank][k], want[rank::world], rtol=1e-5, atol=1e-7)
+        else:
+            np.testing.assert_array_equal(r[0][k], r[1][k])          # replicas stay identical
+            np.testing.assert_allclose(r[0][k], want, rtol=1e-5, atol=1e-7, err_msg=k)

@@ -9,7 +9,9 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import nets
-from tests.test_sharded_cpu import B, D, Dn, F, FC, V, _free_port, _full_problem, _NoStep
+from tests.test_sharded_cpu import D, Dn, F, FC, V, _free_port, _full_problem, _NoStep
+
+B = 48      # divisible by 2, 4 and 8 ranks
 
 pytestmark = pytest.mark.gpu
 
@@ -24,7 +26,7 @@ def _worker(rank, world, port, out_dir):
         from paddlerec_b200 import functional as BF
         from paddlerec_b200 import sharded
         dev = torch.device("cuda", rank)
-        p, ids, dense, label = _full_problem()
+        p, ids, dense, label = _full_problem(B)
         torch.manual_seed(100 + rank)
         model = sharded.ShardedDeepFMLayer(V, D, Dn, F, FC, rank, world, device=dev)
         with torch.no_grad():
@@ -49,12 +51,12 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_deepfm_nccl(world, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    p, ids, dense, label = _full_problem()
+    p, ids, dense, label = _full_problem(B)
     pp = {k: v.double().requires_grad_(True) for k, v in p.items()}
     ids_ok = ids.clone()
     ids_ok[ids_ok >= V] = 0
@@ -106,17 +108,31 @@ def _dcn_worker(rank, world, port, out_dir):
         pred = model(ids[sl].to(dev), dense[sl].to(dev))
         loss = BF.log_loss(pred, label[sl].to(dev)).sum() / Bg
         loss.backward()
-        np.savez(os.path.join(out_dir, "dcn%d.npz" % rank), pred=pred.detach().cpu().numpy(),
-                 dW=model.embedding.grad_rows.to_dense().cpu().numpy())
+        out = dict(pred=pred.detach().cpu().numpy(),
+                   dW=model.embedding.grad_rows.to_dense().cpu().numpy())
+        # one SGD step with ClipGradByGlobalNorm (models/rank/dcn_v2/dygraph_model.py:81-88): the
+        # norm spans the dense gradients AND every rank's table shard (one scalar all-reduce)
+        from paddlerec_b200 import optim
+        inner = optim.SGD(0.5, model.parameters(), grad_clip=optim.ClipGradByGlobalNorm(DCN_CLIP))
+        opt = sharded.DistributedOptimizer(inner, model, world)
+        # loss above is already sum/Bg = the global-batch mean share of this rank
+        opt.step()
+        for k, v in model.state_dict().items():
+            out["p:" + k] = v.detach().cpu().numpy()
+        np.savez(os.path.join(out_dir, "dcn%d.npz" % rank), **out)
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_dcn_v2_nccl(tmp_path):
-    """BASELINE config 3 in miniature: DCN-V2 with its table row-sharded over 2 GPUs."""
-    world = 2
+DCN_CLIP = 0.05
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_dcn_v2_nccl(world, tmp_path):
+    """BASELINE config 3 in miniature: DCN-V2 with its table row-sharded over `world` GPUs, forward
+    + gradients vs the oracle, then one clipped SGD step (global-norm clip across the shards)."""
     if torch.cuda.device_count() < world:
-        pytest.skip("needs 2 GPUs")
+        pytest.skip("needs %d GPUs" % world)
     from tests.util import load_golden, slots, to_params
     mp.spawn(_dcn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     g = load_golden("dcn_v2_v2_stacked")
@@ -135,3 +151,19 @@ def test_sharded_dcn_v2_nccl(tmp_path):
                                    rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(r["dW"], p["embedding.weight"].grad.numpy()[rank::world],
                                    rtol=1e-4, atol=1e-7)
+    norm = float(sum((v.grad ** 2).sum() for v in p.values() if v.grad is not None) ** 0.5)
+    assert norm > 2 * DCN_CLIP
+    scale = DCN_CLIP / max(norm, DCN_CLIP)
+    r = [np.load(os.path.join(str(tmp_path), "dcn%d.npz" % k)) for k in range(world)]
+    for k, v in p.items():
+        if v.grad is None:
+            continue
+        want = (v.detach() - 0.5 * scale * v.grad).numpy()
+        if k == "embedding.weight":
+            for rank in range(world):
+                np.testing.assert_allclose(r[rank]["p:" + k], want[rank::world], rtol=1e-4,
+                                           atol=1e-6)
+        else:
+            for rank in range(1, world):   # replicas must stay bit-identical
+                np.testing.assert_array_equal(r[0]["p:" + k], r[rank]["p:" + k])
+            np.testing.assert_allclose(r[0]["p:" + k], want, rtol=1e-4, atol=1e-6, err_msg=k)
