@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200REC_ABI_VERSION 2
+#define B200REC_ABI_VERSION 3
 
 #define B200REC_OK 0
 #define B200REC_ERR_INVALID (-1)   /* bad argument (shape, alignment, NULL) */
@@ -201,6 +201,54 @@ int b200rec_tower_relu_bwd_split(const float* dy, const void* act_bf16, void* dz
 int b200rec_tower_prep_weight(const float* W, void* W2r_bf16, void* W2c_bf16, void* Wlo_bf16,
                               int K, int N, void* stream);
 int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream);
+
+/* ---- tower GEMMs on the 5th-gen tensor cores (csrc/tc_gemm.cuh) ----------- */
+/* Hand-written tcgen05.mma / TMEM / TMA kernels that replace the library GEMMs of the dense tower
+ * (DNN.forward, models/rank/deepfm/net.py:169-174; dcn_v2/net.py:178-184; CrossNetV2
+ * dcn_v2/net.py:222-226) and of its backward (tools/trainer.py:151).  fp32 products are evaluated
+ * as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo on bf16 operands with fp32 accumulation ("bf16x3").
+ *
+ * "planes": a matrix X[R,C] is passed as bf16 [R, 2*ld] (void*), hi(X) in columns [0,C) and
+ * lo(X) = bf16(X - hi) in columns [ld, ld+C); ld >= C, ld % 8 == 0, base 16-byte aligned.
+ *
+ *   tc_split        planes(relu?(x + bias?)) of an fp32 matrix x[M,K] with row pitch ldx
+ *   tc_split_bwd    g = dy * (mask_hi > 0) (mask may be NULL) -> planes(g), dbias = colsum(g)
+ *   tc_prep_weight  W[K,N] -> planes(W) [K,2*ldn] and planes(W^T) [N,2*ldk] (either may be NULL)
+ *   tc_linear_fwd   y = a @ W + bias, optional ReLU; a = planes [M,2*lda], W^T planes; writes y as
+ *                   fp32 [M,ld_f32] and/or as planes [M,2*ldp] (the next layer's operand)
+ *   tc_cross_fwd    CrossNetV2 layer: out = x0 * (xl @ W + b) + xl  (x0, xl fp32 [M,C] pitch ld_x)
+ *   tc_linear_bwd_dx  dx = g @ W^T (g planes [M,2*ldg], W planes [K,2*ldn]); optional ReLU mask
+ *                   from the hi plane of the layer input (mask_planes [M,2*ld_mask]); dx as fp32
+ *                   and/or planes; dbias_prev[K] = colsum(masked dx) if not NULL (deterministic)
+ *   tc_linear_bwd_dw  dW[K,N] = a^T @ g, batch reduction split across CTAs, fixed-order reduce
+ * One workspace size covers bwd_dx and bwd_dw of a layer. */
+int b200rec_tc_split(const float* x, int64_t ldx, const float* bias, int relu, void* planes,
+                     int64_t ldp, int64_t M, int K, void* stream);
+int b200rec_tc_split_bwd(const float* dy, const void* mask_planes, int64_t ld_mask, void* g_planes,
+                         int64_t ldp, float* dbias, int64_t M, int N, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int b200rec_tc_prep_weight(const float* W, int K, int N, void* w_planes, int64_t ldn,
+                           void* wt_planes, int64_t ldk, void* stream);
+int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_planes, int64_t ldk,
+                          const float* bias, int relu, float* out_f32, int64_t ld_f32,
+                          void* out_planes, int64_t ldp, int64_t M, int N, int K, void* stream);
+int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
+                         const float* bias, const float* x0, const float* xl, int64_t ld_x,
+                         float* out_f32, int64_t ld_f32, void* out_planes, int64_t ldp, int64_t M,
+                         int C, void* stream);
+int b200rec_tc_linear_bwd_workspace_bytes(int64_t M, int K, int N, size_t* bytes_host);
+int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_planes, int64_t ldn,
+                             const void* mask_planes, int64_t ld_mask, float* dx_f32,
+                             int64_t ld_f32, void* dx_planes, int64_t ldp, float* dbias_prev,
+                             int64_t M, int K, int N, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int b200rec_tc_linear_bwd_dw(const void* a_planes, int64_t lda, const void* g_planes, int64_t ldg,
+                             float* dW, int64_t M, int K, int N, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel)
+ * and the device word a pipeline watchdog writes before it traps. */
+int b200rec_tc_debug(int key, int value);
+int b200rec_tc_timeout_word(unsigned int* word_host);
 
 /* Backward of b200rec_din_attn_fwd.  Inputs as forward plus the saved softmax `weights` and
  * dout [B,E].  Outputs: dhist [B,L,E]; dtseq [B,E] = the (h*t)-path part of d/dtseq; dtb [B,80] =

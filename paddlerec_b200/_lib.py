@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _P = c_void_p
 _SIG = {
     "b200rec_abi_version": (c_int, []),
@@ -107,6 +107,21 @@ _SIG = {
     "b200rec_tower_relu_bwd_split": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "b200rec_tower_prep_weight": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "b200rec_tower_fold_dw": (c_int, [_P, _P, c_int, c_int, _P]),
+    "b200rec_tc_split": (c_int, [_P, c_int64, _P, c_int, _P, c_int64, c_int64, c_int, _P]),
+    "b200rec_tc_split_bwd": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _P, c_size_t,
+                                     _P]),
+    "b200rec_tc_prep_weight": (c_int, [_P, c_int, c_int, _P, c_int64, _P, c_int64, _P]),
+    "b200rec_tc_linear_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, _P, c_int64, _P, c_int64,
+                                      c_int64, c_int, c_int, _P]),
+    "b200rec_tc_cross_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64, _P,
+                                     c_int64, c_int64, c_int, _P]),
+    "b200rec_tc_linear_bwd_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "b200rec_tc_linear_bwd_dx": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P,
+                                         c_int64, _P, c_int64, c_int, c_int, _P, c_size_t, _P]),
+    "b200rec_tc_linear_bwd_dw": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, _P,
+                                         c_size_t, _P]),
+    "b200rec_tc_debug": (c_int, [c_int, c_int]),
+    "b200rec_tc_timeout_word": (c_int, [POINTER(ctypes.c_uint)]),
     "b200rec_dot_interact_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
     "b200rec_dot_interact_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "b200rec_hash_keys": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),

@@ -11,6 +11,7 @@
 #include "cross.cuh"
 #include "shard.cuh"
 #include "tower.cuh"
+#include "tc_gemm.cuh"
 #include "cvm.cuh"
 #include "hash_keys.cuh"
 #include "dot_interact.cuh"
@@ -250,7 +251,7 @@ int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V,
 int b200rec_tower_split(const float* x, const float* bias, int relu, void* out_bf16, int64_t M,
                         int K, void* stream) {
   if (M > 0) { NOT_NULL(x); NOT_NULL(out_bf16); }
-  return launch_tower_split(x, bias, relu, out_bf16, M, K, ST(stream));
+  return launch_tower_split(x, K, bias, relu, out_bf16, K, M, K, ST(stream));
 }
 
 int b200rec_tower_bwd_workspace_bytes(int64_t M, int N, size_t* bytes_host) {
@@ -264,8 +265,139 @@ int b200rec_tower_relu_bwd_split(const float* dy, const void* act_bf16, void* dz
                                  size_t workspace_bytes, void* stream) {
   NOT_NULL(dbias);
   if (M > 0) { NOT_NULL(dy); NOT_NULL(dz_bf16); NOT_NULL(workspace); }
-  return launch_tower_relu_bwd_split(dy, act_bf16, dz_bf16, dbias, M, N, workspace,
+  return launch_tower_relu_bwd_split(dy, act_bf16, N, dz_bf16, N, dbias, M, N, workspace,
                                      workspace_bytes, ST(stream));
+}
+
+/* ---- tcgen05 tower GEMMs (csrc/tc_gemm.cuh) ------------------------------------------------ */
+int b200rec_tc_split(const float* x, int64_t ldx, const float* bias, int relu, void* planes,
+                     int64_t ldp, int64_t M, int K, void* stream) {
+  if (M > 0) { NOT_NULL(x); NOT_NULL(planes); }
+  return launch_tower_split(x, ldx, bias, relu, planes, ldp, M, K, ST(stream));
+}
+
+int b200rec_tc_split_bwd(const float* dy, const void* mask_planes, int64_t ld_mask, void* g_planes,
+                         int64_t ldp, float* dbias, int64_t M, int N, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  NOT_NULL(dbias);
+  if (M > 0) { NOT_NULL(dy); NOT_NULL(g_planes); NOT_NULL(workspace); }
+  return launch_tower_relu_bwd_split(dy, mask_planes, ld_mask, g_planes, ldp, dbias, M, N,
+                                     workspace, workspace_bytes, ST(stream));
+}
+
+int b200rec_tc_prep_weight(const float* W, int K, int N, void* w_planes, int64_t ldn,
+                           void* wt_planes, int64_t ldk, void* stream) {
+  B200_REQUIRE(K > 0 && N > 0, "tc_prep_weight: bad sizes");
+  NOT_NULL(W);
+  B200_REQUIRE(w_planes == nullptr || ldn >= N, "tc_prep_weight: ldn < N");
+  B200_REQUIRE(wt_planes == nullptr || ldk >= K, "tc_prep_weight: ldk < K");
+  dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+  tc::tc_prep_weight_kernel<<<grid, block, 0, ST(stream)>>>(
+      W, K, N, static_cast<__nv_bfloat16*>(w_planes), ldn, static_cast<__nv_bfloat16*>(wt_planes),
+      ldk);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_planes, int64_t ldk,
+                          const float* bias, int relu, float* out_f32, int64_t ld_f32,
+                          void* out_planes, int64_t ldp, int64_t M, int N, int K, void* stream) {
+  if (M > 0) { NOT_NULL(a_planes); NOT_NULL(wt_planes); }
+  B200_REQUIRE(out_f32 != nullptr || out_planes != nullptr, "tc_linear_fwd: no output");
+  B200_REQUIRE(out_f32 == nullptr || ld_f32 >= N, "tc_linear_fwd: ld_f32 < N");
+  B200_REQUIRE(out_planes == nullptr || ldp >= N, "tc_linear_fwd: ldp < N");
+  tc::Epilogue ep = {};
+  ep.bias = bias; ep.relu = relu;
+  ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+  ep.out_planes = static_cast<__nv_bfloat16*>(out_planes); ep.ldp = ldp;
+  return tc::launch_gemm_kmajor(a_planes, lda, wt_planes, ldk, M, N, K, ep, ST(stream));
+}
+
+int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
+                         const float* bias, const float* x0, const float* xl, int64_t ld_x,
+                         float* out_f32, int64_t ld_f32, void* out_planes, int64_t ldp, int64_t M,
+                         int C, void* stream) {
+  if (M > 0) { NOT_NULL(xl_planes); NOT_NULL(wt_planes); NOT_NULL(x0); NOT_NULL(xl); }
+  B200_REQUIRE(out_f32 != nullptr || out_planes != nullptr, "tc_cross_fwd: no output");
+  tc::Epilogue ep = {};
+  ep.bias = bias;
+  ep.cross_x0 = x0; ep.cross_xl = xl; ep.ld_cross = ld_x;
+  ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+  ep.out_planes = static_cast<__nv_bfloat16*>(out_planes); ep.ldp = ldp;
+  return tc::launch_gemm_kmajor(xl_planes, lda, wt_planes, ldk, M, C, C, ep, ST(stream));
+}
+
+int b200rec_tc_linear_bwd_workspace_bytes(int64_t M, int K, int N, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  B200_REQUIRE(M >= 0 && K > 0 && N > 0, "tc_linear_bwd_workspace_bytes: bad sizes");
+  const size_t colsum = (size_t)((M + tc::kBM - 1) / tc::kBM) * (size_t)K * sizeof(float);
+  const size_t dw = tc::plan_dw(M, K, N).ws_bytes;
+  *bytes_host = (colsum > dw ? colsum : dw) + 256;
+  return B200REC_OK;
+}
+
+int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_planes, int64_t ldn,
+                             const void* mask_planes, int64_t ld_mask, float* dx_f32,
+                             int64_t ld_f32, void* dx_planes, int64_t ldp, float* dbias_prev,
+                             int64_t M, int K, int N, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (M > 0) { NOT_NULL(g_planes); NOT_NULL(w_planes); }
+  B200_REQUIRE(dx_f32 != nullptr || dx_planes != nullptr, "tc_linear_bwd_dx: no output");
+  B200_REQUIRE(dx_f32 == nullptr || ld_f32 >= K, "tc_linear_bwd_dx: ld_f32 < K");
+  B200_REQUIRE(dx_planes == nullptr || ldp >= K, "tc_linear_bwd_dx: ldp < K");
+  tc::Epilogue ep = {};
+  ep.out_f32 = dx_f32; ep.ld_f32 = ld_f32;
+  ep.out_planes = static_cast<__nv_bfloat16*>(dx_planes); ep.ldp = ldp;
+  ep.mask_src = static_cast<const __nv_bfloat16*>(mask_planes); ep.ld_mask = 2 * ld_mask;
+  const int tiles_m = (int)((M + tc::kBM - 1) / tc::kBM);
+  if (dbias_prev != nullptr) {
+    const size_t need = (size_t)tiles_m * K * sizeof(float);
+    if (workspace_bytes < need || (M > 0 && workspace == nullptr)) {
+      set_error("tc_linear_bwd_dx: workspace %zu < %zu bytes", workspace_bytes, need);
+      return B200REC_ERR_WORKSPACE;
+    }
+    if (M == 0) {
+      B200_CUDA(cudaMemsetAsync(dbias_prev, 0, (size_t)K * sizeof(float), ST(stream)));
+      return B200REC_OK;
+    }
+    ep.colsum = static_cast<float*>(workspace);
+  }
+  // D[M,K] = G[M,N] . W[K,N]^T : the reduction runs over N, the output width is K
+  const int rc = tc::launch_gemm_kmajor(g_planes, ldg, w_planes, ldn, M, K, N, ep, ST(stream));
+  if (rc != B200REC_OK) return rc;
+  if (dbias_prev != nullptr && M > 0) {
+    dim3 block(32, 8);
+    tc::tc_colsum_reduce_kernel<<<(K + 31) / 32, block, 0, ST(stream)>>>(ep.colsum, tiles_m, K,
+                                                                         dbias_prev);
+    B200_LAUNCH_CHECK();
+  }
+  return B200REC_OK;
+}
+
+int b200rec_tc_linear_bwd_dw(const void* a_planes, int64_t lda, const void* g_planes, int64_t ldg,
+                             float* dW, int64_t M, int K, int N, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  NOT_NULL(dW);
+  if (M > 0) { NOT_NULL(a_planes); NOT_NULL(g_planes); }
+  return tc::launch_gemm_dw(a_planes, lda, g_planes, ldg, M, K, N, dW, workspace, workspace_bytes,
+                            ST(stream));
+}
+
+int b200rec_tc_debug(int key, int value) {
+  switch (key) {
+    case 0: tc::g_bn_override = value; break;
+    case 1: tc::g_dw_debug.lbo_a = (uint32_t)value; break;
+    case 2: tc::g_dw_debug.lbo_b = (uint32_t)value; break;
+    case 3: tc::g_dw_debug.sbo = (uint32_t)value; break;
+    default: set_error("tc_debug: unknown key %d", key); return B200REC_ERR_INVALID;
+  }
+  return B200REC_OK;
+}
+
+int b200rec_tc_timeout_word(unsigned int* word_host) {
+  NOT_NULL(word_host);
+  B200_CUDA(cudaMemcpyFromSymbol(word_host, tc::g_tc_timeout, sizeof(unsigned int)));
+  return B200REC_OK;
 }
 
 int b200rec_tower_prep_weight(const float* W, void* W2r_bf16, void* W2c_bf16, void* Wlo_bf16,

@@ -230,7 +230,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
       const int c = g * 4;
       if (c < n_valid) {
         if (ep.bias != nullptr) {
-          if (c + 4 <= n_valid && ((col0 + c) & 3) == 0) {
+          if (c + 4 <= n_valid && (reinterpret_cast<uintptr_t>(ep.bias + col0 + c) & 15u) == 0) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c));
             v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
           } else {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
 #pragma unroll
       for (int g = 0; g < 4; ++g) {   // groups of 8 columns = 16 bytes of bf16
         const int c = g * 8;
-        if (c + 8 <= n_valid && row_ok && ((ep.ld_mask | col0) & 7) == 0) {
+        if (c + 8 <= n_valid && row_ok && (reinterpret_cast<uintptr_t>(mrow + c) & 15u) == 0) {
           const uint4 q = __ldg(reinterpret_cast<const uint4*>(mrow + c));
           const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -284,7 +284,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
   if (row_ok) {
     if (ep.out_f32 != nullptr) {
       float* o = ep.out_f32 + row * ep.ld_f32 + col0;
-      const bool vec_ok = ((ep.ld_f32 | col0) & 3) == 0;
+      const bool vec_ok = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const int c = g * 4;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
     if (ep.out_planes != nullptr) {
       __nv_bfloat16* oh = ep.out_planes + row * 2 * ep.ldp + col0;
       __nv_bfloat16* ol = oh + ep.ldp;
-      const bool vec_ok = ((ep.ldp | col0) & 7) == 0;
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ol)) & 15u) == 0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int c = g * 8;
@@ -602,7 +602,7 @@ tc_gemm_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     const int krow = k0 + q * 32 + lane;
     const int n_tile = (N - n0) < BN ? (N - n0) : BN;
     float* out = partials + ((size_t)split * Kin + (size_t)krow) * N + n0;
-    const bool vec_ok = ((N | n0) & 3) == 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     if (nkb > 0) {
       mbar_wait(bar_tfull, 0, 0x700u);
       tc_fence_after();

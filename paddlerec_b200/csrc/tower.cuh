@@ -32,15 +32,15 @@ struct alignas(8) Bf16x4 {
 // out[m, k] = hi(f(x[m,k])), out[m, K+k] = lo(...), f = optional (+bias[k]) then optional ReLU.
 template <int VEC>
 __global__ void __launch_bounds__(kTowerThreads)
-tower_split_kernel(const float* __restrict__ x, const float* __restrict__ bias, int relu,
-                   __nv_bfloat16* __restrict__ out, int64_t M, int K) {
+tower_split_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ bias,
+                   int relu, __nv_bfloat16* __restrict__ out, int64_t ldp, int64_t M, int K) {
   const int chunks = K / VEC;
   const int64_t total = M * chunks;
   for (int64_t i = (int64_t)blockIdx.x * kTowerThreads + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * kTowerThreads) {
     const int64_t m = i / chunks;
     const int k = (int)(i - m * chunks) * VEC;
-    Vec<VEC> a = ld_row<VEC>(x + (size_t)m * K + k);
+    Vec<VEC> a = ld_row<VEC>(x + (size_t)m * ldx + k);
     if (bias != nullptr) {
       const Vec<VEC> b = ld_cached<VEC>(bias + k);
 #pragma unroll
@@ -50,16 +50,16 @@ tower_split_kernel(const float* __restrict__ x, const float* __restrict__ bias, 
 #pragma unroll
       for (int j = 0; j < VEC; ++j) a.v[j] = fmaxf(a.v[j], 0.f);
     }
-    __nv_bfloat16* row = out + (size_t)m * 2 * K;
+    __nv_bfloat16* row = out + (size_t)m * 2 * ldp;
     if (VEC == 4) {
       Bf16x4 hi, lo;
 #pragma unroll
       for (int j = 0; j < 4; ++j) split1(a.v[j], hi.v[j], lo.v[j]);
       *reinterpret_cast<Bf16x4*>(row + k) = hi;
-      *reinterpret_cast<Bf16x4*>(row + K + k) = lo;
+      *reinterpret_cast<Bf16x4*>(row + ldp + k) = lo;
     } else {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) split1(a.v[j], row[k + j], row[K + k + j]);
+      for (int j = 0; j < VEC; ++j) split1(a.v[j], row[k + j], row[ldp + k + j]);
     }
   }
 }
@@ -68,7 +68,7 @@ tower_split_kernel(const float* __restrict__ x, const float* __restrict__ bias, 
 // of dz per row-slice (thread owns its columns => register accumulation, fixed order).
 template <int VEC>
 __device__ __forceinline__ void relu_bwd_split_row(Vec<VEC>& g, const __nv_bfloat16* a,
-                                                   __nv_bfloat16* row, int N, int c) {
+                                                   __nv_bfloat16* row, int64_t N, int c) {
   if (a != nullptr) {
     if (VEC == 4) {
       const Bf16x4 h = *reinterpret_cast<const Bf16x4*>(a);
@@ -100,8 +100,8 @@ constexpr int kBwdUnroll = 4;
 template <int VEC>
 __global__ void __launch_bounds__(kTowerThreads)
 tower_relu_bwd_split_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ act,
-                            __nv_bfloat16* __restrict__ dz, float* __restrict__ partials,
-                            int64_t M, int N) {
+                            int64_t ld_act, __nv_bfloat16* __restrict__ dz, int64_t ldp,
+                            float* __restrict__ partials, int64_t M, int N) {
   const int chunks = N / VEC;
   const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = chunk * VEC;
@@ -118,16 +118,16 @@ tower_relu_bwd_split_kernel(const float* __restrict__ dy, const __nv_bfloat16* _
 #pragma unroll
       for (int u = 0; u < kBwdUnroll; ++u) {
         const int64_t mm = m + u * row_step;
-        relu_bwd_split_row<VEC>(g[u], act ? act + (size_t)mm * 2 * N + c : nullptr,
-                                dz + (size_t)mm * 2 * N, N, c);
+        relu_bwd_split_row<VEC>(g[u], act ? act + (size_t)mm * 2 * ld_act + c : nullptr,
+                                dz + (size_t)mm * 2 * ldp, ldp, c);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc.v[j] += g[u].v[j];
       }
     }
     for (; m < M; m += row_step) {
       Vec<VEC> g = ld_row<VEC>(dy + (size_t)m * N + c);
-      relu_bwd_split_row<VEC>(g, act ? act + (size_t)m * 2 * N + c : nullptr,
-                              dz + (size_t)m * 2 * N, N, c);
+      relu_bwd_split_row<VEC>(g, act ? act + (size_t)m * 2 * ld_act + c : nullptr,
+                              dz + (size_t)m * 2 * ldp, ldp, c);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) acc.v[j] += g.v[j];
     }
@@ -181,27 +181,29 @@ static int tower_row_slices(int64_t M) {
   return (int)min((int64_t)kTowerRowSlices, M > 0 ? M : (int64_t)1);
 }
 
-static int launch_tower_split(const float* x, const float* bias, int relu, void* out, int64_t M,
-                              int K, cudaStream_t st) {
-  B200_REQUIRE(K > 0 && M >= 0, "tower_split: bad sizes");
+static int launch_tower_split(const float* x, int64_t ldx, const float* bias, int relu, void* out,
+                              int64_t ldp, int64_t M, int K, cudaStream_t st) {
+  B200_REQUIRE(K > 0 && M >= 0 && ldx >= K && ldp >= K, "tower_split: bad sizes");
   if (M == 0) return B200REC_OK;
-  const bool v4 = (K % 4 == 0) && aligned16(x) && aligned8(out) && (!bias || aligned16(bias));
+  const bool v4 = (K % 4 == 0) && (ldx % 4 == 0) && (ldp % 4 == 0) && aligned16(x) &&
+                  aligned8(out) && (!bias || aligned16(bias));
   const int64_t total = M * (v4 ? K / 4 : K);
   const unsigned grid =
       (unsigned)min((total + kTowerThreads - 1) / kTowerThreads, (int64_t)sm_count() * 16);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (v4)
-    tower_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(x, bias, relu, o, M, K);
+    tower_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(x, ldx, bias, relu, o, ldp, M, K);
   else
-    tower_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(x, bias, relu, o, M, K);
+    tower_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(x, ldx, bias, relu, o, ldp, M, K);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }
 
-static int launch_tower_relu_bwd_split(const float* dy, const void* act, void* dz, float* dbias,
-                                       int64_t M, int N, void* ws, size_t ws_bytes,
-                                       cudaStream_t st) {
-  B200_REQUIRE(N > 0 && M >= 0, "tower_relu_bwd_split: bad sizes");
+static int launch_tower_relu_bwd_split(const float* dy, const void* act, int64_t ld_act, void* dz,
+                                       int64_t ldp, float* dbias, int64_t M, int N, void* ws,
+                                       size_t ws_bytes, cudaStream_t st) {
+  B200_REQUIRE(N > 0 && M >= 0 && ldp >= N && (!act || ld_act >= N),
+               "tower_relu_bwd_split: bad sizes");
   const int slices = tower_row_slices(M);
   const size_t need = (size_t)slices * N * sizeof(float);
   if (ws_bytes < need) {
@@ -212,8 +214,8 @@ static int launch_tower_relu_bwd_split(const float* dy, const void* act, void* d
     B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
     return B200REC_OK;
   }
-  const bool v4 = (N % 4 == 0) && aligned16(dy) && aligned8(dz) && (!act || aligned8(act)) &&
-                  aligned16(ws);
+  const bool v4 = (N % 4 == 0) && (ldp % 4 == 0) && (!act || ld_act % 4 == 0) && aligned16(dy) &&
+                  aligned8(dz) && (!act || aligned8(act)) && aligned16(ws);
   const int chunks = v4 ? N / 4 : N;
   // TX = column chunks per block (power of two <= 256), TY = rows per block
   int tx = 32;
@@ -225,9 +227,9 @@ static int launch_tower_relu_bwd_split(const float* dy, const void* act, void* d
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(act);
   __nv_bfloat16* z = static_cast<__nv_bfloat16*>(dz);
   if (v4)
-    tower_relu_bwd_split_kernel<4><<<grid, block, 0, st>>>(dy, a, z, partials, M, N);
+    tower_relu_bwd_split_kernel<4><<<grid, block, 0, st>>>(dy, a, ld_act, z, ldp, partials, M, N);
   else
-    tower_relu_bwd_split_kernel<1><<<grid, block, 0, st>>>(dy, a, z, partials, M, N);
+    tower_relu_bwd_split_kernel<1><<<grid, block, 0, st>>>(dy, a, ld_act, z, ldp, partials, M, N);
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<reduce_partials_grid(N), kRedThreads, 0, st>>>(partials, slices, N, dbias, N,
                                                                           nullptr);

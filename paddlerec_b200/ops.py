@@ -43,7 +43,9 @@ KERNELS_PER_CALL = {
     "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
     "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
-    "tower_prep_weight": 1, "tower_fold_dw": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
+    "tower_prep_weight": 1, "tower_fold_dw": 1, "tc_split": 1, "tc_split_bwd": 2,
+    "tc_prep_weight": 1, "tc_linear_fwd": 1, "tc_cross_fwd": 1, "tc_linear_bwd_dx": 1,
+    "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
 EVENTS = None
@@ -414,6 +416,148 @@ def raw_tower_fold_dw(Mx: torch.Tensor, K: int, N: int) -> torch.Tensor:
     check(lib.b200rec_tower_fold_dw(ptr(Mx), ptr(dW), K, N, _stream()), "tower_fold_dw")
     _count("tower_fold_dw")
     return dW
+
+
+# ---- tcgen05 tower GEMMs (csrc/tc_gemm.cuh) ---------------------------------------------------
+def plane_ld(n: int) -> int:
+    """Plane pitch of a logical width n: the hi and lo planes must both be 16-byte aligned."""
+    return (int(n) + 7) // 8 * 8
+
+
+def _planes(M: int, n: int, device) -> torch.Tensor:
+    return torch.empty(M, 2 * plane_ld(n), dtype=torch.bfloat16, device=device)
+
+
+def raw_tc_split(x: torch.Tensor, bias=None, relu: bool = False) -> torch.Tensor:
+    """fp32 [M,K] -> planes [M, 2*ld(K)] of relu?(x + bias?)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    M, K = x.shape
+    out = _planes(M, K, x.device)
+    check(lib.b200rec_tc_split(ptr(x), K, ptr(bias), int(relu), ptr(out), plane_ld(K), M, K,
+                               _stream()), "tc_split")
+    _count("tc_split")
+    return out
+
+
+def raw_tc_split_bwd(dy: torch.Tensor, mask_planes):
+    """g = dy * (mask_hi > 0) -> (planes(g) [M, 2*ld(N)], dbias [N])."""
+    lib = _lib.load()
+    dy = _req(dy, torch.float32, "dy")
+    M, N = dy.shape
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_tower_bwd_workspace_bytes(M, N, ctypes.byref(nbytes)), "tower_ws")
+    ws = workspace(nbytes.value, dy.device, "tower")
+    g = _planes(M, N, dy.device)
+    dbias = torch.empty(N, dtype=torch.float32, device=dy.device)
+    ld_mask = mask_planes.shape[1] // 2 if mask_planes is not None else 0
+    check(lib.b200rec_tc_split_bwd(ptr(dy), ptr(mask_planes), ld_mask, ptr(g), plane_ld(N),
+                                   ptr(dbias), M, N, ptr(ws), ws.numel(), _stream()),
+          "tc_split_bwd")
+    _count("tc_split_bwd")
+    return g, dbias
+
+
+def raw_tc_prep_weight(W: torch.Tensor, want_w: bool = True, want_wt: bool = True):
+    """W fp32 [K,N] -> (planes(W) [K, 2*ld(N)], planes(W^T) [N, 2*ld(K)])."""
+    lib = _lib.load()
+    W = _req(W, torch.float32, "W")
+    K, N = W.shape
+    Wp = _planes(K, N, W.device) if want_w else None
+    WTp = _planes(N, K, W.device) if want_wt else None
+    check(lib.b200rec_tc_prep_weight(ptr(W), K, N, ptr(Wp), plane_ld(N), ptr(WTp), plane_ld(K),
+                                     _stream()), "tc_prep_weight")
+    _count("tc_prep_weight")
+    return Wp, WTp
+
+
+def raw_tc_linear_fwd(a_planes: torch.Tensor, K: int, WTp: torch.Tensor, N: int, bias, relu: bool,
+                      want_f32: bool, want_planes: bool):
+    """y = a @ W + bias (ReLU optional) on the tcgen05 tensor cores.  Returns (y fp32 [M,N] | None,
+    planes(y) [M, 2*ld(N)] | None)."""
+    lib = _lib.load()
+    M = a_planes.shape[0]
+    dev = a_planes.device
+    y = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+    yp = _planes(M, N, dev) if want_planes else None
+    check(lib.b200rec_tc_linear_fwd(ptr(a_planes), a_planes.shape[1] // 2, ptr(WTp),
+                                    WTp.shape[1] // 2, ptr(bias), int(relu), ptr(y), N, ptr(yp),
+                                    plane_ld(N), M, N, K, _stream()), "tc_linear_fwd")
+    _count("tc_linear_fwd")
+    return y, yp
+
+
+def raw_tc_cross_fwd(xl_planes, WTp, bias, x0, xl, want_planes: bool):
+    """CrossNetV2 layer out = x0 * (xl @ W + b) + xl with the Hadamard/residual epilogue fused into
+    the tcgen05 GEMM.  Returns (out fp32 [M,C], planes(out) | None)."""
+    lib = _lib.load()
+    x0 = _req(x0, torch.float32, "x0")
+    xl = _req(xl, torch.float32, "xl")
+    M, C = x0.shape
+    out = torch.empty(M, C, dtype=torch.float32, device=x0.device)
+    op = _planes(M, C, x0.device) if want_planes else None
+    check(lib.b200rec_tc_cross_fwd(ptr(xl_planes), xl_planes.shape[1] // 2, ptr(WTp),
+                                   WTp.shape[1] // 2, ptr(bias), ptr(x0), ptr(xl), C, ptr(out), C,
+                                   ptr(op), plane_ld(C), M, C, _stream()), "tc_cross_fwd")
+    _count("tc_cross_fwd")
+    return out, op
+
+
+def _tc_bwd_ws(M: int, K: int, N: int, device) -> torch.Tensor:
+    nbytes = ctypes.c_size_t(0)
+    lib = _lib.load()
+    check(lib.b200rec_tc_linear_bwd_workspace_bytes(M, K, N, ctypes.byref(nbytes)),
+          "tc_linear_bwd_ws")
+    return workspace(nbytes.value, device, "tc_bwd")
+
+
+def raw_tc_linear_bwd_dx(g_planes, N: int, Wp, K: int, mask_planes, want_f32: bool,
+                         want_planes: bool, want_dbias: bool):
+    """dx = g @ W^T with the ReLU mask of the layer input, the hi/lo split and the bias column-sum
+    of the PREVIOUS layer fused into the epilogue.  Returns (dx fp32 | None, planes | None,
+    dbias_prev [K] | None)."""
+    lib = _lib.load()
+    M = g_planes.shape[0]
+    dev = g_planes.device
+    dx = torch.empty(M, K, dtype=torch.float32, device=dev) if want_f32 else None
+    dxp = _planes(M, K, dev) if want_planes else None
+    db = torch.empty(K, dtype=torch.float32, device=dev) if want_dbias else None
+    ws = _tc_bwd_ws(M, K, N, dev)
+    ld_mask = mask_planes.shape[1] // 2 if mask_planes is not None else 0
+    check(lib.b200rec_tc_linear_bwd_dx(ptr(g_planes), g_planes.shape[1] // 2, ptr(Wp),
+                                       Wp.shape[1] // 2, ptr(mask_planes), ld_mask, ptr(dx), K,
+                                       ptr(dxp), plane_ld(K), ptr(db), M, K, N, ptr(ws), ws.numel(),
+                                       _stream()), "tc_linear_bwd_dx")
+    _count("tc_linear_bwd_dx_db" if want_dbias else "tc_linear_bwd_dx")
+    return dx, dxp, db
+
+
+def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int) -> torch.Tensor:
+    """dW [K,N] = a^T @ g (batch-split tcgen05 GEMM + fixed-order reduce)."""
+    lib = _lib.load()
+    M = a_planes.shape[0]
+    dev = a_planes.device
+    dW = torch.empty(K, N, dtype=torch.float32, device=dev)
+    ws = _tc_bwd_ws(M, K, N, dev)
+    check(lib.b200rec_tc_linear_bwd_dw(ptr(a_planes), a_planes.shape[1] // 2, ptr(g_planes),
+                                       g_planes.shape[1] // 2, ptr(dW), M, K, N, ptr(ws),
+                                       ws.numel(), _stream()), "tc_linear_bwd_dw")
+    _count("tc_linear_bwd_dw")
+    return dW
+
+
+def tc_debug(key: int, value: int) -> None:
+    """Bring-up / tuning knobs of the tcgen05 GEMMs (0: force tile width BN; 0 = automatic)."""
+    lib = _lib.load()
+    check(lib.b200rec_tc_debug(key, value), "tc_debug")
+
+
+def tc_timeout_word() -> int:
+    """Non-zero if a pipeline watchdog of the tcgen05 kernels fired (which wait, see tc_gemm.cuh)."""
+    lib = _lib.load()
+    w = ctypes.c_uint(0)
+    check(lib.b200rec_tc_timeout_word(ctypes.byref(w)), "tc_timeout_word")
+    return int(w.value)
 
 
 # ------------------------------------------------------------------------------------------------

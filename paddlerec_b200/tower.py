@@ -13,9 +13,18 @@ consumes), never as fp32.
     backward, layer i:  dz = split(dy * mask), db = colsum(dz)                 1 kernel
                         dW = fold([a_hi|a_lo]^T @ [dz_hi|dz_lo])               1 GEMM + 1 kernel
                         dx = [dz_hi|dz_lo] @ [W_hi|W_hi]^T (+)= dz_hi @ W_lo^T   2 GEMMs
+
+Two back ends with the same arithmetic (three bf16 products per fp32 product, fp32 accumulation):
+  'tcgen05' (default)  hand-written tcgen05.mma / TMEM / TMA GEMMs (csrc/tc_gemm.cuh) whose
+                       epilogues apply bias + ReLU and emit the NEXT layer's hi/lo operand directly
+                       (forward), or the ReLU mask + split + bias column-sum (backward); dW is a
+                       batch-split GEMM on MN-major operands.  No elementwise kernel runs between
+                       two GEMMs of the tower.
+  'cublas'             round-1 path, kept for head-to-head timing (B200REC_TOWER=cublas).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
 import torch
@@ -23,6 +32,63 @@ import torch
 from . import ops
 
 F32 = torch.float32
+BACKEND = os.environ.get("B200REC_TOWER", "tcgen05")
+
+
+def set_backend(name: str) -> None:
+    global BACKEND
+    if name not in ("tcgen05", "cublas"):
+        raise ValueError("tower backend must be tcgen05 or cublas")
+    BACKEND = name
+
+
+class _TowerTcFn(torch.autograd.Function):
+    """The whole Linear/ReLU chain on the tcgen05 kernels.  Saved for backward: the split
+    activations of every layer (they are the dW operands and the ReLU masks) and planes(W)."""
+
+    @staticmethod
+    def forward(ctx, x, n_layers, last_act, *params):
+        Ws, bs = params[:n_layers], params[n_layers:]
+        a = ops.raw_tc_split(x)
+        acts, wps = [a], []
+        y = None
+        for i in range(n_layers):
+            K, N = Ws[i].shape
+            Wp, WTp = ops.raw_tc_prep_weight(Ws[i])
+            wps.append(Wp)
+            last = i == n_layers - 1
+            relu = (not last) or last_act
+            y, a = ops.raw_tc_linear_fwd(a, K, WTp, N, bs[i], relu, want_f32=last,
+                                         want_planes=(not last) or last_act)
+            if a is not None:
+                acts.append(a)
+        ctx.n_layers, ctx.last_act = n_layers, last_act
+        ctx.acts, ctx.wps = acts, wps
+        ctx.shapes = [tuple(W.shape) for W in Ws]
+        ctx.has_bias = [b is not None for b in bs]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n = ctx.n_layers
+        acts, wps = ctx.acts, ctx.wps
+        dWs, dbs = [None] * n, [None] * n
+        g, db = ops.raw_tc_split_bwd(dy.contiguous(), acts[n] if ctx.last_act else None)
+        dx0 = None
+        for i in range(n - 1, -1, -1):
+            K, N = ctx.shapes[i]
+            dWs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N)
+            dbs[i] = db if ctx.has_bias[i] else None
+            if i > 0:
+                # dx of layer i is masked by layer i's input (= ReLU output of layer i-1), split,
+                # and its column sums are layer i-1's bias gradient: all in the GEMM epilogue
+                _, g, db = ops.raw_tc_linear_bwd_dx(g, N, wps[i], K, acts[i], want_f32=False,
+                                                    want_planes=True, want_dbias=True)
+            elif ctx.needs_input_grad[0]:
+                dx0, _, _ = ops.raw_tc_linear_bwd_dx(g, N, wps[i], K, None, want_f32=True,
+                                                     want_planes=False, want_dbias=False)
+        ctx.acts = ctx.wps = None
+        return (dx0, None, None, *dWs, *dbs)
 
 
 class _TowerFn(torch.autograd.Function):
@@ -85,6 +151,6 @@ def mlp(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch
         last_act: bool = False) -> torch.Tensor:
     """relu(...relu(x@W0+b0)...)@W_last+b_last  (ReLU after the last layer iff last_act)."""
     lead = x.shape[:-1]
-    y = _TowerFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), len(weights), last_act, *weights,
-                       *biases)
+    fn = _TowerTcFn if BACKEND == "tcgen05" else _TowerFn
+    y = fn.apply(x.reshape(-1, x.shape[-1]).contiguous(), len(weights), last_act, *weights, *biases)
     return y.reshape(*lead, y.shape[-1])

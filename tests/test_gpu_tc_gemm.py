@@ -1,0 +1,177 @@
+"""tcgen05 / TMEM / TMA tower GEMMs (csrc/tc_gemm.cuh) through the C ABI vs an fp64 product of the
+same fp32 operands.  Split precision (bf16x3) drops only the lo*lo term and the residual of the
+residual: ~2^-17 per product, so 5e-5 of the output's max-norm is a tight bar (TF32 would be 5e-4).
+Edge cases: M, N, K not multiples of the tile (128 x BN x 64), N = 1, K = 1, forced narrow tiles,
+every epilogue (bias, ReLU, planes / fp32 / both, ReLU mask + bias column-sum, CrossNet)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from paddlerec_b200 import ops
+    return ops
+
+
+def _join(planes, n):
+    """planes [R, 2*ld] -> fp64 hi + lo of the logical [R, n] matrix."""
+    ld = planes.shape[1] // 2
+    p = planes.double()
+    return p[:, :n] + p[:, ld:ld + n]
+
+
+def _err(got, want):
+    return float((got.double().cpu() - want.cpu()).abs().max() / (want.abs().max() + 1e-30))
+
+
+SHAPES = [(257, 400, 624), (128, 400, 400), (300, 1, 400), (1000, 208, 64), (129, 16, 8),
+          (4096, 624, 400), (513, 40, 1560), (64, 400, 1)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("relu", [False, True])
+def test_tc_linear_fwd(M, N, K, relu):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    want = x.double() @ W.double() + b.double()
+    if relu:
+        want = want.clamp_min(0)
+    a = ops.raw_tc_split(x.to(DEV))
+    assert _err(_join(a, K), x.double()) < 2e-5           # the split itself
+    Wp, WTp = ops.raw_tc_prep_weight(W.to(DEV))
+    assert _err(_join(Wp, N), W.double()) < 2e-5
+    assert _err(_join(WTp, K), W.double().t()) < 2e-5
+    y, yp = ops.raw_tc_linear_fwd(a, K, WTp, N, b.to(DEV), relu, True, True)
+    torch.cuda.synchronize()
+    assert _err(y, want) < 5e-5
+    assert _err(_join(yp, N), want) < 5e-5
+    # no bias, planes only
+    y2, yp2 = ops.raw_tc_linear_fwd(a, K, WTp, N, None, relu, False, True)
+    want2 = x.double() @ W.double()
+    if relu:
+        want2 = want2.clamp_min(0)
+    assert y2 is None and _err(_join(yp2, N), want2) < 5e-5
+
+
+@pytest.mark.parametrize("bn", [16, 64, 128, 256])
+def test_tc_linear_fwd_tile_widths(bn):
+    ops = _ops()
+    g = torch.Generator().manual_seed(bn)
+    M, N, K = 700, 400, 624
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g) / K ** 0.5
+    a = ops.raw_tc_split(x.to(DEV))
+    _, WTp = ops.raw_tc_prep_weight(W.to(DEV))
+    ops.tc_debug(0, bn)
+    try:
+        y, _ = ops.raw_tc_linear_fwd(a, K, WTp, N, None, False, True, False)
+        torch.cuda.synchronize()
+    finally:
+        ops.tc_debug(0, 0)
+    assert _err(y, x.double() @ W.double()) < 5e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(257, 624, 400), (1000, 400, 400), (300, 400, 1), (4096, 400, 624),
+                                   (130, 9, 33)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_tc_linear_bwd_dx(M, K, N, masked):
+    """dx = g @ W^T; masked: by the hi plane of the layer input, + column sums (bias gradient)."""
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(M + K + N)
+    gy = torch.randn(M, N, generator=g_)
+    W = torch.randn(K, N, generator=g_) / N ** 0.5
+    act = torch.randn(M, K, generator=g_).clamp_min(0)     # a ReLU output: ~half zeros
+    gp, db_top = ops.raw_tc_split_bwd(gy.to(DEV), None)
+    assert _err(db_top, gy.double().sum(0)) < 1e-5
+    Wp, _ = ops.raw_tc_prep_weight(W.to(DEV))
+    ap = ops.raw_tc_split(act.to(DEV))
+    want = gy.double() @ W.double().t()
+    if masked:
+        want = want * (act.double() > 0)
+        dx, dxp, db = ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, ap, True, True, True)
+        torch.cuda.synchronize()
+        assert _err(db, want.sum(0)) < 5e-5
+        assert _err(_join(dxp, K), want) < 5e-5
+    else:
+        dx, dxp, db = ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, None, True, False, False)
+        torch.cuda.synchronize()
+        assert dxp is None and db is None
+    assert _err(dx, want) < 5e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(257, 624, 400), (4096, 400, 400), (1000, 400, 1), (8192, 624, 400),
+                                   (33, 9, 33), (70000, 128, 64)])
+def test_tc_linear_bwd_dw(M, K, N):
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(M + 2 * K + N)
+    a = torch.randn(M, K, generator=g_)
+    gy = torch.randn(M, N, generator=g_)
+    ap = ops.raw_tc_split(a.to(DEV))
+    gp, _ = ops.raw_tc_split_bwd(gy.to(DEV), None)
+    dW = ops.raw_tc_linear_bwd_dw(ap, K, gp, N)
+    torch.cuda.synchronize()
+    assert _err(dW, a.double().t() @ gy.double()) < 5e-5
+    dW2 = ops.raw_tc_linear_bwd_dw(ap, K, gp, N)      # deterministic: fixed-order reduce
+    assert torch.equal(dW, dW2)
+
+
+def test_tc_cross_fwd():
+    """CrossNetV2 layer (dcn_v2/net.py:222-226): x0 * (xl @ W + b) + xl in the GEMM epilogue."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, C = 777, 1560
+    x0 = torch.randn(M, C, generator=g)
+    xl = torch.randn(M, C, generator=g)
+    W = torch.randn(C, C, generator=g) / C ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    xlp = ops.raw_tc_split(xl.to(DEV))
+    _, WTp = ops.raw_tc_prep_weight(W.to(DEV), want_w=False)
+    out, outp = ops.raw_tc_cross_fwd(xlp, WTp, b.to(DEV), x0.to(DEV), xl.to(DEV), True)
+    torch.cuda.synchronize()
+    want = x0.double() * (xl.double() @ W.double() + b.double()) + xl.double()
+    assert _err(out, want) < 5e-5
+    assert _err(_join(outp, C), want) < 5e-5
+
+
+@pytest.mark.parametrize("last_act", [False, True])
+@pytest.mark.parametrize("backend", ["tcgen05", "cublas"])
+def test_tower_backends_match_fp64(backend, last_act):
+    """The whole tower (forward + every gradient) on both back ends, headline shape."""
+    from paddlerec_b200 import tower
+    from tests.util import rel_err
+    g = torch.Generator().manual_seed(11)
+    M, sizes = 1000, [624, 400, 400, 400, 1]
+    L = len(sizes) - 1
+    x = torch.randn(M, sizes[0], generator=g)
+    Ws = [torch.randn(sizes[i], sizes[i + 1], generator=g) / sizes[i] ** 0.5 for i in range(L)]
+    bs = [torch.randn(sizes[i + 1], generator=g) * 0.1 for i in range(L)]
+    xd = x.double().requires_grad_(True)
+    Wd = [w.double().requires_grad_(True) for w in Ws]
+    bd = [b.double().requires_grad_(True) for b in bs]
+    h = xd
+    for i in range(L):
+        h = h @ Wd[i] + bd[i]
+        if i < L - 1 or last_act:
+            h = torch.relu(h)
+    gy = torch.randn(M, 1, generator=g)
+    (h * gy.double()).sum().backward()
+    xc = x.to(DEV).requires_grad_(True)
+    Wc = [w.to(DEV).requires_grad_(True) for w in Ws]
+    bc = [b.to(DEV).requires_grad_(True) for b in bs]
+    prev = tower.BACKEND
+    tower.set_backend(backend)
+    try:
+        y = tower.mlp(xc, Wc, bc, last_act=last_act)
+        (y * gy.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        tower.set_backend(prev)
+    assert rel_err(y, h) < 1e-4
+    assert rel_err(xc.grad, xd.grad) < 1e-4
+    for a, b in zip(Wc + bc, Wd + bd):
+        assert rel_err(a.grad, b.grad) < 1e-4
