@@ -221,9 +221,12 @@ int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream
  *                   from the hi plane of the layer input (mask_planes [M,2*ld_mask]); dx as fp32
  *                   and/or planes; dbias_prev[K] = colsum(masked dx) if not NULL (deterministic)
  *   tc_linear_bwd_dw  dW[K,N] = a^T @ g, batch reduction split across CTAs, fixed-order reduce
+ * ones_col (tc_split, tc_linear_fwd): additionally store 1.0 in column C of the emitted planes
+ * (needs ld > C).  Passing K+1 as the width of such an operand to tc_linear_bwd_dw makes row K of
+ * its output the column sum of g, i.e. the layer's bias gradient, at no extra cost.
  * One workspace size covers bwd_dx and bwd_dw of a layer. */
 int b200rec_tc_split(const float* x, int64_t ldx, const float* bias, int relu, void* planes,
-                     int64_t ldp, int64_t M, int K, void* stream);
+                     int64_t ldp, int64_t M, int K, int ones_col, void* stream);
 int b200rec_tc_split_bwd(const float* dy, const void* mask_planes, int64_t ld_mask, void* g_planes,
                          int64_t ldp, float* dbias, int64_t M, int N, void* workspace,
                          size_t workspace_bytes, void* stream);
@@ -231,7 +234,8 @@ int b200rec_tc_prep_weight(const float* W, int K, int N, void* w_planes, int64_t
                            void* wt_planes, int64_t ldk, void* stream);
 int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                           const float* bias, int relu, float* out_f32, int64_t ld_f32,
-                          void* out_planes, int64_t ldp, int64_t M, int N, int K, void* stream);
+                          void* out_planes, int64_t ldp, int ones_col, int64_t M, int N, int K,
+                          void* stream);
 int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                          const float* bias, const float* x0, const float* xl, int64_t ld_x,
                          float* out_f32, int64_t ld_f32, void* out_planes, int64_t ldp, int64_t M,
@@ -245,7 +249,8 @@ int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_pl
 int b200rec_tc_linear_bwd_dw(const void* a_planes, int64_t lda, const void* g_planes, int64_t ldg,
                              float* dW, int64_t M, int K, int N, void* workspace,
                              size_t workspace_bytes, void* stream);
-/* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel)
+/* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel;
+ * 4: k-block of the K-major kernel, 64 = 128-byte swizzle, 32 = 64-byte swizzle, more stages)
  * and the device word a pipeline watchdog writes before it traps. */
 int b200rec_tc_debug(int key, int value);
 int b200rec_tc_timeout_word(unsigned int* word_host);

@@ -133,6 +133,23 @@ def dcn_v2_forward(p: Params, sparse_inputs, dense_inputs, *, n_fc: int, cross_n
 
 
 # ------------------------------------------------------------------------------------------- DIN
+def din_attention_unit(hist, tseq, mask, W1, b1, W2, b2, W3, b3):
+    """The attention unit alone — models/rank/din/net.py:155-173: concat [h, t, h-t, h*t], the
+    512->80->40->1 sigmoid MLP, mask added BEFORE the E^-0.5 scaling (Q7), softmax over the
+    history, weighted sum.  hist [B,L,E], tseq [B,E] (the target tiled over L by the reader,
+    dinReader.py:85-90), mask [B,L,1] in {0,-1e9} or None.  Checker for the fused K4 kernels."""
+    E = hist.shape[2]
+    t = tseq.unsqueeze(1).expand_as(hist)
+    concat = torch.cat([hist, t, hist - t, hist * t], dim=2)                      # :155-161
+    x = torch.sigmoid(linear(concat, W1, b1))                                     # :163-164
+    x = torch.sigmoid(linear(x, W2, b2))
+    x = linear(x, W3, b3)
+    if mask is not None:
+        x = x + mask.reshape(x.shape).to(x.dtype)                                 # :166
+    weight = torch.softmax(x.transpose(1, 2) * (E ** -0.5), dim=-1)               # :167-169
+    return torch.matmul(weight, hist).reshape(-1, E)                              # :171-173
+
+
 def din_forward(p: Params, hist_item_seq, hist_cat_seq, target_item, target_cat, label, mask,
                 target_item_seq, target_cat_seq):
     """DINLayer.forward — models/rank/din/net.py:139-184.  `att.*` are the attention-unit linears

@@ -251,7 +251,7 @@ int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V,
 int b200rec_tower_split(const float* x, const float* bias, int relu, void* out_bf16, int64_t M,
                         int K, void* stream) {
   if (M > 0) { NOT_NULL(x); NOT_NULL(out_bf16); }
-  return launch_tower_split(x, K, bias, relu, out_bf16, K, M, K, ST(stream));
+  return launch_tower_split(x, K, bias, relu, out_bf16, K, M, K, 0, ST(stream));
 }
 
 int b200rec_tower_bwd_workspace_bytes(int64_t M, int N, size_t* bytes_host) {
@@ -271,9 +271,9 @@ int b200rec_tower_relu_bwd_split(const float* dy, const void* act_bf16, void* dz
 
 /* ---- tcgen05 tower GEMMs (csrc/tc_gemm.cuh) ------------------------------------------------ */
 int b200rec_tc_split(const float* x, int64_t ldx, const float* bias, int relu, void* planes,
-                     int64_t ldp, int64_t M, int K, void* stream) {
+                     int64_t ldp, int64_t M, int K, int ones_col, void* stream) {
   if (M > 0) { NOT_NULL(x); NOT_NULL(planes); }
-  return launch_tower_split(x, ldx, bias, relu, planes, ldp, M, K, ST(stream));
+  return launch_tower_split(x, ldx, bias, relu, planes, ldp, M, K, ones_col, ST(stream));
 }
 
 int b200rec_tc_split_bwd(const float* dy, const void* mask_planes, int64_t ld_mask, void* g_planes,
@@ -301,13 +301,14 @@ int b200rec_tc_prep_weight(const float* W, int K, int N, void* w_planes, int64_t
 
 int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                           const float* bias, int relu, float* out_f32, int64_t ld_f32,
-                          void* out_planes, int64_t ldp, int64_t M, int N, int K, void* stream) {
+                          void* out_planes, int64_t ldp, int ones_col, int64_t M, int N, int K,
+                          void* stream) {
   if (M > 0) { NOT_NULL(a_planes); NOT_NULL(wt_planes); }
   B200_REQUIRE(out_f32 != nullptr || out_planes != nullptr, "tc_linear_fwd: no output");
   B200_REQUIRE(out_f32 == nullptr || ld_f32 >= N, "tc_linear_fwd: ld_f32 < N");
-  B200_REQUIRE(out_planes == nullptr || ldp >= N, "tc_linear_fwd: ldp < N");
+  B200_REQUIRE(out_planes == nullptr || ldp >= N + (ones_col ? 1 : 0), "tc_linear_fwd: ldp < N");
   tc::Epilogue ep = {};
-  ep.bias = bias; ep.relu = relu;
+  ep.bias = bias; ep.relu = relu; ep.ones_col = ones_col;
   ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
   ep.out_planes = static_cast<__nv_bfloat16*>(out_planes); ep.ldp = ldp;
   return tc::launch_gemm_kmajor(a_planes, lda, wt_planes, ldk, M, N, K, ep, ST(stream));
@@ -389,6 +390,7 @@ int b200rec_tc_debug(int key, int value) {
     case 1: tc::g_dw_debug.lbo_a = (uint32_t)value; break;
     case 2: tc::g_dw_debug.lbo_b = (uint32_t)value; break;
     case 3: tc::g_dw_debug.sbo = (uint32_t)value; break;
+    case 4: tc::g_bk = value == 32 ? 32 : 64; break;
     default: set_error("tc_debug: unknown key %d", key); return B200REC_ERR_INVALID;
   }
   return B200REC_OK;

@@ -237,7 +237,8 @@ __global__ void din_reduce_partials_kernel(const float* __restrict__ partials, i
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= len) return;
   float t = 0.f;
-  for (int g = 0; g < G; ++g) t += partials[(size_t)g * len + k];
+#pragma unroll 8
+  for (int g = 0; g < G; ++g) t += partials[(size_t)g * len + k];   // loads hoisted, adds in order
   if (k < n0) { o0[k] = t; return; }
   k -= n0;
   if (k < n1) { o1[k] = t; return; }

@@ -587,7 +587,7 @@ embed_fm_bwd_dense_kernel(const float* __restrict__ feat, const float* __restric
 // `len` is small (<= a few thousand) but G can be hundreds: 32 columns x 8 g-lanes per block so
 // the G-long sums are not one serial dependent chain per column.
 constexpr int kRedCols = 32;
-constexpr int kRedLanes = 8;
+constexpr int kRedLanes = 32;   // r1 had 8: 74 dependent L2 round trips per thread = 30 us/launch
 __global__ void __launch_bounds__(kRedCols * kRedLanes)
 reduce_partials_kernel(const float* __restrict__ partials, int G, int len,
                        float* __restrict__ out0, int len0, float* __restrict__ out1) {
@@ -595,8 +595,17 @@ reduce_partials_kernel(const float* __restrict__ partials, int G, int len,
   const int cx = threadIdx.x % kRedCols, gy = threadIdx.x / kRedCols;
   const int k = blockIdx.x * kRedCols + cx;
   float t = 0.f;
-  if (k < len)
-    for (int g = gy; g < G; g += kRedLanes) t += partials[(size_t)g * len + k];
+  if (k < len) {
+    int g = gy;
+    for (; g + 3 * kRedLanes < G; g += 4 * kRedLanes) {   // four loads in flight, fixed add order
+      const float a0 = partials[(size_t)g * len + k];
+      const float a1 = partials[(size_t)(g + kRedLanes) * len + k];
+      const float a2 = partials[(size_t)(g + 2 * kRedLanes) * len + k];
+      const float a3 = partials[(size_t)(g + 3 * kRedLanes) * len + k];
+      t += a0; t += a1; t += a2; t += a3;
+    }
+    for (; g < G; g += kRedLanes) t += partials[(size_t)g * len + k];
+  }
   s[gy][cx] = t;
   __syncthreads();
   if (gy == 0 && k < len) {

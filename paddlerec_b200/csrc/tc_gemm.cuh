@@ -38,7 +38,9 @@ namespace tc {
 constexpr int kBM = 128;         // output rows per tile = UMMA M (cta_group::1)
 constexpr int kBK = 64;          // bf16 per k-block = one 128-byte swizzle row
 constexpr int kUK = 16;          // UMMA K for 16-bit operands
-constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kThreads = 192;    // dW kernel: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kEpiWarps = 8;     // K-major kernel: two epilogue warpgroups (alternate 32-col chunks)
+constexpr int kThreadsK = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;   // whole TMEM of the SM (one CTA per SM by shared-memory size)
 constexpr int kAccStride = 256;  // column offset of the second accumulator stage
 constexpr int kMaxBN = 256;
@@ -163,10 +165,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // ------------------------------------------------------------------------------------------------
 // UMMA shared-memory descriptor, SWIZZLE_128B (bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46)
 // SBO>>4, [46,48) version = 1 on sm_100, [61,64) layout type = 2).
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                              uint32_t sbo_bytes) {
+                                              uint32_t sbo_bytes, uint32_t layout = 2u) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout << 61);
 }
 // instruction descriptor for kind::f16: fp32 accumulate, bf16 x bf16, M = 128, N = n
 __host__ __device__ inline uint32_t umma_idesc(int n, int a_mn_major, int b_mn_major) {
@@ -192,6 +196,9 @@ struct Epilogue {
   const float* cross_x0;
   const float* cross_xl;
   int64_t ld_cross;
+  // also write out_planes[m, N] = 1.0 (hi) / 0 (lo): the column of ones that makes the dW GEMM of
+  // the next layer produce its bias gradient as row N (needs ldp > N)
+  int ones_col;
 };
 
 __device__ __forceinline__ void split_bf16(float x, float& hi_f, __nv_bfloat16& hi,
@@ -217,6 +224,73 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// hi/lo split of two values, packed for a 32-bit store (element a at the lower address)
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
+// Full 32-column chunk, everything 16-byte aligned: vector loads/stores only.  `mk` holds the 32
+// mask values (bf16 pairs) fetched before the TMEM wait.
+__device__ __forceinline__ void epilogue_fast(const Epilogue& ep, float (&v)[32], int64_t row,
+                                              int col0, const uint4 (&mk)[4]) {
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + g);
+      v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+    }
+  }
+  if (ep.cross_x0 != nullptr) {
+    const float4* x0 = reinterpret_cast<const float4*>(ep.cross_x0 + row * ep.ld_cross + col0);
+    const float4* xl = reinterpret_cast<const float4*>(ep.cross_xl + row * ep.ld_cross + col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 a = __ldg(x0 + g), b = __ldg(xl + g);
+      v[4 * g] = fmaf(a.x, v[4 * g], b.x);
+      v[4 * g + 1] = fmaf(a.y, v[4 * g + 1], b.y);
+      v[4 * g + 2] = fmaf(a.z, v[4 * g + 2], b.z);
+      v[4 * g + 3] = fmaf(a.w, v[4 * g + 3], b.w);
+    }
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (ep.mask_src != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // bf16 > 0  <=>  its bit pattern, as a signed integer in the high half, is > 0
+        if (!((int)(w[j] << 16) > 0)) v[8 * g + 2 * j] = 0.f;
+        if (!((int)(w[j] & 0xFFFF0000u) > 0)) v[8 * g + 2 * j + 1] = 0.f;
+      }
+    }
+  }
+  if (ep.out_f32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) o[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  }
+  if (ep.out_planes != nullptr) {
+    uint4* oh = reinterpret_cast<uint4*>(ep.out_planes + row * 2 * ep.ldp + col0);
+    uint4* ol = reinterpret_cast<uint4*>(ep.out_planes + row * 2 * ep.ldp + ep.ldp + col0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_pack2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], h[j], l[j]);
+      oh[g] = make_uint4(h[0], h[1], h[2], h[3]);
+      ol[g] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
 }
 
 // One row (this thread) x 32 columns of the accumulator -> outputs.  n_valid = columns of this chunk
@@ -338,19 +412,26 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
 
 // ------------------------------------------------------------------------------------------------
 // K-major GEMM: D[M,N] = A[M,K] . B[N,K]^T  (three tcgen05.mma per 16-wide k step)
+//   BK = 64: 128-byte swizzle rows (2 pipeline stages at BN = 208)
+//   BK = 32: 64-byte swizzle rows, half-size stages -> 5 stages at BN = 208: same bytes in shared
+//            memory, but a freed slot is refilled twice as early, which hides the TMA latency
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BK>
+__global__ void __launch_bounds__(kThreadsK, 1)
 tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                       const __grid_constant__ CUtensorMap tmA_lo,
                       const __grid_constant__ CUtensorMap tmB_hi,
                       const __grid_constant__ CUtensorMap tmB_lo, int M, int N, int K, int BN,
                       int stages, Epilogue ep) {
+  constexpr uint32_t kRow = BK * 2;                       // bytes per operand row in a stage
+  constexpr uint32_t kLayout = BK == 64 ? 2u : 4u;        // SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t kSbo = 8u * kRow;                    // 8-row swizzle atom
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t base = (raw + 1023u) & ~1023u;          // swizzled tiles: atom-aligned
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t a_bytes = kBM * 128u;                   // one plane of A: 128 rows x 128 B
-  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const uint32_t a_bytes = kBM * kRow;
+  const uint32_t b_bytes = (uint32_t)BN * kRow;
   const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;
   const uint32_t bar0 = base + (uint32_t)stages * stage_bytes;
   // barrier block: full[stages] empty[stages] tfull[2] tempty[2] | tmem ptr | colsum scratch
@@ -358,12 +439,12 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t bar_tfull = bar0 + 16u * stages, bar_tempty = bar_tfull + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * stage_bytes + 16 * stages + 32);
   float* s_colsum = reinterpret_cast<float*>(sm + (size_t)stages * stage_bytes + 16 * stages + 64);
-  // s_colsum: [4 warps][kMaxBN]
+  // s_colsum: [4 lane quarters][kMaxBN], only with ep.colsum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n;
-  const int nkb = (K + kBK - 1) / kBK;
+  const int nkb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
@@ -373,7 +454,7 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8u * s, 1);
-      mbar_init(bar_tempty + 8u * s, 4);     // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8u * s, kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -397,10 +478,10 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
           const uint32_t full = bar_full + 8u * stage;
           const uint32_t sA = base + (uint32_t)stage * stage_bytes;
           mbar_expect_tx(full, stage_bytes);
-          tma_load_2d(sA, &tmA_hi, full, kb * kBK, m0);
-          tma_load_2d(sA + a_bytes, &tmA_lo, full, kb * kBK, m0);
-          tma_load_2d(sA + 2u * a_bytes, &tmB_hi, full, kb * kBK, n0);
-          tma_load_2d(sA + 2u * a_bytes + b_bytes, &tmB_lo, full, kb * kBK, n0);
+          tma_load_2d(sA, &tmA_hi, full, kb * BK, m0);
+          tma_load_2d(sA + a_bytes, &tmA_lo, full, kb * BK, m0);
+          tma_load_2d(sA + 2u * a_bytes, &tmB_hi, full, kb * BK, n0);
+          tma_load_2d(sA + 2u * a_bytes + b_bytes, &tmB_lo, full, kb * BK, n0);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -422,14 +503,14 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
           tc_fence_after();
           const uint32_t sA = base + (uint32_t)stage * stage_bytes;
           const uint32_t sB = sA + 2u * a_bytes;
-          int ksteps = (K - kb * kBK + kUK - 1) / kUK;
-          ksteps = ksteps > kBK / kUK ? kBK / kUK : ksteps;
+          int ksteps = (K - kb * BK + kUK - 1) / kUK;
+          ksteps = ksteps > BK / kUK ? BK / kUK : ksteps;
           for (int j = 0; j < ksteps; ++j) {
-            const uint32_t ko = (uint32_t)j * (kUK * 2);   // 32 bytes inside the swizzle row
-            const uint64_t a_hi = umma_desc(sA + ko, 16, 1024);
-            const uint64_t a_lo = umma_desc(sA + a_bytes + ko, 16, 1024);
-            const uint64_t b_hi = umma_desc(sB + ko, 16, 1024);
-            const uint64_t b_lo = umma_desc(sB + b_bytes + ko, 16, 1024);
+            const uint32_t ko = (uint32_t)j * (kUK * 2);   // 32 bytes further inside the swizzle row
+            const uint64_t a_hi = umma_desc(sA + ko, 16, kSbo, kLayout);
+            const uint64_t a_lo = umma_desc(sA + a_bytes + ko, 16, kSbo, kLayout);
+            const uint64_t b_hi = umma_desc(sB + ko, 16, kSbo, kLayout);
+            const uint64_t b_lo = umma_desc(sB + b_bytes + ko, 16, kSbo, kLayout);
             tc_mma(d_tmem, a_hi, b_hi, idesc, (kb | j) != 0 ? 1u : 0u);
             tc_mma(d_tmem, a_lo, b_hi, idesc, 1u);
             tc_mma(d_tmem, a_hi, b_lo, idesc, 1u);
@@ -442,44 +523,74 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       }
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 only
+    // epilogue: a warp may touch TMEM lanes 32*(warp%4) .. +31 only; the two warps that share a
+    // lane quarter take alternate 32-column chunks
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool want_colsum = ep.colsum != nullptr;
+    const bool base_aligned =
+        (ep.out_f32 == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_f32) | (ep.ld_f32 * 4)) & 15u) == 0) &&
+        (ep.out_planes == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_planes) | (ep.ldp * 2)) & 15u) == 0) &&
+        (ep.mask_src == nullptr || ((reinterpret_cast<uintptr_t>(ep.mask_src) | (ep.ld_mask * 2)) & 15u) == 0) &&
+        (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15u) == 0) &&
+        (ep.cross_x0 == nullptr ||
+         ((reinterpret_cast<uintptr_t>(ep.cross_x0) | reinterpret_cast<uintptr_t>(ep.cross_xl) |
+           (ep.ld_cross * 4)) & 15u) == 0);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m_blk = tile / tiles_n;
       const int m0 = m_blk * kBM, n0 = (tile % tiles_n) * BN;
       const int n_tile = (N - n0) < BN ? (N - n0) : BN;
       const int64_t row = (int64_t)m0 + q * 32 + lane;
       const bool row_ok = row < M;
+      // warp-uniform on purpose: tcgen05.ld is .sync.aligned, so the 32 lanes must not split into a
+      // fast and a slow path inside the chunk loop (a partially valid last row block goes slow)
+      const bool fast_ok =
+          base_aligned && ((int64_t)m0 + q * 32 + 31 < M) && (n0 & 7) == 0 && !want_colsum;
       mbar_wait(bar_tfull + 8u * acc, acc_phase, 0x400u + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccStride;
-      for (int c0 = 0; c0 < n_tile; c0 += 32) {
+      for (int c0 = half * 32; c0 < n_tile; c0 += 64) {
         uint32_t r[32];
+        __syncwarp();
         tmem_ld32(t_row + (uint32_t)c0, r);
+        const int nv = (n_tile - c0) < 32 ? (n_tile - c0) : 32;
+        const bool fast = fast_ok && nv == 32;
+        uint4 mk[4];
+        if (fast && ep.mask_src != nullptr) {    // in flight while the TMEM load completes
+          const uint4* mp = reinterpret_cast<const uint4*>(ep.mask_src + row * ep.ld_mask + n0 + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) mk[g] = __ldg(mp + g);
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int nv = (n_tile - c0) < 32 ? (n_tile - c0) : 32;
-        epilogue_chunk(ep, v, row, row_ok, n0 + c0, nv, lane,
-                       want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr);
+        if (fast)
+          epilogue_fast(ep, v, row, n0 + c0, mk);
+        else
+          epilogue_chunk(ep, v, row, row_ok, n0 + c0, nv, lane,
+                         want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr);
+      }
+      if (ep.ones_col && ep.out_planes != nullptr && row_ok && half == 0 && n0 + n_tile == N) {
+        __nv_bfloat16* oh = ep.out_planes + row * 2 * ep.ldp + N;
+        oh[0] = __float2bfloat16_rn(1.f);
+        oh[ep.ldp] = __float2bfloat16_rn(0.f);
       }
       // accumulator drained -> the MMA warp may overwrite this stage
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
       if (want_colsum) {
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kEpiWarps);
         const int t = threadIdx.x - 64;
-        for (int c = t; c < n_tile; c += 128) {
+        for (int c = t; c < n_tile; c += 32 * kEpiWarps) {
           const float s = ((s_colsum[c] + s_colsum[kMaxBN + c]) + s_colsum[2 * kMaxBN + c]) +
                           s_colsum[3 * kMaxBN + c];
           ep.colsum[(int64_t)m_blk * N + n0 + c] = s;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kEpiWarps);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -742,6 +853,7 @@ static EncodeTiledFn encode_tiled_fn() {
 // out-of-bounds elements read as zero.
 static int make_map(CUtensorMap* m, const void* base, int64_t width, int64_t rows,
                     int64_t pitch_elems, int box_w, int box_rows) {
+  const CUtensorMapSwizzle swz = box_w == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) {
     set_error("tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
@@ -757,8 +869,8 @@ static int make_map(CUtensorMap* m, const void* base, int64_t width, int64_t row
   const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc_gemm: cuTensorMapEncodeTiled failed (%d) width %lld rows %lld pitch %lld box %dx%d",
@@ -777,6 +889,7 @@ static int pick_bn(int N) {
 
 static DwDebug g_dw_debug = {0u, 0u, 0u};
 static int g_bn_override = 0;
+static int g_bk = 64;   // k-block of the K-major kernel: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
 
 // D = A . B^T with A planes [M, 2*lda] (logical [M,K]) and B planes [N, 2*ldb] (logical [N,K]).
 static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M,
@@ -785,29 +898,36 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
   B200_REQUIRE(M < (1ll << 31), "tc_gemm: M too large");
   if (M == 0) return B200REC_OK;
   const int BN = g_bn_override > 0 ? g_bn_override : pick_bn(N);
-  const uint32_t stage_bytes = 2u * kBM * 128u + 2u * (uint32_t)BN * 128u;
+  const int BK = g_bk == 64 ? 64 : 32;
+  const uint32_t stage_bytes = (2u * kBM + 2u * (uint32_t)BN) * (uint32_t)BK * 2u;
   int stages = (int)((kSmemBudget - 4096u - 16u * kMaxBN) / stage_bytes);
-  stages = stages > 6 ? 6 : stages;
+  stages = stages > 8 ? 8 : stages;
   B200_REQUIRE(stages >= 2, "tc_gemm: tile does not fit shared memory");
   const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 64 + 16 * kMaxBN + 1024;
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(A);
   const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(B);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a, K, M, 2 * lda, kBK, kBM)) != B200REC_OK) return rc;
-  if ((rc = make_map(&ma_lo, a + lda, K, M, 2 * lda, kBK, kBM)) != B200REC_OK) return rc;
-  if ((rc = make_map(&mb_hi, b, K, N, 2 * ldb, kBK, BN)) != B200REC_OK) return rc;
-  if ((rc = make_map(&mb_lo, b + ldb, K, N, 2 * ldb, kBK, BN)) != B200REC_OK) return rc;
+  if ((rc = make_map(&ma_hi, a, K, M, 2 * lda, BK, kBM)) != B200REC_OK) return rc;
+  if ((rc = make_map(&ma_lo, a + lda, K, M, 2 * lda, BK, kBM)) != B200REC_OK) return rc;
+  if ((rc = make_map(&mb_hi, b, K, N, 2 * ldb, BK, BN)) != B200REC_OK) return rc;
+  if ((rc = make_map(&mb_lo, b + ldb, K, N, 2 * ldb, BK, BN)) != B200REC_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor_kernel,
+    B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor_kernel<64>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor_kernel<32>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int tiles = (int)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tc_gemm_kmajor_kernel<<<grid, kThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, (int)M, N, K, BN,
-                                                      stages, ep);
+  if (BK == 64)
+    tc_gemm_kmajor_kernel<64><<<grid, kThreadsK, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, (int)M, N,
+                                                             K, BN, stages, ep);
+  else
+    tc_gemm_kmajor_kernel<32><<<grid, kThreadsK, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, (int)M, N,
+                                                             K, BN, stages, ep);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

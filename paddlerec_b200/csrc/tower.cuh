@@ -33,7 +33,8 @@ struct alignas(8) Bf16x4 {
 template <int VEC>
 __global__ void __launch_bounds__(kTowerThreads)
 tower_split_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ bias,
-                   int relu, __nv_bfloat16* __restrict__ out, int64_t ldp, int64_t M, int K) {
+                   int relu, __nv_bfloat16* __restrict__ out, int64_t ldp, int64_t M, int K,
+                   int ones_col) {
   const int chunks = K / VEC;
   const int64_t total = M * chunks;
   for (int64_t i = (int64_t)blockIdx.x * kTowerThreads + threadIdx.x; i < total;
@@ -51,6 +52,10 @@ tower_split_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
       for (int j = 0; j < VEC; ++j) a.v[j] = fmaxf(a.v[j], 0.f);
     }
     __nv_bfloat16* row = out + (size_t)m * 2 * ldp;
+    if (ones_col && k == 0) {   // column K of the hi plane = 1: the dW GEMM then yields colsum(g)
+      row[K] = __float2bfloat16_rn(1.f);
+      row[ldp + K] = __float2bfloat16_rn(0.f);
+    }
     if (VEC == 4) {
       Bf16x4 hi, lo;
 #pragma unroll
@@ -182,8 +187,9 @@ static int tower_row_slices(int64_t M) {
 }
 
 static int launch_tower_split(const float* x, int64_t ldx, const float* bias, int relu, void* out,
-                              int64_t ldp, int64_t M, int K, cudaStream_t st) {
-  B200_REQUIRE(K > 0 && M >= 0 && ldx >= K && ldp >= K, "tower_split: bad sizes");
+                              int64_t ldp, int64_t M, int K, int ones_col, cudaStream_t st) {
+  B200_REQUIRE(K > 0 && M >= 0 && ldx >= K && ldp >= K + (ones_col ? 1 : 0),
+               "tower_split: bad sizes");
   if (M == 0) return B200REC_OK;
   const bool v4 = (K % 4 == 0) && (ldx % 4 == 0) && (ldp % 4 == 0) && aligned16(x) &&
                   aligned8(out) && (!bias || aligned16(bias));
@@ -192,9 +198,11 @@ static int launch_tower_split(const float* x, int64_t ldx, const float* bias, in
       (unsigned)min((total + kTowerThreads - 1) / kTowerThreads, (int64_t)sm_count() * 16);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (v4)
-    tower_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(x, ldx, bias, relu, o, ldp, M, K);
+    tower_split_kernel<4><<<grid, kTowerThreads, 0, st>>>(x, ldx, bias, relu, o, ldp, M, K,
+                                                          ones_col);
   else
-    tower_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(x, ldx, bias, relu, o, ldp, M, K);
+    tower_split_kernel<1><<<grid, kTowerThreads, 0, st>>>(x, ldx, bias, relu, o, ldp, M, K,
+                                                          ones_col);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

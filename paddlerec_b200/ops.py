@@ -419,23 +419,26 @@ def raw_tower_fold_dw(Mx: torch.Tensor, K: int, N: int) -> torch.Tensor:
 
 
 # ---- tcgen05 tower GEMMs (csrc/tc_gemm.cuh) ---------------------------------------------------
-def plane_ld(n: int) -> int:
-    """Plane pitch of a logical width n: the hi and lo planes must both be 16-byte aligned."""
-    return (int(n) + 7) // 8 * 8
+def plane_ld(n: int, ones_col: bool = False) -> int:
+    """Plane pitch of a logical width n (+1 with a ones column): the hi and lo planes must both be
+    16-byte aligned."""
+    return (int(n) + int(ones_col) + 7) // 8 * 8
 
 
-def _planes(M: int, n: int, device) -> torch.Tensor:
-    return torch.empty(M, 2 * plane_ld(n), dtype=torch.bfloat16, device=device)
+def _planes(M: int, n: int, device, ones_col: bool = False) -> torch.Tensor:
+    return torch.empty(M, 2 * plane_ld(n, ones_col), dtype=torch.bfloat16, device=device)
 
 
-def raw_tc_split(x: torch.Tensor, bias=None, relu: bool = False) -> torch.Tensor:
-    """fp32 [M,K] -> planes [M, 2*ld(K)] of relu?(x + bias?)."""
+def raw_tc_split(x: torch.Tensor, bias=None, relu: bool = False,
+                 ones_col: bool = False) -> torch.Tensor:
+    """fp32 [M,K] -> planes [M, 2*ld] of relu?(x + bias?); ones_col: hi[:, K] = 1 (see
+    raw_tc_linear_bwd_dw)."""
     lib = _lib.load()
     x = _req(x, torch.float32, "x")
     M, K = x.shape
-    out = _planes(M, K, x.device)
-    check(lib.b200rec_tc_split(ptr(x), K, ptr(bias), int(relu), ptr(out), plane_ld(K), M, K,
-                               _stream()), "tc_split")
+    out = _planes(M, K, x.device, ones_col)
+    check(lib.b200rec_tc_split(ptr(x), K, ptr(bias), int(relu), ptr(out), out.shape[1] // 2, M, K,
+                               int(ones_col), _stream()), "tc_split")
     _count("tc_split")
     return out
 
@@ -472,17 +475,19 @@ def raw_tc_prep_weight(W: torch.Tensor, want_w: bool = True, want_wt: bool = Tru
 
 
 def raw_tc_linear_fwd(a_planes: torch.Tensor, K: int, WTp: torch.Tensor, N: int, bias, relu: bool,
-                      want_f32: bool, want_planes: bool):
+                      want_f32: bool, want_planes: bool, ones_col: bool = False):
     """y = a @ W + bias (ReLU optional) on the tcgen05 tensor cores.  Returns (y fp32 [M,N] | None,
-    planes(y) [M, 2*ld(N)] | None)."""
+    planes(y) [M, 2*ld] | None)."""
     lib = _lib.load()
     M = a_planes.shape[0]
     dev = a_planes.device
     y = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
-    yp = _planes(M, N, dev) if want_planes else None
+    yp = _planes(M, N, dev, ones_col) if want_planes else None
     check(lib.b200rec_tc_linear_fwd(ptr(a_planes), a_planes.shape[1] // 2, ptr(WTp),
                                     WTp.shape[1] // 2, ptr(bias), int(relu), ptr(y), N, ptr(yp),
-                                    plane_ld(N), M, N, K, _stream()), "tc_linear_fwd")
+                                    yp.shape[1] // 2 if yp is not None else 0,
+                                    int(ones_col and want_planes), M, N, K, _stream()),
+          "tc_linear_fwd")
     _count("tc_linear_fwd")
     return y, yp
 
@@ -532,11 +537,16 @@ def raw_tc_linear_bwd_dx(g_planes, N: int, Wp, K: int, mask_planes, want_f32: bo
     return dx, dxp, db
 
 
-def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int) -> torch.Tensor:
-    """dW [K,N] = a^T @ g (batch-split tcgen05 GEMM + fixed-order reduce)."""
+def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int, bias_row: bool = False):
+    """dW [K,N] = a^T @ g (batch-split tcgen05 GEMM + fixed-order reduce).  With bias_row the
+    operand `a` carries a column of ones at index K (ones_col of raw_tc_split / raw_tc_linear_fwd)
+    and the result is (dW [K,N], dbias [N]) — the bias gradient is row K of the same GEMM."""
     lib = _lib.load()
     M = a_planes.shape[0]
     dev = a_planes.device
+    if bias_row:
+        ext = raw_tc_linear_bwd_dw(a_planes, K + 1, g_planes, N)
+        return ext[:K], ext[K]
     dW = torch.empty(K, N, dtype=torch.float32, device=dev)
     ws = _tc_bwd_ws(M, K, N, dev)
     check(lib.b200rec_tc_linear_bwd_dw(ptr(a_planes), a_planes.shape[1] // 2, ptr(g_planes),

@@ -49,7 +49,11 @@ class _TowerTcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n_layers, last_act, *params):
         Ws, bs = params[:n_layers], params[n_layers:]
-        a = ops.raw_tc_split(x)
+        # Layer i's bias gradient is colsum(g_i).  If its input width is not a multiple of the
+        # 128-row dW tile, a column of ones rides in the input planes and the dW GEMM delivers the
+        # column sum as an extra output row for free; otherwise the dX epilogue sums columns.
+        ones = [b is not None and W.shape[0] % 128 != 0 for W, b in zip(Ws, bs)]
+        a = ops.raw_tc_split(x, ones_col=ones[0])
         acts, wps = [a], []
         y = None
         for i in range(n_layers):
@@ -59,10 +63,11 @@ class _TowerTcFn(torch.autograd.Function):
             last = i == n_layers - 1
             relu = (not last) or last_act
             y, a = ops.raw_tc_linear_fwd(a, K, WTp, N, bs[i], relu, want_f32=last,
-                                         want_planes=(not last) or last_act)
+                                         want_planes=(not last) or last_act,
+                                         ones_col=(not last) and ones[i + 1])
             if a is not None:
                 acts.append(a)
-        ctx.n_layers, ctx.last_act = n_layers, last_act
+        ctx.n_layers, ctx.last_act, ctx.ones = n_layers, last_act, ones
         ctx.acts, ctx.wps = acts, wps
         ctx.shapes = [tuple(W.shape) for W in Ws]
         ctx.has_bias = [b is not None for b in bs]
@@ -70,20 +75,24 @@ class _TowerTcFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        n = ctx.n_layers
+        n, ones = ctx.n_layers, ctx.ones
         acts, wps = ctx.acts, ctx.wps
         dWs, dbs = [None] * n, [None] * n
         g, db = ops.raw_tc_split_bwd(dy.contiguous(), acts[n] if ctx.last_act else None)
         dx0 = None
         for i in range(n - 1, -1, -1):
             K, N = ctx.shapes[i]
-            dWs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N)
-            dbs[i] = db if ctx.has_bias[i] else None
+            if ones[i]:
+                dWs[i], dbs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N, bias_row=True)
+            else:
+                dWs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N)
+                dbs[i] = db if ctx.has_bias[i] else None
             if i > 0:
-                # dx of layer i is masked by layer i's input (= ReLU output of layer i-1), split,
-                # and its column sums are layer i-1's bias gradient: all in the GEMM epilogue
+                # dx of layer i, masked by layer i's input (= ReLU output of layer i-1) and split
+                # into the next GEMM's operand, all in the GEMM epilogue
+                want_db = ctx.has_bias[i - 1] and not ones[i - 1]
                 _, g, db = ops.raw_tc_linear_bwd_dx(g, N, wps[i], K, acts[i], want_f32=False,
-                                                    want_planes=True, want_dbias=True)
+                                                    want_planes=True, want_dbias=want_db)
             elif ctx.needs_input_grad[0]:
                 dx0, _, _ = ops.raw_tc_linear_bwd_dx(g, N, wps[i], K, None, want_f32=True,
                                                      want_planes=False, want_dbias=False)

@@ -90,7 +90,9 @@ def test_optimizer_state_round_trip_resumes_the_same_trajectory(tmp_path):
         torch.manual_seed(5)
         lin = bnn.Linear(6, 3, weight_std=0.3, weight_l2_decay=0.01)
         sched = optim.PiecewiseDecay([2], [0.1, 0.01])
-        return lin, optim.Adam(sched, lin.parameters())
+        opt = optim.Adam(sched, lin.parameters())
+        opt.lr_auto_step = True     # per-step decay is opt-in (the reference never steps it)
+        return lin, opt
 
     def step(lin, opt, seed):
         g = torch.Generator().manual_seed(seed)

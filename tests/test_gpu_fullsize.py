@@ -95,3 +95,114 @@ def test_backward_checksums_and_lazy_update_full_size(problem):
     assert not (changed & ~touched).any()          # untouched rows are bit-identical
     assert (changed[touched]).float().mean() > 0.99
     assert not W[0].any()                           # padding row stays zero
+
+
+# ---------------------------------------------------------------------------------------------------
+# Oracle-backed parity AT the headline configuration: the product model with
+# the V=1e8 table, B=65536, bf16x3 tcgen05 tower.  The fp64 oracle runs on a 512-sample slice with
+# only the touched rows copied to the host and the ids remapped; every comparison is ELEMENT-WISE:
+#     |got - want| <= 1e-4 * |want| + floor,   floor = 1e-4 * rms(want)
+# (a pure relative test is meaningless on entries that are zero up to rounding; the floor is tied to
+# the tensor's own scale so it cannot hide a wrong row).
+NS = 512
+
+
+def _close(got, want, what):
+    got, want = got.double().cpu(), want.double().cpu()
+    floor = 1e-4 * float(want.square().mean().sqrt()) + 1e-30
+    bad = (got - want).abs() > 1e-4 * want.abs() + floor
+    assert not bool(bad.any()), "%s: %d / %d entries off, worst %.3e (floor %.1e)" % (
+        what, int(bad.sum()), bad.numel(), float(((got - want).abs() - 1e-4 * want.abs()).max()), floor)
+
+
+def _oracle_slice(layer, ids_s, dense_s, label_s, denom):
+    """fp64 oracle on a slice: touched rows -> host, ids remapped to 1..U (0 stays padding)."""
+    from oracle import nets
+    sd = layer.state_dict()
+    flat = ids_s.reshape(-1)
+    uniq = torch.unique(flat[flat != 0])
+    remap = torch.searchsorted(uniq, ids_s.reshape(-1)).reshape(ids_s.shape) + 1
+    remap = torch.where(ids_s == 0, torch.zeros_like(remap), remap).cpu()
+    D_ = layer.sparse_feature_dim
+    p = {"fm.embedding.weight": torch.cat([torch.zeros(1, D_, device=DEV),
+                                           sd["fm.embedding.weight"][uniq]]).cpu(),
+         "fm.embedding_one.weight": torch.cat([torch.zeros(1, 1, device=DEV),
+                                               sd["fm.embedding_one.weight"][uniq]]).cpu()}
+    for k, v in sd.items():
+        if not k.startswith("fm.embedding"):
+            p[k] = v.detach().cpu()
+    p = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    n_fc = len(layer.layer_sizes)
+    pred = nets.deepfm_forward(p, [remap[:, i:i + 1] for i in range(remap.shape[1])],
+                               dense_s.double().cpu(), n_fc)
+    loss = nets.log_loss(pred, label_s.double().cpu()).sum() / denom
+    loss.backward()
+    return uniq, pred.detach(), {k: v.grad for k, v in p.items()}
+
+
+@pytest.fixture(scope="module")
+def headline_model():
+    from paddlerec_b200 import nn as bnn
+    from paddlerec_b200.rank.deepfm import net
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of free HBM")
+    torch.manual_seed(12345)
+    bnn.set_matmul_precision("bf16x3")
+    layer = net.DeepFMLayer(V, D, Dn, F, [400, 400, 400], device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(999)
+    ids = torch.randint(1, V, (B, F), device=DEV, generator=g)
+    ids[torch.rand(B, F, device=DEV, generator=g) < 0.02] = 0
+    ids[:NS:7, 3] = ids[0, 3]                 # duplicates inside the slice
+    ids[5, :] = 0                             # an all-padding sample
+    dense = torch.rand(B, Dn, device=DEV, generator=g)
+    dense[torch.rand(B, Dn, device=DEV, generator=g) < 0.3] = 0
+    label = (torch.rand(B, 1, device=DEV, generator=g) < 0.29).float()
+    yield layer, ids, dense, label
+    bnn.set_matmul_precision("fp32")
+
+
+def test_headline_config_logits_and_table_grads_vs_oracle(headline_model):
+    """B=65536, V=1e8: logits of the first 512 samples and the gradient rows of every table row that
+    ONLY those samples touch (a row's gradient is a sum over its positions, each of which depends on
+    its own sample alone) against the fp64 oracle."""
+    from paddlerec_b200 import functional as BF
+    layer, ids, dense, label = headline_model
+    layer.fm._fused.weight.grad_rows = None
+    layer.zero_grad()
+    pred = layer(ids, dense)
+    BF.log_loss(pred, label).mean().backward()
+    uniq, pred_ref, grads = _oracle_slice(layer, ids[:NS], dense[:NS], label[:NS], denom=B)
+    _close(pred[:NS], pred_ref, "logits[:512] at B=65536")
+    sr = layer.fm._fused.weight.grad_rows
+    U = int(sr.num[0])
+    rest = torch.unique(ids[NS:])
+    only = uniq[~torch.isin(uniq, rest)]
+    assert only.numel() > 0.9 * uniq.numel()
+    where = torch.searchsorted(sr.rows[:U].contiguous(), only)
+    assert torch.equal(sr.rows[:U][where], only)
+    got = sr.value[where]
+    idx = (torch.searchsorted(uniq, only) + 1).cpu()
+    _close(got[:, :D], grads["fm.embedding.weight"][idx], "dW rows (second-order table)")
+    _close(got[:, D:D + 1], grads["fm.embedding_one.weight"][idx], "dW1 rows (first-order table)")
+
+
+def test_headline_table_small_batch_every_gradient_vs_oracle(headline_model):
+    """Same V=1e8 model, the 512-sample slice as its own batch: logits, EVERY tower / dense-feature
+    gradient and every touched table row against the oracle."""
+    from paddlerec_b200 import functional as BF
+    layer, ids, dense, label = headline_model
+    layer.fm._fused.weight.grad_rows = None
+    layer.zero_grad()
+    pred = layer(ids[:NS], dense[:NS])
+    BF.log_loss(pred, label[:NS]).mean().backward()
+    uniq, pred_ref, grads = _oracle_slice(layer, ids[:NS], dense[:NS], label[:NS], denom=NS)
+    _close(pred, pred_ref, "logits")
+    for k, v in layer.named_parameters():
+        if v.grad is not None and k in grads:
+            _close(v.grad, grads[k], "grad of " + k)
+    sr = layer.fm._fused.weight.grad_rows
+    U = int(sr.num[0])
+    assert torch.equal(sr.rows[:U], uniq)
+    _close(sr.value[:U, :D], grads["fm.embedding.weight"][1:], "dW rows")
+    _close(sr.value[:U, D:D + 1], grads["fm.embedding_one.weight"][1:], "dW1 rows")

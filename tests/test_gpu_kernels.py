@@ -407,15 +407,15 @@ def test_din_attention_fused_forward_and_grads(B, L, E):
     b3 = torch.randn(1, generator=g) * 0.1
     params = [W1, b1, W2, b2, W3, b3]
     ref_in = [t.double().requires_grad_(True) for t in [hist, tseq] + params]
-    ref = ops._din_attention_composite(ref_in[0], ref_in[1], mask, *ref_in[2:])
+    ref = nets.din_attention_unit(ref_in[0], ref_in[1], mask, *ref_in[2:])
     gout = torch.randn(B, E, generator=g)
     (ref * gout.double()).sum().backward()
     dev_in = [t.to(DEV).requires_grad_(True) for t in [hist, tseq] + params]
     out = ops.din_attention(dev_in[0], dev_in[1], mask.to(DEV), *dev_in[2:])
     assert rel_err(out, ref) < 2e-5
     out_nomask = ops.raw_din_attn_fwd(hist.to(DEV), tseq.to(DEV), None, *[p.to(DEV) for p in params])[0]
-    ref_nomask = ops._din_attention_composite(hist.double(), tseq.double(), None,
-                                              *[p.double() for p in params])
+    ref_nomask = nets.din_attention_unit(hist.double(), tseq.double(), None,
+                                         *[p.double() for p in params])
     assert rel_err(out_nomask, ref_nomask) < 2e-5
     (out * gout.to(DEV)).sum().backward()
     for a, b in zip(dev_in, ref_in):

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import load_golden, rel_err
+from tests.util import elementwise_excess, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -46,6 +46,8 @@ def grads_of(layer, extra=None):
 
 def check(g, pred, loss, grads, tol=TOL):
     assert rel_err(pred.detach().cpu().numpy(), g["out"]["pred"]) < tol
+    # the north-star bar read element-wise: every logit/probability within tol of its own value
+    assert elementwise_excess(pred.detach().cpu().numpy(), g["out"]["pred"], rtol=tol) <= 0
     assert abs(float(loss) - float(g["out"]["loss"])) < tol * max(1.0, abs(float(g["out"]["loss"])))
     for k, ref in g["grad"].items():
         assert k in grads, k

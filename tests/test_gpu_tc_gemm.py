@@ -59,7 +59,9 @@ def test_tc_linear_fwd(M, N, K, relu):
 
 
 @pytest.mark.parametrize("bn", [16, 64, 128, 256])
-def test_tc_linear_fwd_tile_widths(bn):
+@pytest.mark.parametrize("bk", [32, 64])
+def test_tc_linear_fwd_tile_shapes(bn, bk):
+    """Forced tile widths and both k-block / swizzle variants (64 B and 128 B rows)."""
     ops = _ops()
     g = torch.Generator().manual_seed(bn)
     M, N, K = 700, 400, 624
@@ -68,12 +70,37 @@ def test_tc_linear_fwd_tile_widths(bn):
     a = ops.raw_tc_split(x.to(DEV))
     _, WTp = ops.raw_tc_prep_weight(W.to(DEV))
     ops.tc_debug(0, bn)
+    ops.tc_debug(4, bk)
     try:
         y, _ = ops.raw_tc_linear_fwd(a, K, WTp, N, None, False, True, False)
         torch.cuda.synchronize()
     finally:
         ops.tc_debug(0, 0)
+        ops.tc_debug(4, 64)
     assert _err(y, x.double() @ W.double()) < 5e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(257, 624, 400), (5000, 400, 400), (300, 127, 1)])
+def test_tc_bias_row_from_ones_column(M, K, N):
+    """ones_col: the operand planes carry hi[:, K] = 1, the forward GEMM must ignore it (its tensor
+    map stops at K) and the dW GEMM over K+1 rows returns colsum(g) as the extra row."""
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g_)
+    W = torch.randn(K, N, generator=g_) / K ** 0.5
+    gy = torch.randn(M, N, generator=g_)
+    a = ops.raw_tc_split(x.to(DEV), ones_col=True)
+    _, WTp = ops.raw_tc_prep_weight(W.to(DEV), want_w=False)
+    y, yp = ops.raw_tc_linear_fwd(a, K, WTp, N, None, False, True, True, ones_col=True)
+    assert _err(y, x.double() @ W.double()) < 5e-5
+    ld = yp.shape[1] // 2
+    assert ld >= N + 1
+    assert torch.all(yp[:, N].float() == 1) and torch.all(yp[:, ld + N].float() == 0)
+    gp, _ = ops.raw_tc_split_bwd(gy.to(DEV), None)
+    dW, db = ops.raw_tc_linear_bwd_dw(a, K, gp, N, bias_row=True)
+    torch.cuda.synchronize()
+    assert _err(dW, x.double().t() @ gy.double()) < 5e-5
+    assert _err(db, gy.double().sum(0)) < 5e-5
 
 
 @pytest.mark.parametrize("M,K,N", [(257, 624, 400), (1000, 400, 400), (300, 400, 1), (4096, 400, 624),
@@ -120,6 +147,38 @@ def test_tc_linear_bwd_dw(M, K, N):
     assert torch.equal(dW, dW2)
 
 
+def test_tc_many_tiles_per_cta():
+    """More output tiles than SMs: every CTA walks several tiles, alternating the two TMEM
+    accumulator stages while the epilogue of the previous tile is still draining; rows 39936..
+    exercise the partially valid last row block."""
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(77)
+    M, K, N = 40003, 400, 64
+    x = torch.randn(M, N, generator=g_)
+    W = torch.randn(N, K, generator=g_) / N ** 0.5
+    b = torch.randn(K, generator=g_) * 0.1
+    a = ops.raw_tc_split(x.to(DEV))
+    _, WTp = ops.raw_tc_prep_weight(W.to(DEV), want_w=False)
+    y, yp = ops.raw_tc_linear_fwd(a, N, WTp, K, b.to(DEV), True, True, True, ones_col=True)
+    want = (x.double() @ W.double() + b.double()).clamp_min(0)
+    assert _err(y, want) < 5e-5 and _err(_join(yp, K), want) < 5e-5
+    # backward of the same layer, vector epilogue with the ReLU mask (no column sums)
+    gy = torch.randn(M, K, generator=g_)
+    W2 = torch.randn(N, K, generator=g_) / K ** 0.5          # dx [M,N] = g [M,K] @ W2^T
+    gp, _ = ops.raw_tc_split_bwd(gy.to(DEV), yp)             # top split masked by relu(y)
+    wantg = gy.double() * (want > 0)
+    assert _err(_join(gp, K), wantg) < 5e-5
+    act = torch.randn(M, N, generator=g_).clamp_min(0)
+    ap = ops.raw_tc_split(act.to(DEV), ones_col=True)
+    Wp, _ = ops.raw_tc_prep_weight(W2.to(DEV), want_wt=False)
+    dx, dxp, _ = ops.raw_tc_linear_bwd_dx(gp, K, Wp, N, ap, True, True, False)
+    torch.cuda.synchronize()
+    wantdx = (wantg @ W2.double().t()) * (act.double() > 0)
+    assert _err(dx, wantdx) < 5e-5 and _err(_join(dxp, N), wantdx) < 5e-5
+    # element-wise on the tail rows (a max-norm bound would hide one bad row)
+    assert _err(dx[-80:], wantdx[-80:]) < 5e-5
+
+
 def test_tc_cross_fwd():
     """CrossNetV2 layer (dcn_v2/net.py:222-226): x0 * (xl @ W + b) + xl in the GEMM epilogue."""
     ops = _ops()
@@ -138,14 +197,15 @@ def test_tc_cross_fwd():
     assert _err(_join(outp, C), want) < 5e-5
 
 
+@pytest.mark.parametrize("sizes", [[624, 400, 400, 400, 1], [429, 512, 256, 128, 32]])
 @pytest.mark.parametrize("last_act", [False, True])
 @pytest.mark.parametrize("backend", ["tcgen05", "cublas"])
-def test_tower_backends_match_fp64(backend, last_act):
+def test_tower_backends_match_fp64(backend, last_act, sizes):
     """The whole tower (forward + every gradient) on both back ends, headline shape."""
     from paddlerec_b200 import tower
     from tests.util import rel_err
     g = torch.Generator().manual_seed(11)
-    M, sizes = 1000, [624, 400, 400, 400, 1]
+    M = 1000
     L = len(sizes) - 1
     x = torch.randn(M, sizes[0], generator=g)
     Ws = [torch.randn(sizes[i], sizes[i + 1], generator=g) / sizes[i] ** 0.5 for i in range(L)]
@@ -158,7 +218,7 @@ def test_tower_backends_match_fp64(backend, last_act):
         h = h @ Wd[i] + bd[i]
         if i < L - 1 or last_act:
             h = torch.relu(h)
-    gy = torch.randn(M, 1, generator=g)
+    gy = torch.randn(M, sizes[-1], generator=g)
     (h * gy.double()).sum().backward()
     xc = x.to(DEV).requires_grad_(True)
     Wc = [w.to(DEV).requires_grad_(True) for w in Ws]

@@ -206,3 +206,21 @@ def test_dcn_v2_reader_log_transform_and_native_schema():
                                              "runner.packed_schema": "criteo_dcn_v2"}))
     for a, b in zip(plain, packed):
         assert torch.equal(b[1], torch.cat(a[1:27], 1)) and torch.equal(b[2], a[27])
+
+
+def test_optimizer_step_does_not_advance_the_lr_scheduler():
+    """Paddle's optimizer.step() never steps an LRScheduler and tools/trainer.py:151-153 never calls
+    scheduler.step(): the reference DIN run stays at values[0].  Per-step decay is opt-in."""
+    lin = torch.nn.Linear(3, 2)
+    sched = optim.PiecewiseDecay([1], [0.5, 0.05])
+    opt = optim.SGD(sched, lin.parameters())
+    for _ in range(3):
+        opt.clear_grad()
+        lin(torch.ones(1, 3)).sum().backward()
+        opt.step()
+    assert opt.get_lr() == 0.5 and sched.last_epoch == 0
+    opt.lr_auto_step = True
+    opt.clear_grad()
+    lin(torch.ones(1, 3)).sum().backward()
+    opt.step()
+    assert opt.get_lr() == 0.05

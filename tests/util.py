@@ -87,3 +87,14 @@ def rel_err(a, b):
     a = _np(a)
     b = _np(b)
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def elementwise_excess(a, b, rtol=1e-4, floor_frac=1e-4):
+    """Largest amount by which |a - b| exceeds rtol * |b| + floor, floor = floor_frac * rms(b): an
+    ELEMENT-WISE bound (rel_err above is a tensor max-norm bound, lenient on small entries).  The
+    floor is tied to the tensor's own scale so entries that are zero up to rounding do not fail
+    and a wrong row cannot hide.  <= 0 means every entry is within tolerance."""
+    a = _np(a)
+    b = _np(b)
+    floor = floor_frac * float(np.sqrt(np.mean(np.square(b)))) + 1e-30
+    return float((np.abs(a - b) - rtol * np.abs(b) - floor).max())

@@ -44,6 +44,8 @@ def stage(name, arg):
     dev = "cuda"
     g = torch.Generator().manual_seed(1)
     out = {"stage": name, "arg": arg}
+    if name in ("fwd", "dx") and arg:
+        ops.tc_debug(4, int(arg))
     if name == "fwd":
         for (M, N, K) in [(256, 64, 64), (257, 400, 624), (4096, 400, 400), (300, 1, 400)]:
             x = torch.randn(M, K, generator=g)
@@ -93,10 +95,18 @@ def stage(name, arg):
             fl = 3 * 2.0 * M * K * N
             for bn in ([0] if not arg else [int(v) for v in arg.split(",")]):
                 ops.tc_debug(0, bn)
-                t = _time(lambda: ops.raw_tc_linear_fwd(a, K, WTp, N, b, True, False, True))
-                res["fwd %dx%d bn%d" % (K, N, bn)] = [round(t, 4), round(fl / t / 1e9, 1)]
-                t = _time(lambda: ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, a, False, True, True))
-                res["dx  %dx%d bn%d" % (K, N, bn)] = [round(t, 4), round(fl / t / 1e9, 1)]
+                for bk in (32, 64):
+                    ops.tc_debug(4, bk)
+                    tag = "%dx%d bn%d bk%d" % (K, N, bn, bk)
+                    t = _time(lambda: ops.raw_tc_linear_fwd(a, K, WTp, N, b, True, False, True))
+                    res["fwd " + tag] = [round(t, 4), round(fl / t / 1e9, 1)]
+                    t = _time(lambda: ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, a, False, True, False))
+                    res["dx  " + tag] = [round(t, 4), round(fl / t / 1e9, 1)]
+                    t = _time(lambda: ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, a, False, True, True))
+                    res["dx+colsum " + tag] = [round(t, 4), round(fl / t / 1e9, 1)]
+                    t = _time(lambda: ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, None, True, False, False))
+                    res["dx f32 " + tag] = [round(t, 4), round(fl / t / 1e9, 1)]
+                ops.tc_debug(4, 32)
                 t = _time(lambda: ops.raw_tc_linear_bwd_dw(a, K, gp, N))
                 res["dw  %dx%d bn%d" % (K, N, bn)] = [round(t, 4), round(fl / t / 1e9, 1)]
             ops.tc_debug(0, 0)
@@ -120,7 +130,7 @@ def main():
     if len(sys.argv) > 1:
         stage(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "")
         return
-    plan = [("fwd", ""), ("dx", ""), ("dw", ""), ("perf", "")]
+    plan = [("fwd", "32"), ("fwd", "64"), ("dx", "32"), ("dx", "64"), ("dw", ""), ("perf", "")]
     # descriptor candidates for the MN-major operands if the default is wrong: (lbo_a, lbo_b, sbo)
     sweep = [("dw", "1024,1024,4096"), ("dw", "4096,4096,2048"), ("dw", "2048,2048,1024"),
              ("dw", "1024,1024,2048")]
