@@ -13,6 +13,7 @@ B, F, Dn, D, V = 65536, 26, 13, 16, 100_000_000
 @pytest.fixture(scope="module")
 def problem():
     from paddlerec_b200 import ops
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 40e9:
         pytest.skip("needs ~30 GB of free HBM")
@@ -144,6 +145,7 @@ def _oracle_slice(layer, ids_s, dense_s, label_s, denom):
 def headline_model():
     from paddlerec_b200 import nn as bnn
     from paddlerec_b200.rank.deepfm import net
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 60e9:
         pytest.skip("needs ~45 GB of free HBM")

@@ -166,7 +166,9 @@ def test_tc_many_tiles_per_cta():
     gy = torch.randn(M, K, generator=g_)
     W2 = torch.randn(N, K, generator=g_) / K ** 0.5          # dx [M,N] = g [M,K] @ W2^T
     gp, _ = ops.raw_tc_split_bwd(gy.to(DEV), yp)             # top split masked by relu(y)
-    wantg = gy.double() * (want > 0)
+    # the mask is what the kernel emitted (hi plane > 0): a logit within rounding of 0 may round
+    # to either side of the fp64 value's sign, that is not an error of the backward kernel
+    wantg = gy.double() * (yp[:, :K].double().cpu() > 0)
     assert _err(_join(gp, K), wantg) < 5e-5
     act = torch.randn(M, N, generator=g_).clamp_min(0)
     ap = ops.raw_tc_split(act.to(DEV), ones_col=True)
