@@ -17,8 +17,11 @@ all-reduced; weak scaling (B per GPU fixed).
 Printed JSON (one line, rank 0): see the contract in the task statement; extra keys `roofline`
 (fused gather+FM forward kernel, algorithmic bytes / CUDA-event time inside the timed region
 against MEASURED_PEAKS.json), `cpu_baseline` (oracle port timed on the host cores, N=1 only),
-`e2e` (same metric through DygraphModel.train_forward with HOST buffers: H2D of the batch and
-D2H of the loss inside the timed region), `clocks`, `gpu_launches`.
+`e2e` (same metric through the public API — runner.DevicePrefetcher over pinned HOST batches +
+DygraphModel.train_forward incl. its AUC update: H2D of every batch and D2H of the loss inside the
+timed region), `roofline_step` (CUDA-event time of every kernel family of the step + the
+composite bound of the whole step), `clocks`, `gpu_launches`; at N>1 also `parity` (step-0 loss
+of the sharded model == the fp64 oracle on a slice of the global batch).
 """
 from __future__ import annotations
 
@@ -256,33 +259,28 @@ def run_b200(args, rank, world, local_rank):
         optimizer.step()
         return loss
 
-    pending = {"feeds": None}
-    copy_stream = torch.cuda.Stream(device=dev)
+    from paddlerec_b200 import runner
+    metrics, _ = dm.create_metrics()
+    state = {"pf": None}
 
-    def upload(i):
-        """H2D of batch i on the copy stream (pinned host memory -> copy engine runs beside the
-        kernels of the current step)."""
-        with torch.cuda.stream(copy_stream):
-            feeds = dm.create_feeds(host[i % len(host)], config)
-        return feeds
+    def host_stream():
+        i = 0
+        while True:
+            yield host[i % len(host)]
+            i += 1
 
     def step_e2e(i):
-        """Public API (DygraphModel.create_feeds / create_loss) with HOST batches: the H2D copy of
-        batch i+1 is issued while step i computes (one copy per step, inside the timed region) and
-        the loss is read back every step."""
-        cur = torch.cuda.current_stream()
-        feeds = pending["feeds"] or upload(i)
-        cur.wait_stream(copy_stream)
-        label, ids, dense = feeds
-        for t in feeds:
-            t.record_stream(cur)
+        """The public API with HOST batches: runner.DevicePrefetcher uploads batch i+1 from pinned
+        memory on a copy stream while step i computes (one 17.6 MB H2D per step, inside the timed
+        region); DygraphModel.train_forward = create_feeds + forward + loss + AUC update, as the
+        reference's train_forward (deepfm/dygraph_model.py:75-87); the loss is read back every step."""
+        if state["pf"] is None:
+            state["pf"] = runner.DevicePrefetcher(host_stream(), dm, config)
+        batch = next(state["pf"])
         optimizer.clear_grad()
-        pred = model(ids, dense)
-        loss = dm.create_loss(pred, label)
-        pending["feeds"] = upload(i + 1)
+        loss, _, _ = dm.train_forward(model, metrics, batch, config)
         if prefetch is not None:
-            cur.wait_stream(copy_stream)
-            prefetch(pending["feeds"][1])
+            prefetch(state["pf"].peek()[1])
         scale(loss).backward()
         if finish_prefetch is not None:
             finish_prefetch()
@@ -294,7 +292,7 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, collect_events=False):
+    def timed(fn, steps, warmup, collect_events=False, event_filter=None):
         for i in range(warmup):
             fn(i)
         barrier()
@@ -302,6 +300,7 @@ def run_b200(args, rank, world, local_rank):
         if rank == 0:
             sampler.start()
         ops.EVENTS = [] if collect_events else None
+        ops.EVENT_FILTER = event_filter
         n0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -320,12 +319,21 @@ def run_b200(args, rank, world, local_rank):
         return ms, launches, events, clocks
 
     K, W = args.steps, max(args.warmup, 3)
-    ms, launches, events, clocks = timed(step_resident, K, W, collect_events=True)
+    parity = parity_bit(args, model, dm, resident, label_f, rank, world, dev) if world > 1 else None
+    ms, launches, events, clocks = timed(step_resident, K, W, collect_events=True,
+                                         event_filter={"embed_fm_fwd"})
     value = args.batch * world * K / (ms / 1e3)
     k_ms = [s.elapsed_time(e) for (name, s, e) in events if name == "embed_fm_fwd"]
     kernel_ms = sum(k_ms) / max(len(k_ms), 1)
     ms_e2e, _, _, _ = timed(step_e2e, K, 3)
     e2e_value = args.batch * world * K / (ms_e2e / 1e3)
+    # a third, short pass with an event pair around EVERY kernel family: the step's breakdown
+    kb = min(K, 10)
+    ms_b, _, ev_all, _ = timed(step_resident, kb, 2, collect_events=True)
+    per = {}
+    for name, s0, e0 in ev_all:
+        per[name] = per.get(name, 0.0) + s0.elapsed_time(e0)
+    per = {k: v / kb for k, v in per.items()}
 
     if rank != 0:
         return
@@ -354,13 +362,127 @@ def run_b200(args, rank, world, local_rank):
                 "h2d_bytes_per_step": args.batch * (F_SPARSE * 8 + N_DENSE * 4 + 8),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks,
+        "roofline_step": roofline_step(args, per, ms / K, ms_b / kb, world),
     }
+    if parity is not None:
+        line["parity"] = parity
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args)
         except Exception as exc:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
+
+
+def roofline_step(args, per_ms, step_ms, step_ms_with_events, world):
+    """Where the step goes, and how far the WHOLE step is from its own bound.
+
+    per_ms: CUDA-event time per step of every kernel family (event pairs around each C-ABI call;
+    the calls of a family are summed).  Composite bound = tower GEMM flops at the measured
+    SUSTAINED bf16 rate + the algorithmic HBM bytes of the memory-bound kernels at the measured
+    copy bandwidth (SURVEY.md §8(d) per-sample figures; no overlap credit):
+      tower   3 (bf16x3) x 3 (fwd, dX, dW) x 2 M sum(K N) flops
+      K1      4532 B/sample at D=16 (ids + dense + rows + w1 + feat + y)
+      K2      7696 B/sample (ids + dfeat + feat re-read + row RMW)
+      Adam    distinct rows x 3 arrays (w, m, v) x G cols x 4 B x 2 (read + write)
+      planes  every tower activation is written once and read by the next GEMM, the dW GEMM and the
+              ReLU mask (4 B/element each way), dfeat fp32 out
+    """
+    D, B, F, Dn = args.dim, args.batch, F_SPARSE, N_DENSE
+    fc = [int(x) for x in args.fc.split(",")]
+    sizes = [(F + Dn) * D] + fc + [1]
+    kn = sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1))
+    flops = 3 * 3 * 2.0 * B * kn
+    peaks = {}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            peaks = json.load(fh)
+    tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    G = (D + 1 + 3) // 4 * 4
+    k1 = algorithmic_bytes_fwd(D) * B
+    k2 = (F * 8 + (F + Dn) * 4 * D + F * 4 * D + F * 2 * 4 * D) * B
+    adam = 0.98 * F * B * 3 * G * 4 * 2
+    act = sum(sizes[:-1]) * 4 * B           # planes of every layer input (same bytes as fp32)
+    planes = act * 3 + sizes[0] * 4 * B * 2  # written, read by fwd GEMM + dW GEMM (+mask) ; dfeat out/in
+    hbm_bytes = k1 + k2 + adam + planes
+    bound_ms = flops / (tf * 1e12) * 1e3 + hbm_bytes / (hbm * 1e9) * 1e3
+    top = sorted(per_ms.items(), key=lambda kv: -kv[1])
+    gemm_ms = sum(v for k, v in per_ms.items() if k in ("tc_linear_fwd", "tc_linear_bwd_dx",
+                                                         "tc_linear_bwd_dw"))
+    out = {
+        "per_kernel_ms": {k: round(v, 4) for k, v in top},
+        "sum_of_kernels_ms": round(sum(per_ms.values()), 4),
+        "step_ms": round(step_ms, 4), "step_ms_with_events": round(step_ms_with_events, 4),
+        "tower_gemm": {"ms": round(gemm_ms, 4), "flops": flops,
+                       "achieved_tflops": round(flops / (gemm_ms / 1e3) / 1e12, 1) if gemm_ms else None,
+                       "peak_tflops_sustained": tf,
+                       "frac": round(flops / (gemm_ms / 1e3) / 1e12 / tf, 3) if gemm_ms else None,
+                       "kernels": "tc_gemm_kmajor_kernel / tc_gemm_dw_kernel (tcgen05 + TMEM + TMA)"},
+        "composite_bound": {"gemm_ms": round(flops / (tf * 1e12) * 1e3, 4),
+                            "hbm_ms": round(hbm_bytes / (hbm * 1e9) * 1e3, 4),
+                            "hbm_bytes": int(hbm_bytes), "bound_ms": round(bound_ms, 4),
+                            "frac_of_step": round(bound_ms / step_ms, 3)},
+    }
+    if world > 1:
+        out["note"] = ("N>1: embed_fm_fwd reads the RECEIVED rows (contiguous), the random gather is "
+                       "the owner-side `gather`; exchange bytes per GPU per direction = "
+                       "(N-1)/N * B*F*(8 + 4G) = %d" % int((world - 1) / world * B * F * (8 + 4 * G)))
+    return out
+
+
+def parity_bit(args, model, dm, resident, label_f, rank, world, dev):
+    """N>1 correctness bit carried by the scaling run itself: the sharded model's step-0 loss on
+    rank 0's first 4096 samples must equal the fp64 oracle evaluated on those samples with the
+    touched rows fetched from their owners (a forward through the NCCL exchange, no optimizer)."""
+    import torch.distributed as dist
+    n = min(4096, args.batch)
+    label, ids, dense = resident[0]
+    with torch.no_grad():
+        pred = model(ids, dense)          # collective: every rank runs its own batch
+    loss_dev = float(dm.create_loss(pred[:n], label_f[0][:n]))
+    # owners serve rank 0's rows: all-gather of the (small) id slice, each rank contributes its rows
+    sl = ids[:n].contiguous()
+    dist.broadcast(sl, src=0)
+    flat = sl.reshape(-1)
+    uniq = torch.unique(flat[flat != 0])
+    mine = uniq[uniq % world == rank]
+    tab = model.fm._fused
+    rows = tab.weight[mine // world, :tab.embedding_dim + 1].contiguous()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.numel()], device=dev))
+    cap = int(max(int(t) for t in sizes))
+    pad_ids = torch.zeros(cap, dtype=torch.int64, device=dev)
+    pad_rows = torch.zeros(cap, rows.shape[1], device=dev)
+    pad_ids[:mine.numel()], pad_rows[:mine.numel()] = mine, rows
+    all_ids = [torch.empty_like(pad_ids) for _ in range(world)]
+    all_rows = [torch.empty_like(pad_rows) for _ in range(world)]
+    dist.all_gather(all_ids, pad_ids)
+    dist.all_gather(all_rows, pad_rows)
+    if rank != 0:
+        return None
+    from oracle import nets
+    gid = torch.cat([a[:int(k)] for a, k in zip(all_ids, sizes)])
+    grow = torch.cat([a[:int(k)] for a, k in zip(all_rows, sizes)])
+    order = torch.argsort(gid)
+    gid, grow = gid[order], grow[order]
+    Dd = tab.embedding_dim
+    remap = (torch.searchsorted(gid, sl.reshape(-1)).reshape(sl.shape) + 1) * (sl != 0)
+    p = {"fm.embedding.weight": torch.cat([torch.zeros(1, Dd, device=dev), grow[:, :Dd]]),
+         "fm.embedding_one.weight": torch.cat([torch.zeros(1, 1, device=dev), grow[:, Dd:Dd + 1]])}
+    for k, v in model.state_dict().items():
+        if not k.startswith("fm.embedding"):
+            p[k] = v
+    p = {k: v.detach().double().cpu() for k, v in p.items()}
+    remap = remap.cpu()
+    ref = nets.deepfm_forward(p, [remap[:, i:i + 1] for i in range(remap.shape[1])],
+                              dense[:n].double().cpu(), len([int(x) for x in args.fc.split(",")]))
+    loss_ref = float(nets.log_loss(ref, label_f[0][:n].double().cpu()).mean())
+    err = float((pred[:n].double().cpu() - ref).abs().max())
+    return {"samples": n, "loss": loss_dev, "oracle_loss": loss_ref,
+            "max_abs_pred_err": err, "ok": bool(abs(loss_dev - loss_ref) < 1e-4 * abs(loss_ref)
+                                                and err < 1e-4)}
 
 
 def cpu_baseline(args):

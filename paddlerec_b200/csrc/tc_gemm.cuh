@@ -41,6 +41,7 @@ constexpr int kUK = 16;          // UMMA K for 16-bit operands
 constexpr int kThreads = 192;    // dW kernel: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kEpiWarps = 8;     // K-major kernel: two epilogue warpgroups (alternate 32-col chunks)
 constexpr int kThreadsK = 64 + 32 * kEpiWarps;
+constexpr uint32_t kStagingPerWarp = 4096;   // one 32x32 chunk: hi + lo bf16 tiles, or one fp32 tile
 constexpr int kTmemCols = 512;   // whole TMEM of the SM (one CTA per SM by shared-memory size)
 constexpr int kAccStride = 256;  // column offset of the second accumulator stage
 constexpr int kMaxBN = 256;
@@ -199,6 +200,9 @@ struct Epilogue {
   // also write out_planes[m, N] = 1.0 (hi) / 0 (lo): the column of ones that makes the dW GEMM of
   // the next layer produce its bias gradient as row N (needs ldp > N)
   int ones_col;
+  // outputs that leave the SM as TMA bulk stores of swizzled shared-memory tiles (host decides:
+  // needs 16-byte aligned base and pitch; at most one of the two uses the staging buffer)
+  int tma_planes, tma_f32;
 };
 
 __device__ __forceinline__ void split_bf16(float x, float& hi_f, __nv_bfloat16& hi,
@@ -235,10 +239,57 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
+// ---- staged outputs: the warp's 32x32 chunk is written to shared memory in the swizzled layout
+// the TMA engine expects and leaves as ONE bulk tensor store per plane (coalesced, asynchronous,
+// no L1 involvement; rows/columns outside the matrix are clipped by the tensor map).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B): hi tile at sbuf, lo tile at sbuf + 2048
+__device__ __forceinline__ void stage_planes(uint32_t sbuf, int lane, const float (&v)[32]) {
+  const uint32_t rowoff = (uint32_t)lane * 64u;
+  const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pack2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], h[j], l[j]);
+    const uint32_t off = rowoff + (((uint32_t)g ^ sw) << 4);
+    st_shared_v4(sbuf + off, h[0], h[1], h[2], h[3]);
+    st_shared_v4(sbuf + 2048u + off, l[0], l[1], l[2], l[3]);
+  }
+}
+// 32 rows x 32 fp32 (128-byte rows, SWIZZLE_128B) at sbuf
+__device__ __forceinline__ void stage_f32(uint32_t sbuf, int lane, const float (&v)[32]) {
+  const uint32_t rowoff = (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    st_shared_v4(sbuf + rowoff + (((uint32_t)g ^ sw) << 4), __float_as_uint(v[4 * g]),
+                 __float_as_uint(v[4 * g + 1]), __float_as_uint(v[4 * g + 2]),
+                 __float_as_uint(v[4 * g + 3]));
+}
+
 // Full 32-column chunk, everything 16-byte aligned: vector loads/stores only.  `mk` holds the 32
 // mask values (bf16 pairs) fetched before the TMEM wait.
 __device__ __forceinline__ void epilogue_fast(const Epilogue& ep, float (&v)[32], int64_t row,
-                                              int col0, const uint4 (&mk)[4]) {
+                                              int col0, const uint4 (&mk)[4], bool store_f32,
+                                              bool store_planes) {
   if (ep.bias != nullptr) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -274,12 +325,12 @@ __device__ __forceinline__ void epilogue_fast(const Epilogue& ep, float (&v)[32]
       }
     }
   }
-  if (ep.out_f32 != nullptr) {
+  if (ep.out_f32 != nullptr && store_f32) {
     float4* o = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + col0);
 #pragma unroll
     for (int g = 0; g < 8; ++g) o[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
   }
-  if (ep.out_planes != nullptr) {
+  if (ep.out_planes != nullptr && store_planes) {
     uint4* oh = reinterpret_cast<uint4*>(ep.out_planes + row * 2 * ep.ldp + col0);
     uint4* ol = reinterpret_cast<uint4*>(ep.out_planes + row * 2 * ep.ldp + ep.ldp + col0);
 #pragma unroll
@@ -297,7 +348,8 @@ __device__ __forceinline__ void epilogue_fast(const Epilogue& ep, float (&v)[32]
 // that exist in the matrix; row_ok = the row exists.
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32], int64_t row,
                                                bool row_ok, int col0, int n_valid, int lane,
-                                               float* s_colsum /* [32] for this warp or null */) {
+                                               float* s_colsum /* [32] for this warp or null */,
+                                               bool store_f32 = true, bool store_planes = true) {
   if (ep.bias != nullptr || ep.cross_x0 != nullptr || ep.relu || ep.mask_src != nullptr) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {   // groups of 4 columns
@@ -356,7 +408,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
   if (row_ok) {
-    if (ep.out_f32 != nullptr) {
+    if (ep.out_f32 != nullptr && store_f32) {
       float* o = ep.out_f32 + row * ep.ld_f32 + col0;
       const bool vec_ok = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
 #pragma unroll
@@ -371,7 +423,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
         }
       }
     }
-    if (ep.out_planes != nullptr) {
+    if (ep.out_planes != nullptr && store_planes) {
       __nv_bfloat16* oh = ep.out_planes + row * 2 * ep.ldp + col0;
       __nv_bfloat16* ol = oh + ep.ldp;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(oh) | reinterpret_cast<uintptr_t>(ol)) & 15u) == 0;
@@ -421,7 +473,10 @@ __global__ void __launch_bounds__(kThreadsK, 1)
 tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                       const __grid_constant__ CUtensorMap tmA_lo,
                       const __grid_constant__ CUtensorMap tmB_hi,
-                      const __grid_constant__ CUtensorMap tmB_lo, int M, int N, int K, int BN,
+                      const __grid_constant__ CUtensorMap tmB_lo,
+                      const __grid_constant__ CUtensorMap tmO_hi,
+                      const __grid_constant__ CUtensorMap tmO_lo,
+                      const __grid_constant__ CUtensorMap tmO_f32, int M, int N, int K, int BN,
                       int stages, Epilogue ep) {
   constexpr uint32_t kRow = BK * 2;                       // bytes per operand row in a stage
   constexpr uint32_t kLayout = BK == 64 ? 2u : 4u;        // SWIZZLE_128B / SWIZZLE_64B
@@ -433,12 +488,15 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t a_bytes = kBM * kRow;
   const uint32_t b_bytes = (uint32_t)BN * kRow;
   const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;
-  const uint32_t bar0 = base + (uint32_t)stages * stage_bytes;
-  // barrier block: full[stages] empty[stages] tfull[2] tempty[2] | tmem ptr | colsum scratch
+  // [stages][output staging: 4 KB per epilogue warp][barriers][tmem ptr][colsum scratch]
+  const uint32_t stage_end = (uint32_t)stages * stage_bytes;
+  const uint32_t staging = base + stage_end;
+  const uint32_t bar_off = stage_end + kEpiWarps * kStagingPerWarp;
+  const uint32_t bar0 = base + bar_off;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8u * stages;
   const uint32_t bar_tfull = bar0 + 16u * stages, bar_tempty = bar_tfull + 16u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)stages * stage_bytes + 16 * stages + 32);
-  float* s_colsum = reinterpret_cast<float*>(sm + (size_t)stages * stage_bytes + 16 * stages + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)bar_off + 16 * stages + 32);
+  float* s_colsum = reinterpret_cast<float*>(sm + (size_t)bar_off + 16 * stages + 64);
   // s_colsum: [4 lane quarters][kMaxBN], only with ep.colsum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -448,6 +506,8 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    if (ep.tma_planes) { prefetch_tmap(&tmO_hi); prefetch_tmap(&tmO_lo); }
+    if (ep.tma_f32) prefetch_tmap(&tmO_f32);
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full + 8u * s, 1);
       mbar_init(bar_empty + 8u * s, 1);
@@ -530,6 +590,8 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool want_colsum = ep.colsum != nullptr;
+    const bool tma_p = ep.tma_planes != 0 && !want_colsum, tma_f = ep.tma_f32 != 0 && !want_colsum;
+    const uint32_t sbuf = staging + (uint32_t)(warp - 2) * kStagingPerWarp;
     const bool base_aligned =
         (ep.out_f32 == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_f32) | (ep.ld_f32 * 4)) & 15u) == 0) &&
         (ep.out_planes == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_planes) | (ep.ldp * 2)) & 15u) == 0) &&
@@ -567,11 +629,31 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        // outputs staged for TMA are stored below; the others directly from registers
         if (fast)
-          epilogue_fast(ep, v, row, n0 + c0, mk);
+          epilogue_fast(ep, v, row, n0 + c0, mk, !tma_f, !tma_p);
         else
           epilogue_chunk(ep, v, row, row_ok, n0 + c0, nv, lane,
-                         want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr);
+                         want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr, !tma_f, !tma_p);
+        if (tma_p || tma_f) {
+          if (lane == 0) bulk_wait_read0();      // the previous store has finished reading sbuf
+          __syncwarp();
+          if (tma_p)
+            stage_planes(sbuf, lane, v);
+          else
+            stage_f32(sbuf, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (tma_p) {
+              tma_store_2d(&tmO_hi, sbuf, n0 + c0, m0 + q * 32);
+              tma_store_2d(&tmO_lo, sbuf + 2048u, n0 + c0, m0 + q * 32);
+            } else {
+              tma_store_2d(&tmO_f32, sbuf, n0 + c0, m0 + q * 32);
+            }
+            bulk_commit();
+          }
+        }
       }
       if (ep.ones_col && ep.out_planes != nullptr && row_ok && half == 0 && n0 + n_tile == N) {
         __nv_bfloat16* oh = ep.out_planes + row * 2 * ep.ldp + N;
@@ -594,6 +676,7 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if ((tma_p || tma_f) && lane == 0) bulk_wait0();   // shared memory must outlive the stores
   }
   tc_fence_before();
   __syncthreads();
@@ -852,23 +935,26 @@ static EncodeTiledFn encode_tiled_fn() {
 // bf16 matrix [rows, width] with row pitch `pitch_elems`; box = box_w x box_rows, 128B swizzle,
 // out-of-bounds elements read as zero.
 static int make_map(CUtensorMap* m, const void* base, int64_t width, int64_t rows,
-                    int64_t pitch_elems, int box_w, int box_rows) {
-  const CUtensorMapSwizzle swz = box_w == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+                    int64_t pitch_elems, int box_w, int box_rows, int elem_bytes = 2) {
+  const CUtensorMapSwizzle swz = box_w * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                           : CU_TENSOR_MAP_SWIZZLE_64B;
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) {
     set_error("tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
     return B200REC_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (pitch_elems * 2) % 16 != 0) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (pitch_elems * elem_bytes) % 16 != 0) {
     set_error("tc_gemm: operand planes must be 16-byte aligned with a pitch multiple of 8 "
               "(base %p, pitch %lld)", base, (long long)pitch_elems);
     return B200REC_ERR_INVALID;
   }
   const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * elem_bytes};
   const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+  const CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                            : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         2, const_cast<void*>(base), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -881,7 +967,9 @@ static int make_map(CUtensorMap* m, const void* base, int64_t width, int64_t row
 }
 
 static int pick_bn(int N) {
-  const int tiles = (N + kMaxBN - 1) / kMaxBN;
+  // <= 224 columns: two 128-byte-row stages + the output staging must fit 227 KB of shared memory
+  constexpr int kCap = 224;
+  const int tiles = (N + kCap - 1) / kCap;
   int bn = (N + tiles - 1) / tiles;
   bn = (bn + 15) & ~15;
   return bn < 16 ? 16 : bn;
@@ -889,6 +977,7 @@ static int pick_bn(int N) {
 
 static DwDebug g_dw_debug = {0u, 0u, 0u};
 static int g_bn_override = 0;
+static int g_tma_store = 1;   // epilogue outputs through TMA bulk stores (0: direct stores)
 static int g_bk = 64;   // k-block of the K-major kernel: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
 
 // D = A . B^T with A planes [M, 2*lda] (logical [M,K]) and B planes [N, 2*ldb] (logical [N,K]).
@@ -900,10 +989,12 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
   const int BN = g_bn_override > 0 ? g_bn_override : pick_bn(N);
   const int BK = g_bk == 64 ? 64 : 32;
   const uint32_t stage_bytes = (2u * kBM + 2u * (uint32_t)BN) * (uint32_t)BK * 2u;
-  int stages = (int)((kSmemBudget - 4096u - 16u * kMaxBN) / stage_bytes);
+  const uint32_t staging_bytes = kEpiWarps * kStagingPerWarp;
+  int stages = (int)((kSmemBudget - 4096u - 16u * kMaxBN - staging_bytes) / stage_bytes);
   stages = stages > 8 ? 8 : stages;
   B200_REQUIRE(stages >= 2, "tc_gemm: tile does not fit shared memory");
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 64 + 16 * kMaxBN + 1024;
+  const size_t smem =
+      (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 64 + 16 * kMaxBN + 1024;
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(A);
   const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(B);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -912,6 +1003,23 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
   if ((rc = make_map(&ma_lo, a + lda, K, M, 2 * lda, BK, kBM)) != B200REC_OK) return rc;
   if ((rc = make_map(&mb_hi, b, K, N, 2 * ldb, BK, BN)) != B200REC_OK) return rc;
   if ((rc = make_map(&mb_lo, b + ldb, K, N, 2 * ldb, BK, BN)) != B200REC_OK) return rc;
+  // outputs through TMA stores where base and pitch allow it (else: direct stores from registers)
+  Epilogue e2 = ep;
+  CUtensorMap mo_hi = ma_hi, mo_lo = ma_hi, mo_f32 = ma_hi;   // placeholders when unused
+  e2.tma_planes = e2.tma_f32 = 0;
+  if (g_tma_store && ep.colsum == nullptr) {
+    if (ep.out_planes != nullptr && (reinterpret_cast<uintptr_t>(ep.out_planes) & 15u) == 0 &&
+        ep.ldp % 8 == 0) {
+      if ((rc = make_map(&mo_hi, ep.out_planes, N, M, 2 * ep.ldp, 32, 32)) != B200REC_OK) return rc;
+      if ((rc = make_map(&mo_lo, ep.out_planes + ep.ldp, N, M, 2 * ep.ldp, 32, 32)) != B200REC_OK)
+        return rc;
+      e2.tma_planes = 1;
+    } else if (ep.out_planes == nullptr && ep.out_f32 != nullptr &&
+               (reinterpret_cast<uintptr_t>(ep.out_f32) & 15u) == 0 && ep.ld_f32 % 4 == 0) {
+      if ((rc = make_map(&mo_f32, ep.out_f32, N, M, ep.ld_f32, 32, 32, 4)) != B200REC_OK) return rc;
+      e2.tma_f32 = 1;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor_kernel<64>,
@@ -923,11 +1031,11 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
   const int tiles = (int)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (BK == 64)
-    tc_gemm_kmajor_kernel<64><<<grid, kThreadsK, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, (int)M, N,
-                                                             K, BN, stages, ep);
+    tc_gemm_kmajor_kernel<64><<<grid, kThreadsK, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo,
+                                                             mo_f32, (int)M, N, K, BN, stages, e2);
   else
-    tc_gemm_kmajor_kernel<32><<<grid, kThreadsK, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, (int)M, N,
-                                                             K, BN, stages, ep);
+    tc_gemm_kmajor_kernel<32><<<grid, kThreadsK, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo,
+                                                             mo_f32, (int)M, N, K, BN, stages, e2);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

@@ -35,14 +35,14 @@ class Auc:
         y = labels.reshape(-1).to(p.device)
         nb = self.num_thresholds + 1
         idx = (p.detach().float() * self.num_thresholds).to(torch.int64).clamp_(0, nb - 1)
-        pos_mask = y != 0
-        pos = torch.bincount(idx[pos_mask], minlength=nb)
-        neg = torch.bincount(idx[~pos_mask], minlength=nb)
         if self._pos is None:
-            self._pos, self._neg = pos, neg
-        else:
-            self._pos += pos
-            self._neg += neg
+            self._pos = torch.zeros(nb, dtype=torch.int64, device=p.device)
+            self._neg = torch.zeros(nb, dtype=torch.int64, device=p.device)
+        # index_add_ into preallocated histograms: no data-dependent shape, hence no host sync
+        # (boolean indexing / bincount would synchronise every step like the reference's .numpy())
+        is_pos = (y != 0).to(torch.int64)
+        self._pos.index_add_(0, idx, is_pos)
+        self._neg.index_add_(0, idx, 1 - is_pos)
 
     def stats(self):
         """(stat_pos, stat_neg) int64 tensors — what utils_single.py:160-206 all-reduces."""

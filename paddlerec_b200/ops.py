@@ -47,8 +47,10 @@ KERNELS_PER_CALL = {
     "tc_prep_weight": 1, "tc_linear_fwd": 1, "tc_cross_fwd": 1, "tc_linear_bwd_dx": 1,
     "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
 }
-# When set to a list, (name, start_event, end_event) triples are appended around selected kernels.
+# When set to a list, (name, start_event, end_event) triples are appended around the raw_* calls
+# (all of them, or only the names in EVENT_FILTER when that is a set) — bench.py's per-kernel times.
 EVENTS = None
+EVENT_FILTER = None
 
 
 def _count(name: str) -> None:
@@ -61,14 +63,15 @@ class _Timed:
         self.name = name
 
     def __enter__(self):
-        if EVENTS is not None:
+        self.on = EVENTS is not None and (EVENT_FILTER is None or self.name in EVENT_FILTER)
+        if self.on:
             self.start = torch.cuda.Event(enable_timing=True)
             self.end = torch.cuda.Event(enable_timing=True)
             self.start.record()
         return self
 
     def __exit__(self, *exc):
-        if EVENTS is not None:
+        if self.on and EVENTS is not None:
             self.end.record()
             EVENTS.append((self.name, self.start, self.end))
         return False
@@ -545,14 +548,15 @@ def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int, bias_row: bool = Fa
     M = a_planes.shape[0]
     dev = a_planes.device
     if bias_row:
-        ext = raw_tc_linear_bwd_dw(a_planes, K + 1, g_planes, N)
-        return ext[:K], ext[K]
+        K = K + 1
     dW = torch.empty(K, N, dtype=torch.float32, device=dev)
     ws = _tc_bwd_ws(M, K, N, dev)
     check(lib.b200rec_tc_linear_bwd_dw(ptr(a_planes), a_planes.shape[1] // 2, ptr(g_planes),
                                        g_planes.shape[1] // 2, ptr(dW), M, K, N, ptr(ws),
                                        ws.numel(), _stream()), "tc_linear_bwd_dw")
     _count("tc_linear_bwd_dw")
+    if bias_row:
+        return dW[:K - 1], dW[K - 1]
     return dW
 
 
@@ -1055,3 +1059,25 @@ def gather(W, ids, padding_idx, sink, hook):
 
 def cross_v2(x0, xl, W, bias, mm, precision="fp32"):
     return _CrossV2.apply(x0, xl, W, bias, mm, precision)
+
+
+# ---- per-kernel CUDA-event timing of every entry point (bench.py roofline_step) -----------------
+def _wrap_timed(fn, name):
+    import functools
+
+    @functools.wraps(fn)
+    def timed(*a, **k):
+        if EVENTS is None:
+            return fn(*a, **k)
+        with _Timed(name):
+            return fn(*a, **k)
+    return timed
+
+
+for _n in ("group_ids", "embed_fm_bwd", "gather", "gather_pool_sum", "segment_reduce", "sparse_sgd",
+           "sparse_adam", "sparse_adagrad", "cross_v2_fwd", "cross_v2_bwd", "shard_bucketize",
+           "tc_split", "tc_split_bwd", "tc_prep_weight", "tc_linear_fwd", "tc_cross_fwd",
+           "tc_linear_bwd_dx", "tc_linear_bwd_dw", "din_attn_fwd", "din_attn_bwd", "tower_split",
+           "tower_relu_bwd_split", "tower_prep_weight", "tower_fold_dw"):
+    globals()["raw_" + _n] = _wrap_timed(globals()["raw_" + _n], _n)
+del _n

@@ -152,6 +152,49 @@ def load_model(model_path, net, prefix="rec", optimizer=None):
         checkpoint.load_pdopt(optimizer, net, opt_path)
 
 
+class DevicePrefetcher:
+    """Iterates a host-batch iterable and yields the batches as DEVICE tensors (the output of
+    `dy_model_class.create_feeds`), uploading batch i+1 on a copy stream while the caller's step i
+    runs on the compute stream — pinned host memory makes the copy asynchronous, so the copy engine
+    works beside the kernels instead of in front of them.  `train_forward` accepts the yielded
+    tuple unchanged (create_feeds is a no-op on device tensors).  `peek()` returns the batch that
+    the next iteration will yield (the sharded model plans its id exchange from it)."""
+
+    def __init__(self, batches, dy_model_class, config):
+        self._it = iter(batches)
+        self._dm, self._config = dy_model_class, config
+        self._copy = torch.cuda.Stream()
+        self._next = None
+        self._upload()
+
+    def _upload(self):
+        try:
+            host = next(self._it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self._copy):
+            self._next = tuple(self._dm.create_feeds(host, self._config))
+
+    def peek(self):
+        return self._next
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self._copy)
+        batch = self._next
+        for t in batch:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(cur)
+        self._upload()
+        return batch
+
+
 # ---- the loop (trainer.py:49-223) ---------------------------------------------------------------
 def parse_args(argv=None):
     p = argparse.ArgumentParser("PaddleRec-shaped dygraph trainer on the b200rec engine")

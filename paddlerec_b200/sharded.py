@@ -20,6 +20,7 @@ inject a torch stand-in for the kernel set — the product default `ops` has no 
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass
 from typing import List, Optional
@@ -31,6 +32,11 @@ import torch.nn as tnn
 from . import nn as bnn
 from . import ops as _cuda_ops
 from . import optim
+
+
+def _timed(name: str):
+    """CUDA-event pair around a collective when bench.py collects per-kernel times (CUDA only)."""
+    return _cuda_ops._Timed(name) if torch.cuda.is_available() else contextlib.nullcontext()
 
 
 def shard_rows(V: int, rank: int, world: int) -> int:
@@ -144,8 +150,9 @@ class ShardExchange:
         returns [n, D] in bucket order."""
         rows_out = self.k.raw_gather(shard, plan.recv_ids, local_pad, D)
         rows_in = torch.empty(plan.n, rows_out.shape[-1], dtype=shard.dtype, device=shard.device)
-        dist.all_to_all_single(rows_in, rows_out, plan.send_splits, plan.recv_splits,
-                               group=self.group)
+        with _timed("nccl_a2a_rows"):
+            dist.all_to_all_single(rows_in, rows_out, plan.send_splits, plan.recv_splits,
+                                   group=self.group)
         return rows_in
 
     def push(self, plan: ExchangePlan, grads_bucket_order: torch.Tensor) -> torch.Tensor:
@@ -154,8 +161,9 @@ class ShardExchange:
         D = grads_bucket_order.shape[1]
         out = torch.empty(plan.recv_ids.numel(), D, dtype=grads_bucket_order.dtype,
                           device=grads_bucket_order.device)
-        dist.all_to_all_single(out, grads_bucket_order.contiguous(), plan.recv_splits,
-                               plan.send_splits, group=self.group)
+        with _timed("nccl_a2a_grads"):
+            dist.all_to_all_single(out, grads_bucket_order.contiguous(), plan.recv_splits,
+                                   plan.send_splits, group=self.group)
         return out
 
     def owner_reduce(self, plan: ExchangePlan, grads: torch.Tensor, V_loc: int, local_pad: int):
@@ -420,12 +428,13 @@ class DistributedOptimizer:
     def step(self):
         grads = [p.grad for p in self._dense if p.grad is not None]
         if grads and self.world > 1:
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat, group=self.group)
-            off = 0
-            for g in grads:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+            with _timed("nccl_allreduce_dense"):
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat, group=self.group)
+                off = 0
+                for g in grads:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
         self.inner.step()
 
 

@@ -58,7 +58,7 @@ def test_tc_linear_fwd(M, N, K, relu):
     assert y2 is None and _err(_join(yp2, N), want2) < 5e-5
 
 
-@pytest.mark.parametrize("bn", [16, 64, 128, 256])
+@pytest.mark.parametrize("bn", [16, 64, 128, 224])
 @pytest.mark.parametrize("bk", [32, 64])
 def test_tc_linear_fwd_tile_shapes(bn, bk):
     """Forced tile widths and both k-block / swizzle variants (64 B and 128 B rows)."""
@@ -73,11 +73,17 @@ def test_tc_linear_fwd_tile_shapes(bn, bk):
     ops.tc_debug(4, bk)
     try:
         y, _ = ops.raw_tc_linear_fwd(a, K, WTp, N, None, False, True, False)
+        _, yp = ops.raw_tc_linear_fwd(a, K, WTp, N, None, False, False, True)
+        ops.tc_debug(5, 0)      # direct register stores instead of TMA bulk stores
+        y2, yp2 = ops.raw_tc_linear_fwd(a, K, WTp, N, None, False, True, True)
         torch.cuda.synchronize()
     finally:
         ops.tc_debug(0, 0)
         ops.tc_debug(4, 64)
-    assert _err(y, x.double() @ W.double()) < 5e-5
+        ops.tc_debug(5, 1)
+    want = x.double() @ W.double()
+    assert _err(y, want) < 5e-5 and _err(_join(yp, N), want) < 5e-5
+    assert torch.equal(y, y2) and torch.equal(yp[:, :N], yp2[:, :N])
 
 
 @pytest.mark.parametrize("M,K,N", [(257, 624, 400), (5000, 400, 400), (300, 127, 1)])
@@ -207,11 +213,24 @@ def test_tower_backends_match_fp64(backend, last_act, sizes):
     from paddlerec_b200 import tower
     from tests.util import rel_err
     g = torch.Generator().manual_seed(11)
-    M = 1000
+    M = 1100
     L = len(sizes) - 1
     x = torch.randn(M, sizes[0], generator=g)
     Ws = [torch.randn(sizes[i], sizes[i + 1], generator=g) / sizes[i] ** 0.5 for i in range(L)]
     bs = [torch.randn(sizes[i + 1], generator=g) * 0.1 for i in range(L)]
+    # ReLU is not differentiable at 0: a pre-activation within rounding of 0 may land on either
+    # side in fp32 and flip that unit's whole gradient path, which is not an error of either
+    # implementation.  Drop the (few) samples that have any pre-activation that close to 0.
+    keep = torch.ones(M, dtype=torch.bool)
+    h = x.double()
+    for i in range(L):
+        z = h @ Ws[i].double() + bs[i].double()
+        if i < L - 1 or last_act:
+            keep &= (z.abs() > 1e-4).all(1)
+            h = torch.relu(z)
+    x = x[keep].contiguous()
+    M = x.shape[0]
+    assert 700 < M < 1100
     xd = x.double().requires_grad_(True)
     Wd = [w.double().requires_grad_(True) for w in Ws]
     bd = [b.double().requires_grad_(True) for b in bs]

@@ -1,32 +1,16 @@
-#!/usr/bin/env bash
-# One-call GPU validation of the tree, for `gpurun --timeout 1500 -- 'bash tools/gpu_validate.sh'`.
-# Every stage has its own timeout and writes to gpurun_out/, so a slow box or a failing stage never
-# hides the others (round 1 lost its last run to a single tight timeout).  Stages, ~10 GPU-minutes:
-#   1 full parity suite (no -x, slowest tests listed)      gpurun_out/validate_tests.log
-#   2 experimental kernels (B200REC_TEST_EXPERIMENTAL=1)    gpurun_out/validate_experimental.log
-#   3 K6 / hash_keys micro-benchmarks, default and v2       gpurun_out/validate_dot_bench*.jsonl
-#   4 smoke()                                               gpurun_out/validate_smoke.log
-#   5 bench.py (N=1) and its reference arm                  gpurun_out/validate_bench*.json
-#   6 ncu launch list of one bench step                     gpurun_out/validate_launches.csv
+#!/bin/bash
+# One-GPU validation pass used during round 2 (run under gpurun): kernel tests, the oracle-backed
+# headline-config tests, the bench line, the per-launch list and one full ncu capture of the
+# tcgen05 GEMM.  Outputs land in gpurun_out/.
 set -u
-cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-RC=gpurun_out/validate_rc.log
-: > "$RC"
-stage() {  # stage <name> <timeout-seconds> <command...>
-  local name=$1 t=$2
-  shift 2
-  local t0=$SECONDS
-  timeout "$t" "$@"
-  echo "$name rc=$? seconds=$((SECONDS - t0))" >> "$RC"
-}
-stage tests 900 bash -c 'python -m pytest tests -m gpu -q --durations=15 > gpurun_out/validate_tests.log 2>&1'
-stage experimental 240 bash -c 'B200REC_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "v2" > gpurun_out/validate_experimental.log 2>&1'
-stage dot_bench 180 bash -c 'python tools/dot_bench.py > gpurun_out/validate_dot_bench.jsonl 2> gpurun_out/validate_dot_bench.err'
-stage dot_bench_v2 180 bash -c 'python tools/dot_bench.py --v2 > gpurun_out/validate_dot_bench_v2.jsonl 2> gpurun_out/validate_dot_bench_v2.err'
-stage smoke 240 bash -c 'python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/validate_smoke.log 2>&1'
-stage bench 420 bash -c 'python bench.py > gpurun_out/validate_bench.json 2> gpurun_out/validate_bench.err'
-stage bench_ref 420 bash -c 'python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/validate_bench_ref.json 2> gpurun_out/validate_bench_ref.err'
-stage launches 420 bash -c 'ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/validate_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/validate_launches.log 2>&1'
-cat "$RC"
-tail -n 4 gpurun_out/validate_tests.log
+O=gpurun_out
+mkdir -p $O
+timeout 300 python -m pytest tests/test_gpu_tc_gemm.py tests/test_gpu_fullsize.py -q -rs 2>&1 | tail -15 > $O/r2b_tests.log
+timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -2 > $O/r2b_bench_n1.json
+if [ "${1:-}" = "ncu" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 600 --csv \
+      --log-file $O/r2b_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2b_bench_under_ncu.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 20 -c 6 \
+      -o $O/r2b_prof_tc_gemm python tools/tc_probe.py perf > $O/r2b_ncu_tc.log 2>&1
+fi
+cat $O/r2b_tests.log; cat $O/r2b_bench_n1.json
