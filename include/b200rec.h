@@ -216,9 +216,11 @@ int b200rec_tower_fold_dw(const float* Mx, float* dW, int K, int N, void* stream
  *   tc_prep_weight  W[K,N] -> planes(W) [K,2*ldn] and planes(W^T) [N,2*ldk] (either may be NULL)
  *   tc_linear_fwd   y = a @ W + bias, optional ReLU; a = planes [M,2*lda], W^T planes; writes y as
  *                   fp32 [M,ld_f32] and/or as planes [M,2*ldp] (the next layer's operand)
- *   tc_cross_fwd    CrossNetV2 layer: out = x0 * (xl @ W + b) + xl  (x0, xl fp32 [M,C] pitch ld_x)
+ *   tc_cross_fwd    CrossNetV2 layer: out = x0 * u + xl with u = xl @ W + b (x0, xl fp32 [M,C] pitch
+ *                   ld_x); u_f32 (may be NULL) receives u [M,C] for the backward (pitch ld_f32)
  *   tc_linear_bwd_dx  dx = g @ W^T (g planes [M,2*ldg], W planes [K,2*ldn]); optional ReLU mask
- *                   from the hi plane of the layer input (mask_planes [M,2*ld_mask]); dx as fp32
+ *                   from the hi plane of the layer input (mask_planes [M,2*ld_mask]); `addend`
+ *                   (fp32 [M,K] contiguous, may be NULL) is added first (residual paths); dx as fp32
  *                   and/or planes; dbias_prev[K] = colsum(masked dx) if not NULL (deterministic)
  *   tc_linear_bwd_dw  dW[K,N] = a^T @ g, batch reduction split across CTAs, fixed-order reduce
  * ones_col (tc_split, tc_linear_fwd): additionally store 1.0 in column C of the emitted planes
@@ -238,14 +240,14 @@ int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_plan
                           void* stream);
 int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                          const float* bias, const float* x0, const float* xl, int64_t ld_x,
-                         float* out_f32, int64_t ld_f32, void* out_planes, int64_t ldp, int64_t M,
-                         int C, void* stream);
+                         float* u_f32, float* out_f32, int64_t ld_f32, void* out_planes,
+                         int64_t ldp, int64_t M, int C, void* stream);
 int b200rec_tc_linear_bwd_workspace_bytes(int64_t M, int K, int N, size_t* bytes_host);
 int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_planes, int64_t ldn,
-                             const void* mask_planes, int64_t ld_mask, float* dx_f32,
-                             int64_t ld_f32, void* dx_planes, int64_t ldp, float* dbias_prev,
-                             int64_t M, int K, int N, void* workspace, size_t workspace_bytes,
-                             void* stream);
+                             const void* mask_planes, int64_t ld_mask, const float* addend,
+                             float* dx_f32, int64_t ld_f32, void* dx_planes, int64_t ldp,
+                             float* dbias_prev, int64_t M, int K, int N, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int b200rec_tc_linear_bwd_dw(const void* a_planes, int64_t lda, const void* g_planes, int64_t ldg,
                              float* dW, int64_t M, int K, int N, void* workspace,
                              size_t workspace_bytes, void* stream);

@@ -316,12 +316,13 @@ int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_plan
 
 int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                          const float* bias, const float* x0, const float* xl, int64_t ld_x,
-                         float* out_f32, int64_t ld_f32, void* out_planes, int64_t ldp, int64_t M,
-                         int C, void* stream) {
+                         float* u_f32, float* out_f32, int64_t ld_f32, void* out_planes,
+                         int64_t ldp, int64_t M, int C, void* stream) {
   if (M > 0) { NOT_NULL(xl_planes); NOT_NULL(wt_planes); NOT_NULL(x0); NOT_NULL(xl); }
   B200_REQUIRE(out_f32 != nullptr || out_planes != nullptr, "tc_cross_fwd: no output");
   tc::Epilogue ep = {};
   ep.bias = bias;
+  ep.aux_f32 = u_f32; ep.ld_aux = ld_f32;
   ep.cross_x0 = x0; ep.cross_xl = xl; ep.ld_cross = ld_x;
   ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
   ep.out_planes = static_cast<__nv_bfloat16*>(out_planes); ep.ldp = ldp;
@@ -338,10 +339,10 @@ int b200rec_tc_linear_bwd_workspace_bytes(int64_t M, int K, int N, size_t* bytes
 }
 
 int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_planes, int64_t ldn,
-                             const void* mask_planes, int64_t ld_mask, float* dx_f32,
-                             int64_t ld_f32, void* dx_planes, int64_t ldp, float* dbias_prev,
-                             int64_t M, int K, int N, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+                             const void* mask_planes, int64_t ld_mask, const float* addend,
+                             float* dx_f32, int64_t ld_f32, void* dx_planes, int64_t ldp,
+                             float* dbias_prev, int64_t M, int K, int N, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (M > 0) { NOT_NULL(g_planes); NOT_NULL(w_planes); }
   B200_REQUIRE(dx_f32 != nullptr || dx_planes != nullptr, "tc_linear_bwd_dx: no output");
   B200_REQUIRE(dx_f32 == nullptr || ld_f32 >= K, "tc_linear_bwd_dx: ld_f32 < K");
@@ -350,6 +351,7 @@ int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_pl
   ep.out_f32 = dx_f32; ep.ld_f32 = ld_f32;
   ep.out_planes = static_cast<__nv_bfloat16*>(dx_planes); ep.ldp = ldp;
   ep.mask_src = static_cast<const __nv_bfloat16*>(mask_planes); ep.ld_mask = 2 * ld_mask;
+  ep.addend = addend; ep.ld_add = K;
   const int tiles_m = (int)((M + tc::kBM - 1) / tc::kBM);
   if (dbias_prev != nullptr) {
     const size_t need = (size_t)tiles_m * K * sizeof(float);

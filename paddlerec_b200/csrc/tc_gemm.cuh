@@ -203,6 +203,10 @@ struct Epilogue {
   // outputs that leave the SM as TMA bulk stores of swizzled shared-memory tiles (host decides:
   // needs 16-byte aligned base and pitch; at most one of the two uses the staging buffer)
   int tma_planes, tma_f32;
+  const float* addend;              // [M, ld_add] added to acc (+bias) before everything else, or null
+  int64_t ld_add;
+  float* aux_f32;                   // [M, ld_aux] receives acc + bias + addend, i.e. the value BEFORE
+  int64_t ld_aux;                   //   the CrossNet / ReLU / mask transforms, or null
 };
 
 __device__ __forceinline__ void split_bf16(float x, float& hi_f, __nv_bfloat16& hi,
@@ -297,6 +301,19 @@ __device__ __forceinline__ void epilogue_fast(const Epilogue& ep, float (&v)[32]
       v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
     }
   }
+  if (ep.addend != nullptr) {
+    const float4* ad = reinterpret_cast<const float4*>(ep.addend + row * ep.ld_add + col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 a = __ldg(ad + g);
+      v[4 * g] += a.x; v[4 * g + 1] += a.y; v[4 * g + 2] += a.z; v[4 * g + 3] += a.w;
+    }
+  }
+  if (ep.aux_f32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(ep.aux_f32 + row * ep.ld_aux + col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) o[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  }
   if (ep.cross_x0 != nullptr) {
     const float4* x0 = reinterpret_cast<const float4*>(ep.cross_x0 + row * ep.ld_cross + col0);
     const float4* xl = reinterpret_cast<const float4*>(ep.cross_xl + row * ep.ld_cross + col0);
@@ -350,7 +367,8 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
                                                bool row_ok, int col0, int n_valid, int lane,
                                                float* s_colsum /* [32] for this warp or null */,
                                                bool store_f32 = true, bool store_planes = true) {
-  if (ep.bias != nullptr || ep.cross_x0 != nullptr || ep.relu || ep.mask_src != nullptr) {
+  if (ep.bias != nullptr || ep.cross_x0 != nullptr || ep.relu || ep.mask_src != nullptr ||
+      ep.addend != nullptr || ep.aux_f32 != nullptr) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {   // groups of 4 columns
       const int c = g * 4;
@@ -364,6 +382,16 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, float (&v)[32
             for (int j = 0; j < 4; ++j)
               if (c + j < n_valid) v[c + j] += __ldg(ep.bias + col0 + c + j);
           }
+        }
+        if (ep.addend != nullptr && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < n_valid) v[c + j] += __ldg(ep.addend + row * ep.ld_add + col0 + c + j);
+        }
+        if (ep.aux_f32 != nullptr && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < n_valid) ep.aux_f32[row * ep.ld_aux + col0 + c + j] = v[c + j];
         }
         if (ep.cross_x0 != nullptr && row_ok) {
           const float* x0 = ep.cross_x0 + row * ep.ld_cross + col0 + c;
@@ -597,6 +625,8 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         (ep.out_planes == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_planes) | (ep.ldp * 2)) & 15u) == 0) &&
         (ep.mask_src == nullptr || ((reinterpret_cast<uintptr_t>(ep.mask_src) | (ep.ld_mask * 2)) & 15u) == 0) &&
         (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15u) == 0) &&
+        (ep.addend == nullptr || ((reinterpret_cast<uintptr_t>(ep.addend) | (ep.ld_add * 4)) & 15u) == 0) &&
+        (ep.aux_f32 == nullptr || ((reinterpret_cast<uintptr_t>(ep.aux_f32) | (ep.ld_aux * 4)) & 15u) == 0) &&
         (ep.cross_x0 == nullptr ||
          ((reinterpret_cast<uintptr_t>(ep.cross_x0) | reinterpret_cast<uintptr_t>(ep.cross_xl) |
            (ep.ld_cross * 4)) & 15u) == 0);
@@ -629,13 +659,17 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        // outputs staged for TMA are stored below; the others directly from registers
+        // Full 32-column chunks leave through the TMA staging buffer; a partial chunk (tile width
+        // not a multiple of 32) is stored directly: its 32-wide box would spill into the
+        // neighbouring tile's columns (the tensor map clips only at the matrix edge).
+        const bool via_tma = (tma_p || tma_f) && nv == 32;
+        const bool st_f = !(tma_f && via_tma), st_p = !(tma_p && via_tma);
         if (fast)
-          epilogue_fast(ep, v, row, n0 + c0, mk, !tma_f, !tma_p);
+          epilogue_fast(ep, v, row, n0 + c0, mk, st_f, st_p);
         else
           epilogue_chunk(ep, v, row, row_ok, n0 + c0, nv, lane,
-                         want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr, !tma_f, !tma_p);
-        if (tma_p || tma_f) {
+                         want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr, st_f, st_p);
+        if (via_tma) {
           if (lane == 0) bulk_wait_read0();      // the previous store has finished reading sbuf
           __syncwarp();
           if (tma_p)

@@ -495,20 +495,23 @@ def raw_tc_linear_fwd(a_planes: torch.Tensor, K: int, WTp: torch.Tensor, N: int,
     return y, yp
 
 
-def raw_tc_cross_fwd(xl_planes, WTp, bias, x0, xl, want_planes: bool):
-    """CrossNetV2 layer out = x0 * (xl @ W + b) + xl with the Hadamard/residual epilogue fused into
-    the tcgen05 GEMM.  Returns (out fp32 [M,C], planes(out) | None)."""
+def raw_tc_cross_fwd(xl_planes, WTp, bias, x0, xl, want_planes: bool, want_u: bool = False,
+                     ones_col: bool = False):
+    """CrossNetV2 layer out = x0 * u + xl, u = xl @ W + b, with the Hadamard/residual epilogue fused
+    into the tcgen05 GEMM.  Returns (out fp32 [M,C], planes(out) | None, u fp32 | None)."""
     lib = _lib.load()
     x0 = _req(x0, torch.float32, "x0")
     xl = _req(xl, torch.float32, "xl")
     M, C = x0.shape
     out = torch.empty(M, C, dtype=torch.float32, device=x0.device)
-    op = _planes(M, C, x0.device) if want_planes else None
+    u = torch.empty(M, C, dtype=torch.float32, device=x0.device) if want_u else None
+    op = _planes(M, C, x0.device, ones_col) if want_planes else None
     check(lib.b200rec_tc_cross_fwd(ptr(xl_planes), xl_planes.shape[1] // 2, ptr(WTp),
-                                   WTp.shape[1] // 2, ptr(bias), ptr(x0), ptr(xl), C, ptr(out), C,
-                                   ptr(op), plane_ld(C), M, C, _stream()), "tc_cross_fwd")
+                                   WTp.shape[1] // 2, ptr(bias), ptr(x0), ptr(xl), C, ptr(u),
+                                   ptr(out), C, ptr(op), op.shape[1] // 2 if op is not None else 0,
+                                   M, C, _stream()), "tc_cross_fwd")
     _count("tc_cross_fwd")
-    return out, op
+    return out, op, u
 
 
 def _tc_bwd_ws(M: int, K: int, N: int, device) -> torch.Tensor:
@@ -520,7 +523,7 @@ def _tc_bwd_ws(M: int, K: int, N: int, device) -> torch.Tensor:
 
 
 def raw_tc_linear_bwd_dx(g_planes, N: int, Wp, K: int, mask_planes, want_f32: bool,
-                         want_planes: bool, want_dbias: bool):
+                         want_planes: bool, want_dbias: bool, addend=None):
     """dx = g @ W^T with the ReLU mask of the layer input, the hi/lo split and the bias column-sum
     of the PREVIOUS layer fused into the epilogue.  Returns (dx fp32 | None, planes | None,
     dbias_prev [K] | None)."""
@@ -533,7 +536,9 @@ def raw_tc_linear_bwd_dx(g_planes, N: int, Wp, K: int, mask_planes, want_f32: bo
     ws = _tc_bwd_ws(M, K, N, dev)
     ld_mask = mask_planes.shape[1] // 2 if mask_planes is not None else 0
     check(lib.b200rec_tc_linear_bwd_dx(ptr(g_planes), g_planes.shape[1] // 2, ptr(Wp),
-                                       Wp.shape[1] // 2, ptr(mask_planes), ld_mask, ptr(dx), K,
+                                       Wp.shape[1] // 2, ptr(mask_planes), ld_mask,
+                                       ptr(_req(addend, torch.float32, "addend")
+                                           if addend is not None else None), ptr(dx), K,
                                        ptr(dxp), plane_ld(K), ptr(db), M, K, N, ptr(ws), ws.numel(),
                                        _stream()), "tc_linear_bwd_dx")
     _count("tc_linear_bwd_dx_db" if want_dbias else "tc_linear_bwd_dx")
@@ -674,6 +679,84 @@ class _GatherPool(torch.autograd.Function):
 
 def gather_pool_sum(W, keys, offsets, padding_idx, sink, hook):
     return _GatherPool.apply(W, keys, offsets, padding_idx, sink, hook)
+
+
+def tc_backend() -> bool:
+    """True when the hand-written tcgen05 GEMMs serve the 'bf16x3' matmuls (tower.BACKEND)."""
+    from . import tower
+    return tower.BACKEND == "tcgen05"
+
+
+class _TcLinear(torch.autograd.Function):
+    """y = x @ W (+ b) as ONE tcgen05 GEMM per direction (split precision): forward with the bias in
+    the epilogue, dW as the batch-split MN-major GEMM (the bias gradient rides along as an extra
+    output row when the input width is not a multiple of 128), dx as the K-major GEMM.  Used by
+    every nn.Linear / split_mm of the package in 'bf16x3' precision."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        K, N = W.shape
+        ones = b is not None and K % 128 != 0
+        xs = raw_tc_split(x, ones_col=ones)
+        Wp, WTp = raw_tc_prep_weight(W, want_w=ctx.needs_input_grad[0])
+        y, _ = raw_tc_linear_fwd(xs, K, WTp, N, b, False, True, False)
+        ctx.xs, ctx.Wp, ctx.shape, ctx.ones, ctx.has_b = xs, Wp, (K, N), ones, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        K, N = ctx.shape
+        gs, db = raw_tc_split_bwd(dy.contiguous(), None)
+        if ctx.ones:
+            dW, db = raw_tc_linear_bwd_dw(ctx.xs, K, gs, N, bias_row=True)
+        else:
+            dW = raw_tc_linear_bwd_dw(ctx.xs, K, gs, N)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _, _ = raw_tc_linear_bwd_dx(gs, N, ctx.Wp, K, None, True, False, False)
+        ctx.xs = ctx.Wp = None
+        return dx, dW, (db if ctx.has_b else None)
+
+
+def tc_linear(x, W, b=None):
+    lead = x.shape[:-1]
+    y = _TcLinear.apply(x.reshape(-1, x.shape[-1]).contiguous(), W, b)
+    return y.reshape(*lead, y.shape[-1])
+
+
+class _CrossV2Tc(torch.autograd.Function):
+    """One CrossNetV2 layer X_{i+1} = X_i + X_0 * (X_i W + b) (dcn_v2/net.py:222-226) on the tcgen05
+    kernels: ONE GEMM whose epilogue applies bias, Hadamard and residual, saves u = X_i W + b for
+    the backward and emits the next layer's hi/lo operand; backward = K3 (dxw, dx0) + the split +
+    the dW GEMM + the dX GEMM with the residual gradient added in its epilogue."""
+
+    @staticmethod
+    def forward(ctx, x0, xl, W, bias, xl_planes):
+        C = W.shape[0]
+        ones = bias is not None and C % 128 != 0
+        xs = xl_planes if xl_planes is not None else raw_tc_split(xl, ones_col=ones)
+        Wp, WTp = raw_tc_prep_weight(W)
+        out, outp, u = raw_tc_cross_fwd(xs, WTp, bias, x0, xl, True, want_u=True, ones_col=ones)
+        ctx.save_for_backward(x0, u)
+        ctx.xs, ctx.Wp, ctx.C, ctx.ones, ctx.has_b = xs, Wp, C, ones, bias is not None
+        ctx.mark_non_differentiable(outp)   # handed to the next cross layer (no re-split)
+        return out, outp
+
+    @staticmethod
+    def backward(ctx, dout, _dplanes):
+        x0, u = ctx.saved_tensors
+        C = ctx.C
+        dout = dout.contiguous()
+        zero_b = torch.zeros(C, dtype=torch.float32, device=dout.device)
+        dxw, dx0, dbias = raw_cross_v2_bwd(dout, x0, u, zero_b)        # u already holds the bias
+        gs, _ = raw_tc_split_bwd(dxw, None)
+        if ctx.ones:
+            dW, dbias = raw_tc_linear_bwd_dw(ctx.xs, C, gs, C, bias_row=True)
+        else:
+            dW = raw_tc_linear_bwd_dw(ctx.xs, C, gs, C)
+        dxl, _, _ = raw_tc_linear_bwd_dx(gs, C, ctx.Wp, C, None, True, False, False, addend=dout)
+        ctx.xs = ctx.Wp = None
+        return dx0, dxl, dW, (dbias if ctx.has_b else None), None
 
 
 class _CrossV2(torch.autograd.Function):
@@ -1041,6 +1124,8 @@ class _CrossCombine(torch.autograd.Function):
 
 
 def split_mm(a, W):
+    if tc_backend() and a.is_cuda:
+        return tc_linear(a, W, None)
     return _SplitMM.apply(a, W)
 
 
@@ -1057,8 +1142,12 @@ def gather(W, ids, padding_idx, sink, hook):
     return _Gather.apply(W, ids, padding_idx, sink, hook)
 
 
-def cross_v2(x0, xl, W, bias, mm, precision="fp32"):
-    return _CrossV2.apply(x0, xl, W, bias, mm, precision)
+def cross_v2(x0, xl, W, bias, mm, precision="fp32", xl_planes=None):
+    """-> (X_{i+1}, its hi/lo planes or None).  Pass the planes back as `xl_planes` of the next
+    layer: on the tcgen05 back end the GEMM epilogue has already produced that operand."""
+    if precision == "bf16x3" and x0.is_cuda and tc_backend():
+        return _CrossV2Tc.apply(x0, xl, W, bias, xl_planes)
+    return _CrossV2.apply(x0, xl, W, bias, mm, precision), None
 
 
 # ---- per-kernel CUDA-event timing of every entry point (bench.py roofline_step) -----------------

@@ -3,8 +3,9 @@ models/rank/dcn_v2/net.py (DCN_V2Layer :21-137, DNNLayer :140-184, DeepCrossLaye
 CrossNetV2 :214-226, CrossNetMix :229-320).
 
 CUDA path: the 26-slot lookup is b200rec_gather (+ sorted segment-reduce backward); every
-CrossNetV2 layer is one library GEMM + the fused b200rec_cross_v2 epilogue; the MLP is the
-tensor-core tower (tower.py).  CrossNetMix is re-associated from the reference's per-sample
+CrossNetV2 layer is ONE hand-written tcgen05 GEMM whose epilogue applies bias, Hadamard and residual
+and emits the next layer's operand (ops._CrossV2Tc); the MLP is the tcgen05 tower (tower.py) in
+eval mode and per-layer tcgen05 Linears around the reference's dropouts in train mode.  CrossNetMix is re-associated from the reference's per-sample
 [B,in,1] batched GEMVs into three batched GEMMs over all experts (mathematically identical).
 Quirks kept: Dropout(0.5) after every Linear AND every ReLU in train
 mode; L2Decay(1e-7) on the DNN weights (applied by the optimizer, optim._apply_regularizers); dense_emb is a full Linear(13 -> 13*D).
@@ -116,10 +117,11 @@ class CrossNetV2(tnn.Module):
 
     def forward(self, X_0):
         X_0 = X_0.contiguous()
-        X_i = X_0
+        X_i, planes = X_0, None
         for layer in self.cross_layers:       # X_i + X_0 * (X_i W + b): GEMM + fused epilogue
-            X_i = ops.cross_v2(X_0, X_i, layer.weight, layer.bias, bnn.mm,
-                               bnn.get_matmul_precision() if X_i.is_cuda else "fp32")
+            X_i, planes = ops.cross_v2(X_0, X_i, layer.weight, layer.bias, bnn.mm,
+                                       bnn.get_matmul_precision() if X_i.is_cuda else "fp32",
+                                       xl_planes=planes)
         return X_i
 
 

@@ -198,11 +198,68 @@ def test_tc_cross_fwd():
     b = torch.randn(C, generator=g) * 0.1
     xlp = ops.raw_tc_split(xl.to(DEV))
     _, WTp = ops.raw_tc_prep_weight(W.to(DEV), want_w=False)
-    out, outp = ops.raw_tc_cross_fwd(xlp, WTp, b.to(DEV), x0.to(DEV), xl.to(DEV), True)
+    out, outp, u = ops.raw_tc_cross_fwd(xlp, WTp, b.to(DEV), x0.to(DEV), xl.to(DEV), True,
+                                        want_u=True)
     torch.cuda.synchronize()
-    want = x0.double() * (xl.double() @ W.double() + b.double()) + xl.double()
+    wantu = xl.double() @ W.double() + b.double()
+    want = x0.double() * wantu + xl.double()
+    assert _err(u, wantu) < 5e-5
     assert _err(out, want) < 5e-5
     assert _err(_join(outp, C), want) < 5e-5
+
+
+def test_cross_v2_layer_chain_autograd():
+    """Two chained CrossNetV2 layers through ops.cross_v2 on the tcgen05 back end (the second
+    consumes the planes the first one's epilogue emitted): output and every gradient vs fp64."""
+    from paddlerec_b200 import nn as bnn
+    from tests.util import rel_err
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    M, C = 300, 200
+    x0 = torch.randn(M, C, generator=g)
+    Ws = [torch.randn(C, C, generator=g) / C ** 0.5 for _ in range(2)]
+    bs = [torch.randn(C, generator=g) * 0.1 for _ in range(2)]
+    gy = torch.randn(M, C, generator=g)
+    x0d = x0.double().requires_grad_(True)
+    Wd = [w.double().requires_grad_(True) for w in Ws]
+    bd = [b.double().requires_grad_(True) for b in bs]
+    xi = x0d
+    for W, b in zip(Wd, bd):
+        xi = xi + x0d * (xi @ W + b)
+    (xi * gy.double()).sum().backward()
+    x0c = x0.to(DEV).requires_grad_(True)
+    Wc = [w.to(DEV).requires_grad_(True) for w in Ws]
+    bc = [b.to(DEV).requires_grad_(True) for b in bs]
+    xc, planes = x0c, None
+    for W, b in zip(Wc, bc):
+        xc, planes = ops.cross_v2(x0c, xc, W, b, bnn.mm, "bf16x3", xl_planes=planes)
+    (xc * gy.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(xc, xi) < 1e-4 and rel_err(x0c.grad, x0d.grad) < 1e-4
+    for a, b in zip(Wc + bc, Wd + bd):
+        assert rel_err(a.grad, b.grad) < 1e-4
+
+
+def test_tc_linear_autograd_small_and_odd_shapes():
+    """nn.Linear in bf16x3 precision = ops.tc_linear: shapes the models actually use (13 -> 13*D,
+    K = 13, N = 1, 3-D inputs)."""
+    from tests.util import rel_err
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    for lead, K, N in [((70,), 13, 208), ((33,), 256, 1), ((4, 25), 128, 80), ((129,), 40, 7)]:
+        x = torch.randn(*lead, K, generator=g)
+        W = torch.randn(K, N, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g) * 0.1
+        gy = torch.randn(*lead, N, generator=g)
+        xd, Wd, bd = (t.double().requires_grad_(True) for t in (x, W, b))
+        ((xd @ Wd + bd) * gy.double()).sum().backward()
+        xc, Wc, bc = (t.to(DEV).requires_grad_(True) for t in (x, W, b))
+        y = ops.tc_linear(xc, Wc, bc)
+        (y * gy.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+        assert rel_err(y, x.double() @ W.double() + b.double()) < 5e-5
+        for a, r in ((xc, xd), (Wc, Wd), (bc, bd)):
+            assert rel_err(a.grad, r.grad) < 5e-5, (lead, K, N)
 
 
 @pytest.mark.parametrize("sizes", [[624, 400, 400, 400, 1], [429, 512, 256, 128, 32]])
