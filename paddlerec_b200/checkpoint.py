@@ -67,9 +67,20 @@ def load_pdparams(path: str) -> Dict[str, np.ndarray]:
 
 
 def set_state_dict(net: torch.nn.Module, state: Dict[str, np.ndarray], strict: bool = True):
-    """Layer.set_state_dict: match by structured name, check shapes, copy on the module's device."""
+    """Layer.set_state_dict: match by structured name, check shapes, copy on the module's device.
+
+    A module may declare `optional_state_prefixes`: keys of ITS state_dict that a reference-produced
+    checkpoint does not contain.  DIN's attention-unit linears are the case (the
+    reference's sub-layer name collision drops them from state_dict(), so a Paddle rec.pdparams
+    has no `attention.linear_*`; they keep their seeded initialisation, as in the reference)."""
     dev = next((p.device for p in net.parameters()), torch.device("cpu"))
     tensors = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in state.items()}
+    optional = tuple(getattr(net, "optional_state_prefixes", ()))
+    if strict and optional:
+        own = net.state_dict()
+        for k, v in own.items():
+            if k not in tensors and k.startswith(optional):
+                tensors[k] = v
     return net.load_state_dict(tensors, strict=strict)
 
 

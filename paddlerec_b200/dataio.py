@@ -229,7 +229,12 @@ def parse_slot_text_lod(data, schema: SlotSchema = CRITEO, threads: int = 0):
         schema.dense_slot.encode() if schema.dense_slot else None, schema.dense_dim,
         _np_ptr(label), _np_ptr(keys), _np_ptr(offsets), _np_ptr(dense), cap, keys.size,
         ctypes.byref(n), ctypes.byref(nk), threads))
-    return label, keys[:nk.value].copy(), offsets, dense
+    # `cap` counts every line, the parser drops blank / whitespace-only ones: trim to the n samples
+    # it actually produced (the tail rows are uninitialised; offsets would index out of bounds)
+    k = n.value
+    F = schema.n_sparse
+    return (label[:k] if label is not None else None, keys[:nk.value].copy(),
+            offsets[:k * F + 1].copy(), dense[:k] if dense is not None else None)
 
 
 def parse_multislot(data, slot_is_float: Sequence[bool], threads: int = 0):
@@ -250,8 +255,11 @@ def parse_multislot(data, slot_is_float: Sequence[bool], threads: int = 0):
         p, nbytes, flags, len(slot_is_float), _np_ptr(keys) if n_int else None, _np_ptr(koff),
         keys.size, _np_ptr(fvals) if n_float else None, _np_ptr(foff), fvals.size, cap,
         ctypes.byref(n), ctypes.byref(nk), ctypes.byref(nf), threads))
-    return {"n": n.value, "keys": keys[:nk.value].copy(), "key_offsets": koff,
-            "fvals": fvals[:nf.value].copy(), "float_offsets": foff}
+    k = n.value
+    return {"n": k, "keys": keys[:nk.value].copy(),
+            "key_offsets": koff[:k * n_int + 1].copy() if koff is not None else None,
+            "fvals": fvals[:nf.value].copy(),
+            "float_offsets": foff[:k * n_float + 1].copy() if foff is not None else None}
 
 
 def parse_criteo_tsv(data, hash_kind: int = HASH_STD, hash_dim: int = 1000001, cont_min=None,

@@ -205,9 +205,8 @@ class Embedding(tnn.Module):
             w[self.padding_idx].zero_()  # paddle dygraph zeroes the padding row at construction
 
     def accept(self, sr: ops.SelectedRows) -> None:
-        if self.grad_rows is not None:
-            raise RuntimeError("Embedding used twice in one step: merge of SelectedRows grads "
-                               "is not implemented (clear_grad between steps)")
+        if self.grad_rows is not None:      # shared table / micro-batch accumulation: merge-add
+            sr = ops.merge_selected_rows(self.grad_rows, sr)
         self.weight.grad_rows = sr
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
@@ -300,9 +299,10 @@ class FusedTable(tnn.Module):
         return ops.raw_group_ids(ids, V, pad)
 
     def accept_fused(self, sr: ops.SelectedRows) -> None:
-        if self.weight.grad_rows is not None:
-            raise RuntimeError("FusedTable used twice in one step (clear_grad between steps)")
         sr.ncols = self.grad_cols
+        if self.weight.grad_rows is not None:   # second use in one step: merge-add like Paddle
+            sr = ops.merge_selected_rows(self.weight.grad_rows, sr)
+            sr.ncols = self.grad_cols
         self.weight.grad_rows = sr
 
     @property

@@ -281,6 +281,21 @@ def raw_segment_reduce(dOut: torch.Tensor, groups_seg, groups_pos, num, n: int,
     return rows
 
 
+def merge_selected_rows(a: SelectedRows, b: SelectedRows) -> SelectedRows:
+    """Paddle's merge-add of two SelectedRows gradients of the same table (a table looked up twice
+    in one forward, or gradients accumulated over micro-batches): concatenate the valid rows and
+    reduce duplicates with the same sorted segment reduce the backward uses (deterministic).
+    Rare path: reads the two row counts on the host."""
+    na, nb = a.count(), b.count()
+    cols = min(a.cols, b.cols)
+    rows = torch.cat([a.rows[:na], b.rows[:nb]])
+    vals = torch.cat([a.value[:na, :cols], b.value[:nb, :cols]]).contiguous()
+    groups = raw_group_ids(rows, a.height, -1)
+    merged = raw_segment_reduce(vals, groups.seg_offsets, groups.sorted_pos, groups.num, groups.n)
+    return SelectedRows(groups.unique_ids, merged, groups.num, a.height,
+                        cols if a.ncols is not None else None)
+
+
 def raw_rows_to_dense(sr: SelectedRows, dW: torch.Tensor) -> None:
     lib = _lib.load()
     dW = _req(dW, torch.float32, "dW")

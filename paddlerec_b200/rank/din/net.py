@@ -62,6 +62,8 @@ class DINLayer(tnn.Module):
         E = item_emb_size + cat_emb_size
         self.firInDim = self.firOutDim = E
         self.attention = _MLP3([4 * E, 80, 40, 1]).to(device)          # net.py:84-104
+        # absent from a reference-produced checkpoint (Q6): checkpoint.set_state_dict tolerates it
+        self.optional_state_prefixes = ("attention.",)
         if faithful_frozen_attention:
             for p in self.attention.parameters():
                 p.requires_grad_(False)

@@ -129,3 +129,25 @@ def test_runner_save_and_load_use_the_reference_layout(tmp_path):
         m2.embedding.weight.zero_()
     runner.load_model(str(tmp_path / "7"), m2, optimizer=opt)
     assert torch.equal(m.embedding.weight, m2.embedding.weight)
+
+
+def test_reference_din_checkpoint_without_attention_keys_loads():
+    """a Paddle-produced DIN rec.pdparams has no attention.linear_* keys (the reference's
+    name collision hides them from state_dict()); strict loading must accept that and keep the
+    seeded attention weights, while a genuinely missing key still fails."""
+    from paddlerec_b200.rank.din import net
+    torch.manual_seed(3)
+    m = net.DINLayer(8, 8, "sigmoid", True, True, 50, 7, device="cpu")
+    full = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    ref_like = {k: v for k, v in full.items() if not k.startswith("attention.")}
+    assert len(ref_like) < len(full)
+    torch.manual_seed(4)
+    m2 = net.DINLayer(8, 8, "sigmoid", True, True, 50, 7, device="cpu")
+    att_before = m2.attention.linear_0.weight.detach().clone()
+    checkpoint.set_state_dict(m2, ref_like)
+    assert torch.equal(m2.attention.linear_0.weight, att_before)
+    assert torch.equal(m2.linearCon.weight, m.linearCon.weight)
+    broken = dict(ref_like)
+    broken.pop("linearCon.weight")
+    with pytest.raises(RuntimeError):
+        checkpoint.set_state_dict(m2, broken)

@@ -467,3 +467,16 @@ def test_pack_dataset_tool_and_packed_training_input(tmp_path):
     (cache / "day_0.b2r").unlink()
     batches = list(runner.create_data_loader(cfg))
     assert len(batches) == 10 and batches[0][1].shape == (100, 26)
+
+
+def test_lod_and_multislot_outputs_are_trimmed_to_the_parsed_samples():
+    """whitespace-only lines are counted for the capacity but dropped by the parser; the
+    returned label / offsets / dense must be cut to the n samples actually produced (the tail was
+    uninitialised memory and the offsets fed out-of-bounds reads of the pooled gather)."""
+    sch = dataio.SlotSchema(sparse_slots=("a", "b"), label_slot="y", dense_slot="d", dense_dim=1)
+    text = "y:1 a:5 a:6 b:7 d:0.5\n   \n\ny:0 a:8 b:9 b:10 d:0.25\n \t \n"
+    label, keys, offsets, dense = dataio.parse_slot_text_lod(text, sch)
+    assert label.shape == (2, 1) and dense.shape == (2, 1)
+    assert offsets.tolist() == [0, 2, 3, 4, 6] and keys.tolist() == [5, 6, 7, 8, 9, 10]
+    got = dataio.parse_multislot("1 3 1 4\n   \n2 5 6 1 7\n\n", [False, False])
+    assert got["n"] == 2 and got["key_offsets"].tolist() == [0, 1, 2, 4, 5]

@@ -607,3 +607,25 @@ def test_dot_interact_v2_matches_v1(B, N, d, self_interaction, monkeypatch):
     dT2 = ops.raw_dot_interact_bwd(T, dR, self_interaction)
     assert torch.equal(R1, R2)
     assert torch.equal(dT1, dT2)
+
+
+def test_embedding_used_twice_merges_selected_rows():
+    """Paddle merge-adds the SelectedRows gradients of a table that is looked up twice
+    in one forward (shared embedding) or across micro-batches; the table gradient must equal the
+    dense autograd gradient of the same computation."""
+    from paddlerec_b200 import nn as bnn
+    g = torch.Generator().manual_seed(5)
+    V, D = 97, 8
+    emb = bnn.Embedding(V, D, padding_idx=0, init_std=0.1, device=DEV)
+    ids1 = torch.randint(0, V, (33, 4), generator=g).to(DEV)
+    ids2 = torch.randint(0, V, (20, 3), generator=g).to(DEV)
+    w1 = torch.randn(33, 4, D, generator=g).to(DEV)
+    w2 = torch.randn(20, 3, D, generator=g).to(DEV)
+    ((emb(ids1) * w1).sum() + (emb(ids2) * w2).sum()).backward()
+    got = emb.grad_rows.to_dense()
+    Wd = emb.weight.detach().double().clone().requires_grad_(True)
+    m1 = (ids1 != 0).unsqueeze(2)
+    m2 = (ids2 != 0).unsqueeze(2)
+    ((Wd[ids1] * m1 * w1.double()).sum() + (Wd[ids2] * m2 * w2.double()).sum()).backward()
+    assert rel_err(got, Wd.grad) < 1e-6
+    assert not got[0].any()
