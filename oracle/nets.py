@@ -196,6 +196,21 @@ def wide_deep_forward(p: Params, sparse_inputs, dense_inputs, n_fc: int):
     return torch.sigmoid(wide + deep)                                             # :99-101
 
 
+def wide_deep_forward_gpubox(p: Params, sparse_inputs, dense_inputs, n_fc: int):
+    """WideDeepLayer.forward, `sync_mode == "gpubox"` branch — models/rank/wide_deep/net.py:80-88:
+    the table rows are [show, click, embedding(D)] (sparse_embedding size [V, D+2]) and every
+    looked-up row goes through continuous_value_model(emb, show_click, use_cvm=False), which keeps
+    only the embedding columns in forward.  (Its backward writes the sample's show/click into the
+    two dropped gradient columns: cvm_grad — checked separately, it is not a derivative.)"""
+    wide = linear(dense_inputs, p["wide_part.weight"], p["wide_part.bias"])       # :75
+    D = p["embedding.weight"].shape[1] - 2
+    embs = [cvm(embedding(p["embedding.weight"], s).reshape(-1, D + 2), False)     # :81-88
+            for s in sparse_inputs]
+    deep = torch.cat(embs + [dense_inputs], 1)                                    # :95
+    deep = mlp_relu(p, "", deep, n_fc + 1)                                        # :96-97
+    return torch.sigmoid(wide + deep)                                             # :99-101
+
+
 def cvm(emb_with_show_click: torch.Tensor, use_cvm: bool) -> torch.Tensor:
     """continuous_value_model forward (wide_deep/net.py:87-88): input [N, D+2] whose first two
     columns are show/click.  use_cvm=False drops them; True maps them to

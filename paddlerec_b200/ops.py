@@ -307,8 +307,8 @@ def raw_rows_to_dense(sr: SelectedRows, dW: torch.Tensor) -> None:
 
 def raw_sparse_sgd(W: torch.Tensor, sr: SelectedRows, lr: float) -> None:
     lib = _lib.load()
-    n, ld_rows = sr.value.shape
-    check(lib.b200rec_sparse_sgd(ptr(W), W.shape[1], ptr(sr.rows), ptr(sr.value), ld_rows,
+    n, ld_rows = sr.value.shape[0], sr.value.stride(0)     # column views of a table are allowed
+    check(lib.b200rec_sparse_sgd(ptr(W), W.stride(0), ptr(sr.rows), ptr(sr.value), ld_rows,
                                  ptr(sr.num), n, sr.cols, sr.height, float(lr), _stream()),
           "sparse_sgd")
     _count("sparse_sgd")
@@ -316,8 +316,8 @@ def raw_sparse_sgd(W: torch.Tensor, sr: SelectedRows, lr: float) -> None:
 
 def raw_sparse_adam(W, m, v, sr: SelectedRows, lr, beta1, beta2, eps, beta1_pow, beta2_pow) -> None:
     lib = _lib.load()
-    n, ld_rows = sr.value.shape
-    check(lib.b200rec_sparse_adam(ptr(W), ptr(m), ptr(v), W.shape[1], ptr(sr.rows), ptr(sr.value),
+    n, ld_rows = sr.value.shape[0], sr.value.stride(0)
+    check(lib.b200rec_sparse_adam(ptr(W), ptr(m), ptr(v), W.stride(0), ptr(sr.rows), ptr(sr.value),
                                   ld_rows, ptr(sr.num), n, sr.cols, sr.height, float(lr),
                                   float(beta1), float(beta2), float(eps), float(beta1_pow),
                                   float(beta2_pow), _stream()), "sparse_adam")
@@ -326,8 +326,8 @@ def raw_sparse_adam(W, m, v, sr: SelectedRows, lr, beta1, beta2, eps, beta1_pow,
 
 def raw_sparse_adagrad(W, g2sum, sr: SelectedRows, lr, initial_g2sum, lo, hi) -> None:
     lib = _lib.load()
-    n, ld_rows = sr.value.shape
-    check(lib.b200rec_sparse_adagrad(ptr(W), ptr(g2sum), W.shape[1], ptr(sr.rows), ptr(sr.value),
+    n, ld_rows = sr.value.shape[0], sr.value.stride(0)
+    check(lib.b200rec_sparse_adagrad(ptr(W), ptr(g2sum), W.stride(0), ptr(sr.rows), ptr(sr.value),
                                      ld_rows, ptr(sr.num), n, sr.cols, sr.height, float(lr),
                                      float(initial_g2sum), float(lo), float(hi), _stream()),
           "sparse_adagrad")

@@ -115,6 +115,20 @@ class _Base:
                 sr.value.mul_(scale)
 
 
+    def _table_parts(self, p, sr):
+        """(W, SelectedRows) restricted to the TRAINABLE columns of a table.  A GPUBox / PS table
+        (`cvm_stat_cols = 2`, rows = [show, click, embedding...]) receives the batch's show/click
+        counts in its first two gradient columns (cvm_grad, wide_deep/net.py:87-88); the accessor
+        ACCUMULATES them (show += pushed show, click += pushed click) instead of descending on them
+        (CtrCommonAccessor of models/rank/slot_dnn/config_online.yaml:57-79)."""
+        k = int(getattr(p, "cvm_stat_cols", 0))
+        if not k:
+            return p.data, sr, 0
+        stat = ops.SelectedRows(sr.rows, sr.value[:, :k], sr.num, sr.height, ncols=k)
+        ops.raw_sparse_sgd(p.data[:, :k], stat, -1.0)
+        main = ops.SelectedRows(sr.rows, sr.value[:, k:], sr.num, sr.height, ncols=sr.cols - k)
+        return p.data[:, k:], main, k
+
     def _apply_regularizers(self) -> None:
         """Per-parameter L2Decay set through ParamAttr (nn.Linear(weight_l2_decay=c), reference:
         models/rank/dcn_v2/net.py:166-168): grad += c * param.  Paddle's Optimizer.apply_gradients
@@ -145,7 +159,8 @@ class SGD(_Base):
         for p in self._sparse:
             sr = getattr(p, "grad_rows", None)
             if sr is not None:
-                ops.raw_sparse_sgd(p.data, sr, lr)
+                W, sr, _ = self._table_parts(p, sr)
+                ops.raw_sparse_sgd(W, sr, lr)
         self.step_count += 1
         self._maybe_step_lr()
 
@@ -194,7 +209,9 @@ class Adam(_Base):
             sr = getattr(p, "grad_rows", None)
             if sr is not None:
                 m, v = self.moments(p)
-                ops.raw_sparse_adam(p.data, m, v, sr, lr, self.beta1, self.beta2, self.eps, b1p, b2p)
+                W, sr, k = self._table_parts(p, sr)
+                ops.raw_sparse_adam(W, m[:, k:], v[:, k:], sr, lr, self.beta1, self.beta2, self.eps,
+                                    b1p, b2p)
         self._maybe_step_lr()
 
 
@@ -225,6 +242,7 @@ class SparseAdaGrad(_Base):
         for p in self._sparse:
             sr = getattr(p, "grad_rows", None)
             if sr is not None:
-                ops.raw_sparse_adagrad(p.data, self.g2sum(p), sr, self.get_lr(), self.g0, self.lo,
+                W, sr, _ = self._table_parts(p, sr)
+                ops.raw_sparse_adagrad(W, self.g2sum(p), sr, self.get_lr(), self.g0, self.lo,
                                        self.hi)
         self.step_count += 1

@@ -217,3 +217,89 @@ def test_din_faithful_frozen_attention_default():
     layer = net.DINLayer(8, 8, "sigmoid", False, False, 50, 11)
     assert all(not p.requires_grad for p in layer.attention.parameters())
     assert layer.linear_0.weight.requires_grad
+
+
+def test_wide_deep_gpubox_branch_vs_oracle():
+    """The reference's PSGPU branch (wide_deep/net.py:80-88): [show, click, emb] rows, CVM with
+    use_cvm=False, show/click pushed through the gradient and ACCUMULATED by the optimizer; uint64
+    feasigns hashed to rows on the device (bit-exact vs oracle/readers.hash_keys)."""
+    from oracle import nets, readers
+    from paddlerec_b200 import functional as BF
+    from paddlerec_b200 import optim
+    from paddlerec_b200.rank.wide_deep import net
+    from tests.util import slots
+    g = torch.Generator().manual_seed(31)
+    V, D, B, F = 211, 8, 37, 26
+    layer = net.WideDeepLayer(V, D, 13, F, [32, 16], sync_mode="gpubox", device="cuda")
+    assert layer.embedding.weight.shape == (V, D + 2)
+    with torch.no_grad():    # give the statistic columns some history
+        layer.embedding.weight[:, :2] = torch.randint(0, 5, (V, 2), generator=g).float().cuda()
+    keys = torch.randint(0, 2 ** 62, (B, F), generator=g)
+    keys[3, 5] = keys[7, 5]                                   # the same feasign twice in a slot
+    dense = torch.rand(B, 13, generator=g)
+    label = (torch.rand(B, 1, generator=g) < 0.4).float()
+    show_click = torch.stack([torch.ones(B), label[:, 0]], 1)  # static_model.py:88-94
+    slot = np.tile(np.arange(F, dtype=np.int32), B)
+    rows_ref = readers.hash_keys(keys.numpy().reshape(-1), V, slot).astype(np.int64).reshape(B, F)
+    p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in layer.state_dict().items()}
+    pred_ref = nets.wide_deep_forward_gpubox(p, slots(torch.from_numpy(rows_ref)), dense.double(), 2)
+    nets.log_loss(pred_ref, label.double()).mean().backward()
+
+    W0 = layer.embedding.weight.detach().clone()
+    opt = optim.SGD(0.1, layer.parameters())
+    pred = layer(keys.cuda(), dense.cuda(), show_click.cuda(), feasigns=True)
+    BF.log_loss(pred, label.cuda()).mean().backward()
+    assert rel_err(pred, pred_ref.detach()) < TOL
+    dW = layer.embedding.grad_rows.to_dense().cpu().double()
+    assert rel_err(dW[:, 2:], p["embedding.weight"].grad[:, 2:]) < TOL
+    # cvm_grad: the two leading gradient columns of a row are the sums of (show, click) over its
+    # positions in the batch
+    want_stats = torch.zeros(V, 2, dtype=torch.float64)
+    want_stats.index_add_(0, torch.from_numpy(rows_ref.reshape(-1)),
+                          show_click.double().repeat_interleave(F, dim=0))
+    assert torch.equal(dW[:, :2], want_stats)
+    for k, v in layer.named_parameters():
+        if k != "embedding.weight" and v.grad is not None:
+            assert rel_err(v.grad, p[k].grad) < TOL, k
+    opt.step()
+    W1 = layer.embedding.weight.detach().cpu().double()
+    assert torch.equal(W1[:, :2], W0[:, :2].cpu().double() + want_stats)      # accumulated, exact
+    assert rel_err(W1[:, 2:], W0[:, 2:].cpu().double() - 0.1 * p["embedding.weight"].grad[:, 2:]) < 1e-6
+
+
+def test_fused_seqpool_cvm_gpu_vs_oracle():
+    """ops.fused_seqpool_cvm itself (tools/utils/static_ps/model_util.py:411-415): multi-hot bags,
+    sum-pool + CVM in both modes, forward and the table gradient incl. the show/click columns."""
+    from oracle import nets
+    from paddlerec_b200 import nn as bnn
+    g = torch.Generator().manual_seed(8)
+    V, D, B, F = 101, 6, 19, 4
+    emb = bnn.Embedding(V, D + 2, padding_idx=0, init="uniform", device="cuda")
+    with torch.no_grad():
+        emb.weight[:, :2].abs_()
+    lens = torch.randint(0, 4, (B * F,), generator=g)
+    lens[5] = 0
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    keys = torch.randint(0, V, (int(offsets[-1]),), generator=g)
+    show_click = torch.stack([torch.ones(B), (torch.rand(B, generator=g) < 0.3).float()], 1)
+    W = emb.weight.detach().cpu().double()
+    for use_cvm in (False, True):
+        emb.clear_grad()
+        Wd = W.clone().requires_grad_(True)
+        rows = nets.embedding(Wd, keys, 0)
+        pooled = torch.zeros(B * F, D + 2, dtype=torch.float64)
+        bag = torch.repeat_interleave(torch.arange(B * F), lens)
+        pooled = pooled.index_add(0, bag, rows)
+        want = nets.cvm(pooled, use_cvm).reshape(B, F, -1)
+        gy = torch.randn(want.shape, generator=g, dtype=torch.float64)
+        # cvm_grad is not the derivative: only the embedding columns follow autograd
+        (want[..., (2 if use_cvm else 0):] * gy[..., (2 if use_cvm else 0):]).sum().backward()
+        got = emb.forward_seqpool_cvm(keys.cuda(), offsets.cuda(), F, show_click.cuda(), use_cvm)
+        assert rel_err(got, want.detach()) < 1e-5
+        (got * gy.float().cuda()).sum().backward()
+        dW = emb.grad_rows.to_dense().cpu().double()
+        assert rel_err(dW[:, 2:], Wd.grad[:, 2:]) < 1e-5
+        live = keys != 0
+        want_stats = torch.zeros(V, 2, dtype=torch.float64)
+        want_stats.index_add_(0, keys[live], show_click.double().repeat_interleave(F, dim=0)[bag][live])
+        assert rel_err(dW[:, :2], want_stats) < 1e-6 and not dW[0].any()
