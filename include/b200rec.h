@@ -251,6 +251,17 @@ int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_pl
 int b200rec_tc_linear_bwd_dw(const void* a_planes, int64_t lda, const void* g_planes, int64_t ldg,
                              float* dW, int64_t M, int K, int N, void* workspace,
                              size_t workspace_bytes, void* stream);
+/* The width-1 head of a CTR tower (last Linear of deepfm/net.py:169-174, K -> 1) as streaming
+ * kernels (HBM-bound: a GEMM tile would waste 15/16 of the tensor core on it):
+ *   tc_head_fwd  y[m] = sum_k a[m,k] w[k] + bias[0]          (a = planes [M,2*lda], w fp32 [K])
+ *   tc_head_bwd  g = planes(dy[m] * w[k] * (a_hi[m,k] > 0)) [M,2*ldg],  dW[k] = sum_m a[m,k] dy[m],
+ *                db[0] = sum_m dy[m]   (K % 8 == 0, K <= 2048; deterministic) */
+int b200rec_tc_head_fwd(const void* a_planes, int64_t lda, int K, const float* w, const float* bias,
+                        float* y, int64_t M, void* stream);
+int b200rec_tc_head_bwd_workspace_bytes(int K, size_t* bytes_host);
+int b200rec_tc_head_bwd(const void* a_planes, int64_t lda, int K, const float* w, const float* dy,
+                        void* g_planes, int64_t ldg, float* dW, float* db, int64_t M,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel;
  * 4: k-block of the K-major kernel, 64 = 128-byte swizzle, 32 = 64-byte swizzle, more stages)
  * and the device word a pipeline watchdog writes before it traps. */

@@ -386,6 +386,27 @@ int b200rec_tc_linear_bwd_dw(const void* a_planes, int64_t lda, const void* g_pl
                             ST(stream));
 }
 
+int b200rec_tc_head_fwd(const void* a_planes, int64_t lda, int K, const float* w, const float* bias,
+                        float* y, int64_t M, void* stream) {
+  if (M > 0) { NOT_NULL(a_planes); NOT_NULL(w); NOT_NULL(y); }
+  return launch_tower_head_fwd(a_planes, lda, K, w, bias, y, M, ST(stream));
+}
+
+int b200rec_tc_head_bwd_workspace_bytes(int K, size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  *bytes_host = tower_head_bwd_ws_bytes(K) + 16;
+  return B200REC_OK;
+}
+
+int b200rec_tc_head_bwd(const void* a_planes, int64_t lda, int K, const float* w, const float* dy,
+                        void* g_planes, int64_t ldg, float* dW, float* db, int64_t M,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  NOT_NULL(dW); NOT_NULL(db);
+  if (M > 0) { NOT_NULL(a_planes); NOT_NULL(w); NOT_NULL(dy); NOT_NULL(g_planes); NOT_NULL(workspace); }
+  return launch_tower_head_bwd(a_planes, lda, K, w, dy, g_planes, ldg, dW, db, M, workspace,
+                               workspace_bytes, ST(stream));
+}
+
 int b200rec_tc_debug(int key, int value) {
   switch (key) {
     case 0: tc::g_bn_override = value; break;

@@ -32,10 +32,12 @@ struct K1Config {
   int debug;
   int tma;  // 1: shared-memory-staged variant with a bulk (TMA) store of the feat tile
   int minb;  // __launch_bounds__ min blocks/SM (register cap) variants: 4 (default), 5, 6, 8
+  int warp_sched;  // 1: per-warp pipeline with a dynamic group scheduler (no CTA barriers)
 };
 static K1Config k1_config() {
   static K1Config cfg = [] {
-    K1Config c{13, 0, 8, 0, 0, 4};
+    K1Config c{13, 0, 8, 0, 0, 4, 0};
+    if (const char* s = getenv("B200REC_K1_WARP")) c.warp_sched = atoi(s);
     if (const char* s = getenv("B200REC_K1_UNROLL")) c.unroll = atoi(s);
     if (const char* s = getenv("B200REC_K1_CACHE")) c.cache_rows = atoi(s);
     if (const char* s = getenv("B200REC_K1_CTAS")) c.ctas_per_sm = atoi(s);
@@ -182,6 +184,151 @@ embed_fm_fwd_kernel(const float* __restrict__ W, const float* __restrict__ W1,
     __syncthreads();  // buffer (it&1) is free for the prefetch issued two iterations later
   }
   cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, warp-scheduled variant: the same per-sample arithmetic, but every WARP runs its own
+// double-buffered pipeline over groups of 32/TPR samples and takes its next group from a global
+// atomic counter.  Compared with the CTA-tiled kernel above there is no __syncthreads (the four
+// warps of a CTA no longer wait for the slowest one twice per tile), no static tile-to-CTA map
+// (2048 tiles over 1184 CTAs leaves a 1-vs-2 tile imbalance), and the id round trip of a warp's
+// FIRST group is the only one that is exposed.  sched[0] = next group, sched[1] = warps that have
+// finished; the last warp to finish resets both, so the buffer needs no memset between launches
+// (one launch at a time per scheduler buffer).
+__device__ unsigned int g_k1_sched[2] = {0u, 0u};
+
+template <int VEC, int TPR, int kFieldUnroll, bool CACHE>
+__global__ void __launch_bounds__(128, 4)
+embed_fm_fwd_warp_kernel(const float* __restrict__ W, const float* __restrict__ W1,
+                         const int64_t* __restrict__ ids, const float* __restrict__ dense,
+                         const float* __restrict__ dense_w, const float* __restrict__ dense_w1,
+                         float* __restrict__ feat, float* __restrict__ y1, float* __restrict__ y2,
+                         float* __restrict__ S, int64_t B, int F, int Dn, int D, int64_t V,
+                         int64_t pad, int64_t ldw, int64_t ldw1, int dbg) {
+  constexpr int SPW = 32 / TPR;                      // samples per warp-group (8 at D=16)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t ids_elems = (size_t)SPW * F;
+  const size_t dense_elems = (size_t)SPW * Dn;
+  const size_t buf_bytes = (ids_elems * 8 + dense_elems * 4 + 15) / 16 * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* my_smem = smem_raw + (size_t)warp * 2 * buf_bytes;
+  const unsigned ngroups = (unsigned)((B + SPW - 1) / SPW);
+  const int s = lane / TPR;
+  const int r = lane % TPR;
+  const bool lane_ok = r * VEC < D;
+  const int N = F + Dn;
+
+  auto grab = [&]() -> unsigned {
+    unsigned g = 0;
+    if (lane == 0) g = atomicAdd(&g_k1_sched[0], 1u);
+    return __shfl_sync(0xffffffffu, g, 0);
+  };
+  auto stage = [&](unsigned g, int buf) {
+    int64_t* s_ids = reinterpret_cast<int64_t*>(my_smem + (size_t)buf * buf_bytes);
+    float* s_dense = reinterpret_cast<float*>(s_ids + ids_elems);
+    const int64_t b0 = (int64_t)g * SPW;
+    const int nb = (int)min((int64_t)SPW, B - b0);
+    for (int i = lane; i < nb * F; i += 32) cp_async_8(s_ids + i, ids + b0 * F + i);
+    for (int i = lane; i < nb * Dn; i += 32) cp_async_4(s_dense + i, dense + b0 * Dn + i);
+  };
+
+  unsigned g = grab();
+  if (g < ngroups) stage(g, 0);
+  cp_async_commit();
+  unsigned gn = grab();
+  for (int it = 0; g < ngroups; ++it) {
+    if (gn < ngroups) stage(gn, (it + 1) & 1);
+    cp_async_commit();
+    const unsigned gnn = grab();   // consumed one iteration later: its latency hides behind this group
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const int64_t* s_ids = reinterpret_cast<const int64_t*>(my_smem + (size_t)(it & 1) * buf_bytes);
+    const float* s_dense = reinterpret_cast<const float*>(s_ids + ids_elems);
+    const int64_t b0 = (int64_t)g * SPW;
+    const int nb = (int)min((int64_t)SPW, B - b0);
+    const bool sample_ok = s < nb;
+    const int64_t b = b0 + s;
+
+    Vec<VEC> Ssum = vzero<VEC>();
+    Vec<VEC> Q = vzero<VEC>();
+    float first = 0.f;
+    if (sample_ok) {
+      const int64_t* my_ids = s_ids + (size_t)s * F;
+      float* feat_row = feat + (size_t)b * N * D + r * VEC;
+      for (int f0 = 0; f0 < F; f0 += kFieldUnroll) {
+        Vec<VEC> e[kFieldUnroll];
+        float w1v[kFieldUnroll];
+#pragma unroll
+        for (int j = 0; j < kFieldUnroll; ++j) {
+          const int f = f0 + j;
+          const int64_t id = (f < F) ? my_ids[f] : pad;
+          const bool in_range = (uint64_t)id < (uint64_t)V;
+          const bool live = (f < F) && in_range && id != pad && !(dbg & 2);
+          const size_t row = live ? (size_t)id : 0;
+          e[j] = ld_row_pred<VEC, CACHE>(W + row * ldw + r * VEC, live && lane_ok);
+          w1v[j] = ld_row_pred<1, true>(W1 + row * ldw1, live && ((f & (TPR - 1)) == r)).v[0];
+          if ((f < F) && !in_range && r == 0) atomicAdd(&g_oob_count, 1ull);
+        }
+#pragma unroll
+        for (int j = 0; j < kFieldUnroll; ++j) {
+          const int f = f0 + j;
+          if (f < F) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              Ssum.v[k] += e[j].v[k];
+              Q.v[k] = fmaf(e[j].v[k], e[j].v[k], Q.v[k]);
+            }
+            if (lane_ok && !(dbg & 1)) st_stream<VEC>(feat_row + (size_t)f * D, e[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kFieldUnroll; ++j) first += w1v[j];
+      }
+      const float* my_dense = s_dense + (size_t)s * Dn;
+      for (int j = 0; j < Dn; ++j) {
+        const float x = my_dense[j];
+        Vec<VEC> e = vzero<VEC>();
+        if (lane_ok) {
+          const Vec<VEC> w = ld_cached<VEC>(dense_w + (size_t)j * D + r * VEC);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) e.v[k] = x * w.v[k];
+          if (!(dbg & 1)) st_stream<VEC>(feat_row + (size_t)(F + j) * D, e);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          Ssum.v[k] += e.v[k];
+          Q.v[k] = fmaf(e.v[k], e.v[k], Q.v[k]);
+        }
+        if ((j & (TPR - 1)) == r) first = fmaf(x, __ldg(dense_w1 + j), first);
+      }
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) t += Ssum.v[k] * Ssum.v[k] - Q.v[k];
+    t = group_sum<TPR>(t);
+    first = group_sum<TPR>(first);
+    if (sample_ok) {
+      if (r == 0) {
+        y1[b] = first;
+        y2[b] = 0.5f * t;
+      }
+      if (S != nullptr && lane_ok) st_plain<VEC>(S + (size_t)b * D + r * VEC, Ssum);
+    }
+    __syncwarp();   // every lane is done with buffer (it&1) before the next iteration refills it
+    g = gn;
+    gn = gnn;
+  }
+  cp_async_wait<0>();
+  if (lane == 0) {
+    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned done = atomicAdd(&g_k1_sched[1], 1u);
+    if (done == total_warps - 1) {   // nobody else will touch the scheduler in this launch
+      g_k1_sched[0] = 0u;
+      g_k1_sched[1] = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -390,6 +537,23 @@ static int k1_tma_launch(const K1Args& a, cudaStream_t st) {
   return B200REC_OK;
 }
 
+template <int VEC, int TPR, int U>
+static int k1_warp_launch(const K1Args& a, int ctas_per_sm, cudaStream_t st) {
+  constexpr int SPW = 32 / TPR;
+  const size_t buf = ((size_t)SPW * a.F * sizeof(int64_t) + (size_t)SPW * a.Dn * sizeof(float) + 15) /
+                     16 * 16;
+  const size_t smem = 4 * 2 * buf;     // 4 warps x 2 buffers
+  auto kern = embed_fm_fwd_warp_kernel<VEC, TPR, U, false>;
+  if (smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ngroups = (a.B + SPW - 1) / SPW;
+  const int64_t grid = min((ngroups + 3) / 4, (int64_t)sm_count() * ctas_per_sm);
+  kern<<<(unsigned)grid, 128, smem, st>>>(a.W, a.W1, a.ids, a.dense, a.dense_w, a.dense_w1, a.feat,
+                                          a.y1, a.y2, a.S, a.B, a.F, a.Dn, a.D, a.V, a.pad, a.ldw,
+                                          a.ldw1, k1_config().debug);
+  return B200REC_OK;
+}
+
 template <int VEC, int TPR, int U, bool C, int MINB = 4>
 static int k1_launch(const K1Args& a, int64_t grid, size_t smem, cudaStream_t st) {
   auto kern = embed_fm_fwd_kernel<VEC, TPR, U, C, MINB>;
@@ -435,6 +599,10 @@ static int launch_embed_fm_fwd(const float* W, const float* W1, const int64_t* i
     if (VEC == 4 && cfg.tma && cfg.debug == 0 && aligned16(dense_w) && (ldw % 4 == 0) &&
         K1TmaSmem(kTmaThreads / TPR, F, Dn, D).total <= 110 * 1024)
       rc = k1_tma_launch<TPR>(a, st);
+    else if (cfg.warp_sched && cfg.unroll == 8)
+      rc = k1_warp_launch<VEC, TPR, 8>(a, cfg.ctas_per_sm, st);
+    else if (cfg.warp_sched)
+      rc = k1_warp_launch<VEC, TPR, 13>(a, cfg.ctas_per_sm, st);
     else if (cfg.minb == 5 && cfg.unroll == 13)
       rc = k1_launch<VEC, TPR, 13, false, 5>(a, grid, smem, st);
     else if (cfg.minb == 6 && cfg.unroll == 13)

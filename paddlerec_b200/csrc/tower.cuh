@@ -181,6 +181,132 @@ __global__ void tower_fold_dw_kernel(const float* __restrict__ Mx, float* __rest
   dW[i] = (Mx[r0 + n] + Mx[r0 + N + n]) + Mx[r1 + n];
 }
 
+// ------------------------------------------------------------------------------------------------
+// The width-1 head of a CTR tower (deepfm/net.py:169-174 last Linear: 400 -> 1) as two streaming
+// kernels instead of three 128 x 16-column GEMM tiles that would each re-stream the activations:
+//   head_fwd : y[m] = sum_k (a_hi + a_lo)[m,k] * w[k] + b                      reads 4K B/sample
+//   head_bwd : g[m,k] = dy[m] * w[k] * (a_hi[m,k] > 0)  -> planes (the next dX/dW operand),
+//              dW[k] = sum_m (a_hi + a_lo)[m,k] * dy[m],  db = sum_m dy[m]      reads 4K, writes 4K
+// One warp per row; a lane owns the same 8-column chunks for every row it visits, so the dW sums
+// stay in registers; warps -> CTA in shared memory, CTAs -> result in fixed order (deterministic).
+constexpr int kHeadThreads = 256;
+constexpr int kHeadMaxIter = 8;      // K <= 8 * 256
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+tower_head_fwd_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int K,
+                      const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ y, int64_t M) {
+  extern __shared__ float s_w[];
+  for (int k = threadIdx.x; k < K; k += kHeadThreads) s_w[k] = w[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (kHeadThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kHeadThreads / 32);
+  const float b = bias != nullptr ? __ldg(bias) : 0.f;
+  const int chunks = K / 8;
+  for (int64_t m = warp0; m < M; m += nwarps) {
+    const __nv_bfloat16* row = a + m * 2 * lda;
+    float acc = 0.f;
+    for (int c = lane; c < chunks; c += 32) {
+      const uint4 qh = __ldg(reinterpret_cast<const uint4*>(row) + c);
+      const uint4 ql = __ldg(reinterpret_cast<const uint4*>(row + lda) + c);
+      float h[8], l[8];
+      bf16x8_to_float(qh, h);
+      bf16x8_to_float(ql, l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(h[j] + l[j], s_w[c * 8 + j], acc);
+    }
+    for (int k = chunks * 8 + lane; k < K; k += 32)
+      acc = fmaf(__bfloat162float(row[k]) + __bfloat162float(row[lda + k]), s_w[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[m] = acc + b;
+  }
+}
+
+template <int NITER>
+__global__ void __launch_bounds__(kHeadThreads)
+tower_head_bwd_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int K,
+                      const float* __restrict__ w, const float* __restrict__ dy,
+                      __nv_bfloat16* __restrict__ g, int64_t ldg, float* __restrict__ partials,
+                      int64_t M) {
+  extern __shared__ float s_buf[];      // [K] w, then [warps][K + 1] per-warp dW partials
+  float* s_w = s_buf;
+  float* s_part = s_buf + K;
+  for (int k = threadIdx.x; k < K; k += kHeadThreads) s_w[k] = w[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * (kHeadThreads / 32) + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * (kHeadThreads / 32);
+  const int chunks = K / 8;             // K % 8 == 0 (checked on the host)
+  float acc[NITER][8];
+#pragma unroll
+  for (int i = 0; i < NITER; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float dsum = 0.f;
+  for (int64_t m = warp0; m < M; m += nwarps) {
+    const __nv_bfloat16* row = a + m * 2 * lda;
+    __nv_bfloat16* grow = g + m * 2 * ldg;
+    const float d = __ldg(dy + m);
+    dsum += d;
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+      const int c = lane + 32 * i;
+      if (c < chunks) {
+        const uint4 qh = __ldg(reinterpret_cast<const uint4*>(row) + c);
+        const uint4 ql = __ldg(reinterpret_cast<const uint4*>(row + lda) + c);
+        float h[8], l[8];
+        bf16x8_to_float(qh, h);
+        bf16x8_to_float(ql, l);
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v0 = h[2 * j] > 0.f ? d * s_w[c * 8 + 2 * j] : 0.f;
+          float v1 = h[2 * j + 1] > 0.f ? d * s_w[c * 8 + 2 * j + 1] : 0.f;
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          oh[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          v0 -= __uint_as_float(oh[j] << 16);
+          v1 -= __uint_as_float(oh[j] & 0xFFFF0000u);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0, v1);
+          ol[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        *(reinterpret_cast<uint4*>(grow) + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *(reinterpret_cast<uint4*>(grow + ldg) + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(h[j] + l[j], d, acc[i][j]);
+      }
+    }
+  }
+  // warp partials -> shared memory, CTA sum in fixed warp order, one partial row per CTA:
+  // partials[cta][0..K) = dW, partials[cta][K] = db
+  float* mine = s_part + (size_t)warp * (K + 1);
+#pragma unroll
+  for (int i = 0; i < NITER; ++i) {
+    const int c = lane + 32 * i;
+    if (c < chunks)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[c * 8 + j] = acc[i][j];
+  }
+  if (lane == 0) mine[K] = dsum;
+  __syncthreads();
+  for (int k = threadIdx.x; k <= K; k += kHeadThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) t += s_part[(size_t)wv * (K + 1) + k];
+    partials[(size_t)blockIdx.x * (K + 1) + k] = t;
+  }
+}
+
 constexpr int kTowerRowSlices = 148 * 4;
 static int tower_row_slices(int64_t M) {
   return (int)min((int64_t)kTowerRowSlices, M > 0 ? M : (int64_t)1);
@@ -241,6 +367,67 @@ static int launch_tower_relu_bwd_split(const float* dy, const void* act, int64_t
   B200_LAUNCH_CHECK();
   reduce_partials_kernel<<<reduce_partials_grid(N), kRedThreads, 0, st>>>(partials, slices, N, dbias, N,
                                                                           nullptr);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static int head_grid() { return sm_count() * 2; }
+
+static int launch_tower_head_fwd(const void* a, int64_t lda, int K, const float* w,
+                                 const float* bias, float* y, int64_t M, cudaStream_t st) {
+  B200_REQUIRE(K > 0 && M >= 0 && lda >= K && lda % 8 == 0 && aligned16(a),
+               "tower_head_fwd: bad sizes / alignment");
+  if (M == 0) return B200REC_OK;
+  const size_t smem = (size_t)K * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, "tower_head_fwd: K=%d too large", K);
+  const int64_t rows_per_cta = kHeadThreads / 32;
+  const int grid = (int)min((int64_t)head_grid(), (M + rows_per_cta - 1) / rows_per_cta);
+  tower_head_fwd_kernel<<<grid, kHeadThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(a), lda, K,
+                                                         w, bias, y, M);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static size_t tower_head_bwd_ws_bytes(int K) { return (size_t)head_grid() * (K + 1) * sizeof(float); }
+
+static int launch_tower_head_bwd(const void* a, int64_t lda, int K, const float* w, const float* dy,
+                                 void* g, int64_t ldg, float* dW, float* db, int64_t M, void* ws,
+                                 size_t ws_bytes, cudaStream_t st) {
+  B200_REQUIRE(K > 0 && K % 8 == 0 && K <= kHeadMaxIter * 256 && lda >= K && ldg >= K &&
+                   lda % 8 == 0 && ldg % 8 == 0 && aligned16(a) && aligned16(g),
+               "tower_head_bwd: K must be a multiple of 8 and <= %d, planes 16-byte aligned",
+               kHeadMaxIter * 256);
+  if (ws_bytes < tower_head_bwd_ws_bytes(K)) {
+    set_error("tower_head_bwd: workspace %zu < %zu bytes", ws_bytes, tower_head_bwd_ws_bytes(K));
+    return B200REC_ERR_WORKSPACE;
+  }
+  if (M == 0) {
+    B200_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * sizeof(float), st));
+    B200_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
+    return B200REC_OK;
+  }
+  const size_t smem = ((size_t)K + (size_t)(kHeadThreads / 32) * (K + 1)) * sizeof(float);
+  const int64_t rows_per_cta = kHeadThreads / 32;
+  const int grid = (int)min((int64_t)head_grid(), (M + rows_per_cta - 1) / rows_per_cta);
+  const int niter = (K / 8 + 31) / 32;
+  const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
+  __nv_bfloat16* gp = static_cast<__nv_bfloat16*>(g);
+  float* partials = static_cast<float*>(ws);
+#define B200_HEAD_BWD(NI)                                                                          \
+  do {                                                                                             \
+    auto kern = tower_head_bwd_kernel<NI>;                                                         \
+    if (smem > 48 * 1024)                                                                          \
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kHeadThreads, smem, st>>>(ap, lda, K, w, dy, gp, ldg, partials, M);               \
+  } while (0)
+  if (niter <= 1) B200_HEAD_BWD(1);
+  else if (niter <= 2) B200_HEAD_BWD(2);
+  else if (niter <= 4) B200_HEAD_BWD(4);
+  else B200_HEAD_BWD(8);
+#undef B200_HEAD_BWD
+  B200_LAUNCH_CHECK();
+  reduce_partials_kernel<<<reduce_partials_grid(K + 1), kRedThreads, 0, st>>>(partials, grid, K + 1, dW,
+                                                                              K, db);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

@@ -45,7 +45,7 @@ KERNELS_PER_CALL = {
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
     "tower_prep_weight": 1, "tower_fold_dw": 1, "tc_split": 1, "tc_split_bwd": 2,
     "tc_prep_weight": 1, "tc_linear_fwd": 1, "tc_cross_fwd": 1, "tc_linear_bwd_dx": 1,
-    "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
+    "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "tc_head_fwd": 1, "tc_head_bwd": 2, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around the raw_* calls
 # (all of them, or only the names in EVENT_FILTER when that is a set) — bench.py's per-kernel times.
@@ -169,14 +169,16 @@ def raw_embed_fm_fwd(W, W1, ids, dense, dense_w, dense_w1, padding_idx: int, wan
     return feat, y1, y2, S
 
 
-def raw_group_ids(ids: torch.Tensor, V: int, padding_idx: int) -> IdGroups:
+def raw_group_ids(ids: torch.Tensor, V: int, padding_idx: int, ws_tag: str = "group") -> IdGroups:
+    """ws_tag: a call enqueued on a SIDE stream must not share the scratch buffer of the calls on
+    the main stream (the workspace cache is ordered by stream, not across streams)."""
     lib = _lib.load()
     ids = _req(ids, torch.int64, "ids").reshape(-1)
     n = ids.numel()
     dev = ids.device
     nbytes = ctypes.c_size_t(0)
     check(lib.b200rec_group_ids_workspace_bytes(n, V, ctypes.byref(nbytes)), "group_ids_ws")
-    ws = workspace(nbytes.value, dev, "group")
+    ws = workspace(nbytes.value, dev, ws_tag)
     unique_ids = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     seg_offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     sorted_pos = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
@@ -578,6 +580,39 @@ def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int, bias_row: bool = Fa
     if bias_row:
         return dW[:K - 1], dW[K - 1]
     return dW
+
+
+def raw_tc_head_fwd(a_planes, K: int, w, bias) -> torch.Tensor:
+    """y [M,1] = a @ w + bias for a width-1 last layer (w fp32 [K,1] or [K]): one streaming pass."""
+    lib = _lib.load()
+    M = a_planes.shape[0]
+    y = torch.empty(M, 1, dtype=torch.float32, device=a_planes.device)
+    check(lib.b200rec_tc_head_fwd(ptr(a_planes), a_planes.shape[1] // 2, K,
+                                  ptr(_req(w.detach().reshape(-1), torch.float32, "w")), ptr(bias),
+                                  ptr(y), M, _stream()), "tc_head_fwd")
+    _count("tc_head_fwd")
+    return y
+
+
+def raw_tc_head_bwd(a_planes, K: int, w, dy):
+    """Backward of the width-1 head: (planes(g) [M, 2*ld(K)] with g = dy * w^T masked by a_hi > 0,
+    dW [K,1], db [1]) in one streaming pass + a fixed-order reduce."""
+    lib = _lib.load()
+    M = a_planes.shape[0]
+    dev = a_planes.device
+    g = _planes(M, K, dev)
+    dW = torch.empty(K, 1, dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    nbytes = ctypes.c_size_t(0)
+    check(lib.b200rec_tc_head_bwd_workspace_bytes(K, ctypes.byref(nbytes)), "tc_head_bwd_ws")
+    ws = workspace(nbytes.value, dev, "tc_head")
+    check(lib.b200rec_tc_head_bwd(ptr(a_planes), a_planes.shape[1] // 2, K,
+                                  ptr(_req(w.detach().reshape(-1), torch.float32, "w")),
+                                  ptr(_req(dy.reshape(-1), torch.float32, "dy")), ptr(g),
+                                  g.shape[1] // 2, ptr(dW), ptr(db), M, ptr(ws), ws.numel(),
+                                  _stream()), "tc_head_bwd")
+    _count("tc_head_bwd")
+    return g, dW, db
 
 
 def tc_debug(key: int, value: int) -> None:
@@ -1181,7 +1216,7 @@ def _wrap_timed(fn, name):
 for _n in ("group_ids", "embed_fm_bwd", "gather", "gather_pool_sum", "segment_reduce", "sparse_sgd",
            "sparse_adam", "sparse_adagrad", "cross_v2_fwd", "cross_v2_bwd", "shard_bucketize",
            "tc_split", "tc_split_bwd", "tc_prep_weight", "tc_linear_fwd", "tc_cross_fwd",
-           "tc_linear_bwd_dx", "tc_linear_bwd_dw", "din_attn_fwd", "din_attn_bwd", "tower_split",
+           "tc_linear_bwd_dx", "tc_linear_bwd_dw", "tc_head_fwd", "tc_head_bwd", "din_attn_fwd", "din_attn_bwd", "tower_split",
            "tower_relu_bwd_split", "tower_prep_weight", "tower_fold_dw"):
     globals()["raw_" + _n] = _wrap_timed(globals()["raw_" + _n], _n)
 del _n

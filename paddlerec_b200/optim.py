@@ -197,12 +197,18 @@ class Adam(_Base):
     @torch.no_grad()
     def step(self) -> None:
         self._prepare_grads()
+        self.step_sparse(prepared=True)
+        self.step_dense(prepared=True)
+
+    @torch.no_grad()
+    def step_sparse(self, prepared: bool = False) -> None:
+        """The row-wise table updates (first half of step(); sharded.DistributedOptimizer runs it
+        beside the dense all-reduce).  Without clipping / regularisers on the tables the two halves
+        are independent."""
+        if not prepared:
+            assert self._clip is None, "split stepping is not defined with gradient clipping"
         lr = self.get_lr()
         self.step_count += 1
-        if self._torch is not None:
-            for g in self._torch.param_groups:
-                g["lr"] = lr
-            self._torch.step()
         b1p = self.beta1 ** self.step_count
         b2p = self.beta2 ** self.step_count
         for p in self._sparse:
@@ -212,6 +218,17 @@ class Adam(_Base):
                 W, sr, k = self._table_parts(p, sr)
                 ops.raw_sparse_adam(W, m[:, k:], v[:, k:], sr, lr, self.beta1, self.beta2, self.eps,
                                     b1p, b2p)
+
+    @torch.no_grad()
+    def step_dense(self, prepared: bool = False) -> None:
+        """Second half of step(): the replicated dense parameters (torch's fused Adam)."""
+        if not prepared:
+            self._apply_regularizers()
+        lr = self.get_lr()
+        if self._torch is not None:
+            for g in self._torch.param_groups:
+                g["lr"] = lr
+            self._torch.step()
         self._maybe_step_lr()
 
 

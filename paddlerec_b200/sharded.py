@@ -52,6 +52,7 @@ class ExchangePlan:
     send_splits: List[int]    # ids sent to each rank
     recv_splits: List[int]    # ids received from each rank
     recv_ids: torch.Tensor    # int64 [m]: local rows requested from this rank (owner view)
+    owner_groups: object = None   # grouping of recv_ids by local row, if it was precomputed
 
 
 class _PendingPlan:
@@ -71,10 +72,14 @@ class ShardExchange:
     D2H copy of the NEXT batch run on a side stream while the current step computes; by the time
     `plan(ids_next)` is called the counts are already on the host."""
 
-    def __init__(self, V: int, rank: int, world: int, group=None, kernels=_cuda_ops):
+    def __init__(self, V: int, rank: int, world: int, group=None, kernels=_cuda_ops,
+                 owner_pad: Optional[int] = None):
         self.V, self.rank, self.world, self.group, self.k = V, rank, world, group, kernels
         self._pending = None
         self._side = None
+        # local padding row of the tables behind this exchange (None = unknown): lets the prefetch
+        # also run the OWNER-side grouping of the received ids (a CUB sort) off the critical path
+        self.owner_pad = owner_pad
 
     def _bucketize_and_count(self, ids):
         send_ids, perm, inv_perm, counts = self.k.raw_shard_bucketize(ids, self.world, self.V)
@@ -116,10 +121,17 @@ class ShardExchange:
             recv_ids = torch.empty(sum(recv_splits), dtype=torch.int64, device=pend.send_ids.device)
             dist.all_to_all_single(recv_ids, pend.send_ids, recv_splits, send_splits,
                                    group=self.group)
+            groups = None
+            if self.owner_pad is not None:
+                # what owner_reduce() needs in the backward of the NEXT step: done here, on the side
+                # stream, while the current backward runs (own scratch buffer: ws_tag)
+                groups = self.k.raw_group_ids(recv_ids, max(shard_rows(self.V, self.rank, self.world), 1),
+                                              self.owner_pad, ws_tag="group_side")
             ev = torch.cuda.Event()
             ev.record(self._side)
         recv_ids.record_stream(self._side)
         pend.recv_ids, pend.splits, pend.event2 = recv_ids, (send_splits, recv_splits), ev
+        pend.groups = groups
 
     def plan(self, ids: torch.Tensor) -> ExchangePlan:
         pend, self._pending = self._pending, None
@@ -130,9 +142,15 @@ class ShardExchange:
             if getattr(pend, "recv_ids", None) is not None:       # fully prefetched
                 torch.cuda.current_stream().wait_event(pend.event2)
                 send_splits, recv_splits = pend.splits
+                cur = torch.cuda.current_stream()
                 for t in (pend.recv_ids, perm, inv_perm):
-                    t.record_stream(torch.cuda.current_stream())
-                return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, pend.recv_ids)
+                    t.record_stream(cur)
+                groups = getattr(pend, "groups", None)
+                if groups is not None:
+                    for t in (groups.unique_ids, groups.seg_offsets, groups.sorted_pos, groups.num):
+                        t.record_stream(cur)
+                return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, pend.recv_ids,
+                                    groups)
             pend.event.synchronize()                              # normally long complete
             torch.cuda.current_stream().wait_event(pend.event)
             send_splits, recv_splits = pend.host_counts[0].tolist(), pend.host_counts[1].tolist()
@@ -168,7 +186,9 @@ class ShardExchange:
 
     def owner_reduce(self, plan: ExchangePlan, grads: torch.Tensor, V_loc: int, local_pad: int):
         """Merge the received gradients by local row -> SelectedRows on the local shard."""
-        groups = self.k.raw_group_ids(plan.recv_ids, max(V_loc, 1), local_pad)
+        groups = plan.owner_groups
+        if groups is None or local_pad != self.owner_pad:
+            groups = self.k.raw_group_ids(plan.recv_ids, max(V_loc, 1), local_pad)
         rows = self.k.raw_segment_reduce(grads.contiguous(), groups.seg_offsets, groups.sorted_pos,
                                          groups.num, groups.n)
         return self.k.SelectedRows(groups.unique_ids, rows, groups.num, V_loc)
@@ -210,7 +230,8 @@ class ShardedEmbedding(bnn.Embedding):
         super().__init__(shard_rows(num_embeddings, rank, world), embedding_dim, local_pad,
                          init_std=init_std, init=init, device=device)
         self.global_rows, self.rank, self.world = num_embeddings, rank, world
-        self.exchange = ShardExchange(num_embeddings, rank, world, group, kernels)
+        self.exchange = ShardExchange(num_embeddings, rank, world, group, kernels,
+                                      owner_pad=(-1 if local_pad is None else local_pad))
 
     def forward(self, ids):
         return _ShardedLookup.apply(ids, self, bnn._autograd_hook(ids.device))
@@ -333,7 +354,8 @@ class ShardedFM(bnn.FusedTableOwner):
             torch.empty(1, dense_feature_dim, sparse_feature_dim, device=device))
         tnn.init.trunc_normal_(self.dense_w_one, 0.0, std, -2 * std, 2 * std)
         tnn.init.trunc_normal_(self.dense_w, 0.0, std, -2 * std, 2 * std)
-        self.exchange = ShardExchange(sparse_feature_number, rank, world, group, kernels)
+        self.exchange = ShardExchange(sparse_feature_number, rank, world, group, kernels,
+                                      owner_pad=(0 if rank == 0 else -1))   # padding id 0 lives on rank 0
         self._trivial = {}
 
     def table_grad_dense(self):
@@ -408,6 +430,7 @@ class DistributedOptimizer:
     def __init__(self, inner, model: tnn.Module, world: int, group=None):
         self.inner, self.world, self.group = inner, world, group
         self._dense = [p for p in dense_parameters(model) if p.requires_grad]
+        self._side = None
         if world > 1 and hasattr(inner, "sparse_sq_reduce"):
             # ClipGradByGlobalNorm (DCN-V2): the table gradients live on their owners, so the
             # squared norm of that part is one scalar all-reduce; the dense part is identical on
@@ -425,7 +448,7 @@ class DistributedOptimizer:
     def clear_grad(self):
         self.inner.clear_grad()
 
-    def step(self):
+    def _allreduce_dense(self):
         grads = [p.grad for p in self._dense if p.grad is not None]
         if grads and self.world > 1:
             with _timed("nccl_allreduce_dense"):
@@ -435,7 +458,26 @@ class DistributedOptimizer:
                 for g in grads:
                     g.copy_(flat[off:off + g.numel()].view_as(g))
                     off += g.numel()
-        self.inner.step()
+
+    def step(self):
+        inner = self.inner
+        split = (hasattr(inner, "step_sparse") and getattr(inner, "_clip", None) is None
+                 and self.world > 1 and self._dense and self._dense[0].is_cuda)
+        if not split:       # clipping needs the reduced gradients first (global norm)
+            self._allreduce_dense()
+            inner.step()
+            return
+        # The dense all-reduce runs on a side stream while the row-wise table update (the large
+        # part of the optimizer) runs on the main stream; they touch disjoint tensors.
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._allreduce_dense()
+        inner.step_sparse()
+        main.wait_stream(self._side)
+        inner.step_dense()
 
 
 def create_sharded_deepfm(config, device, rank, world, group=None, kernels=_cuda_ops):

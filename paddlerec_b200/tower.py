@@ -53,22 +53,32 @@ class _TowerTcFn(torch.autograd.Function):
         # 128-row dW tile, a column of ones rides in the input planes and the dW GEMM delivers the
         # column sum as an extra output row for free; otherwise the dX epilogue sums columns.
         ones = [b is not None and W.shape[0] % 128 != 0 for W, b in zip(Ws, bs)]
+        # A width-1 last layer (the CTR logit) is two streaming kernels, not GEMM tiles
+        head = (n_layers >= 2 and Ws[-1].shape[1] == 1 and not last_act and
+                Ws[-1].shape[0] % 8 == 0 and Ws[-1].shape[0] <= 2048)
+        if head:
+            ones[-1] = False
         a = ops.raw_tc_split(x, ones_col=ones[0])
         acts, wps = [a], []
         y = None
         for i in range(n_layers):
             K, N = Ws[i].shape
+            last = i == n_layers - 1
+            if last and head:
+                y = ops.raw_tc_head_fwd(a, K, Ws[i], bs[i])
+                wps.append(None)
+                break
             Wp, WTp = ops.raw_tc_prep_weight(Ws[i])
             wps.append(Wp)
-            last = i == n_layers - 1
             relu = (not last) or last_act
             y, a = ops.raw_tc_linear_fwd(a, K, WTp, N, bs[i], relu, want_f32=last,
                                          want_planes=(not last) or last_act,
                                          ones_col=(not last) and ones[i + 1])
             if a is not None:
                 acts.append(a)
-        ctx.n_layers, ctx.last_act, ctx.ones = n_layers, last_act, ones
+        ctx.n_layers, ctx.last_act, ctx.ones, ctx.head = n_layers, last_act, ones, head
         ctx.acts, ctx.wps = acts, wps
+        ctx.w_last = Ws[-1].detach() if head else None
         ctx.shapes = [tuple(W.shape) for W in Ws]
         ctx.has_bias = [b is not None for b in bs]
         return y
@@ -78,9 +88,23 @@ class _TowerTcFn(torch.autograd.Function):
         n, ones = ctx.n_layers, ctx.ones
         acts, wps = ctx.acts, ctx.wps
         dWs, dbs = [None] * n, [None] * n
-        g, db = ops.raw_tc_split_bwd(dy.contiguous(), acts[n] if ctx.last_act else None)
+        top = n - 1
+        if ctx.head:
+            # g of the layer below, dW and db of the head in one pass over its input activations
+            K = ctx.shapes[top][0]
+            g, dWs[top], db_head = ops.raw_tc_head_bwd(acts[top], K, ctx.w_last, dy.contiguous())
+            dbs[top] = db_head if ctx.has_bias[top] else None
+            top -= 1
+            db = None
+            if ctx.has_bias[top] and not ones[top]:
+                # rare (input width of that layer a multiple of 128): column sums of g
+                ld = g.shape[1] // 2
+                N_top = ctx.shapes[top][1]
+                db = (g[:, :N_top].float() + g[:, ld:ld + N_top].float()).sum(0)
+        else:
+            g, db = ops.raw_tc_split_bwd(dy.contiguous(), acts[n] if ctx.last_act else None)
         dx0 = None
-        for i in range(n - 1, -1, -1):
+        for i in range(top, -1, -1):
             K, N = ctx.shapes[i]
             if ones[i]:
                 dWs[i], dbs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N, bias_row=True)

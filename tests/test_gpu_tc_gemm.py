@@ -313,3 +313,27 @@ def test_tower_backends_match_fp64(backend, last_act, sizes):
     assert rel_err(xc.grad, xd.grad) < 1e-4
     for a, b in zip(Wc + bc, Wd + bd):
         assert rel_err(a.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,K", [(1000, 400), (257, 8), (5000, 2048), (70, 520)])
+def test_tc_head_width1_layer(M, K):
+    """The streaming kernels of the width-1 head (forward GEMV, backward outer product + mask +
+    split + dW/db) vs fp64."""
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(M + K)
+    act = torch.randn(M, K, generator=g_).clamp_min(0)
+    w = torch.randn(K, 1, generator=g_) / K ** 0.5
+    b = torch.randn(1, generator=g_)
+    dy = torch.randn(M, 1, generator=g_)
+    ap = ops.raw_tc_split(act.to(DEV))
+    a64 = _join(ap, K).cpu()                      # what the kernel actually reads (hi + lo)
+    y = ops.raw_tc_head_fwd(ap, K, w.to(DEV), b.to(DEV))
+    assert _err(y, a64 @ w.double() + b.double()) < 1e-5
+    gp, dW, db = ops.raw_tc_head_bwd(ap, K, w.to(DEV), dy.to(DEV))
+    torch.cuda.synchronize()
+    want_g = (dy.double() @ w.double().t()) * (ap[:, :K].double().cpu() > 0)
+    assert _err(_join(gp, K), want_g) < 2e-5
+    assert _err(dW, a64.t() @ dy.double()) < 1e-5
+    assert abs(float(db) - float(dy.double().sum())) < 1e-5 * float(dy.abs().sum())
+    gp2, dW2, db2 = ops.raw_tc_head_bwd(ap, K, w.to(DEV), dy.to(DEV))
+    assert torch.equal(dW, dW2) and torch.equal(db, db2)        # deterministic

@@ -36,6 +36,18 @@ def child():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / 20
+    # correctness of this variant on a slice (bit-exact gathers, fp64 sums)
+    feat, y1, y2, S = ops.raw_embed_fm_fwd(Wf, None, ids[0], den[0], dw, dw1, 0, D=D)
+    n = 4096
+    rows = Wf[ids[0][:n]]                                   # [n,F,32]
+    live = (ids[0][:n] != 0).unsqueeze(2)
+    fe = torch.cat([rows[..., :D] * live, den[0][:n].unsqueeze(2) * dw.unsqueeze(0)], 1)
+    ok = bool(torch.equal(feat[:n], fe))
+    Sd = fe.double().sum(1)
+    y2r = 0.5 * (Sd.square() - fe.double().square().sum(1)).sum(1)
+    y1r = (rows[..., D].double() * live[..., 0]).sum(1) + (den[0][:n].double() * dw1.double()).sum(1)
+    err = max(float((y2[:n].double() - y2r).abs().max()), float((y1[:n].double() - y1r).abs().max()),
+              float((S[:n].double() - Sd).abs().max()))
     alg = B * (F * 8 + Dn * 4 + F * 4 * D + F * 4 + (F + Dn) * 4 * D + 8)
     a = t(lambda i: ops.raw_embed_fm_fwd(W, W1, ids[i], den[i], dw, dw1, 0))
     b = t(lambda i: ops.raw_embed_fm_fwd(Wf, None, ids[i], den[i], dw, dw1, 0, D=D))
@@ -45,6 +57,8 @@ def child():
                       "debug_mask": os.environ.get("B200REC_K1_DEBUG"),
                       "tma_variant": os.environ.get("B200REC_K1_TMA"),
                       "minb": os.environ.get("B200REC_K1_MINB"),
+                      "warp_sched": os.environ.get("B200REC_K1_WARP"),
+                      "feat_exact": ok, "max_abs_err": err,
                       "two_tables_ms": a, "two_tables_GBps": alg / a / 1e6,
                       "fused_slots_ms": b, "fused_slots_GBps": alg / b / 1e6}), flush=True)
 
@@ -57,6 +71,13 @@ if __name__ == "__main__":
             for u, mb, ctas in (("13", "4", "8"), ("13", "5", "5"), ("13", "5", "10"), ("13", "6", "6"),
                                 ("13", "6", "12"), ("8", "6", "6"), ("8", "8", "8"), ("8", "8", "16")):
                 env = dict(os.environ, B200REC_K1_UNROLL=u, B200REC_K1_MINB=mb, B200REC_K1_CTAS=ctas)
+                subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
+            sys.exit(0)
+        if len(sys.argv) > 1 and sys.argv[1] == "warp":
+            # CTA-tiled kernel vs the warp-scheduled one (dynamic groups, no CTA barriers)
+            for w, u, ctas in (("0", "13", "8"), ("1", "13", "4"), ("1", "13", "8"), ("1", "13", "16"),
+                               ("1", "8", "4"), ("1", "8", "8"), ("1", "8", "16")):
+                env = dict(os.environ, B200REC_K1_WARP=w, B200REC_K1_UNROLL=u, B200REC_K1_CTAS=ctas)
                 subprocess.run([sys.executable, __file__, "child"], env=env, check=False)
             sys.exit(0)
         if len(sys.argv) > 1 and sys.argv[1] == "tma":
