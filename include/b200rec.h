@@ -263,7 +263,9 @@ int b200rec_tc_head_bwd(const void* a_planes, int64_t lda, int K, const float* w
                         void* g_planes, int64_t ldg, float* dW, float* db, int64_t M,
                         void* workspace, size_t workspace_bytes, void* stream);
 /* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel;
- * 4: k-block of the K-major kernel, 64 = 128-byte swizzle, 32 = 64-byte swizzle, more stages)
+ * 4: k-block of the K-major kernel, 64 = 128-byte swizzle, 32 = 64-byte swizzle, more stages;
+ * 5: epilogue outputs through TMA bulk stores (1) or register stores (0); 6: K-major GEMM on CTA
+ * pairs (tcgen05 cta_group::2, 256-row tiles) for M >= 4096)
  * and the device word a pipeline watchdog writes before it traps. */
 int b200rec_tc_debug(int key, int value);
 int b200rec_tc_timeout_word(unsigned int* word_host);

@@ -415,6 +415,7 @@ int b200rec_tc_debug(int key, int value) {
     case 3: tc::g_dw_debug.sbo = (uint32_t)value; break;
     case 4: tc::g_bk = value == 32 ? 32 : 64; break;
     case 5: tc::g_tma_store = value != 0; break;
+    case 6: tc::g_two_cta = value != 0; break;
     default: set_error("tc_debug: unknown key %d", key); return B200REC_ERR_INVALID;
   }
   return B200REC_OK;

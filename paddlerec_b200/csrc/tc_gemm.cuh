@@ -140,6 +140,61 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrival on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the barrier at local offset `bar` in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote)
+               : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -174,10 +229,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)layout << 61);
 }
 // instruction descriptor for kind::f16: fp32 accumulate, bf16 x bf16, M = 128, N = n
-__host__ __device__ inline uint32_t umma_idesc(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ inline uint32_t umma_idesc(int n, int a_mn_major, int b_mn_major,
+                                               int m = 128) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn_major & 1) << 15) |
          ((uint32_t)(b_mn_major & 1) << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(kBM >> 4) << 24);
+         ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -721,6 +777,250 @@ tc_gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-major GEMM on CTA PAIRS (cta_group::2): the two SMs of a cluster compute one 256 x BN tile.
+// Each CTA loads its own 128 rows of A but only HALF of the B tile; tcgen05.mma.cta_group::2 (issued
+// by the leader CTA alone) reads B from both shared memories, so the L2 -> SM operand traffic per
+// flop drops by ~30 % (A 32 KB + B 26 KB per k-block per SM instead of 32 + 52 at BN = 208) — the
+// 1-CTA kernel above is bound by exactly that traffic — and the freed shared memory holds a third
+// pipeline stage.  Protocol (as CUTLASS's 2-SM pipelines): both producers signal the LEADER's full
+// barrier (peer bit of the barrier address cleared), the leader arms it with the bytes of both;
+// tcgen05.commit multicasts the slot release and the accumulator-ready signal to both CTAs; the
+// peer's epilogue warps arrive remotely on the leader's TMEM-empty barrier.
+// ------------------------------------------------------------------------------------------------
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsK, 1)
+tc_gemm_kmajor2_kernel(const __grid_constant__ CUtensorMap tmA_hi,
+                      const __grid_constant__ CUtensorMap tmA_lo,
+                      const __grid_constant__ CUtensorMap tmB_hi,
+                      const __grid_constant__ CUtensorMap tmB_lo,
+                      const __grid_constant__ CUtensorMap tmO_hi,
+                      const __grid_constant__ CUtensorMap tmO_lo,
+                      const __grid_constant__ CUtensorMap tmO_f32, int M, int N, int K, int BN,
+                      int stages, Epilogue ep) {
+  constexpr uint32_t kRow = BK * 2;                       // bytes per operand row in a stage
+  constexpr uint32_t kLayout = BK == 64 ? 2u : 4u;        // SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t kSbo = 8u * kRow;                    // 8-row swizzle atom
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;          // swizzled tiles: atom-aligned
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t cta_rank = cluster_ctarank();          // 0 = leader: issues every tcgen05.mma
+  const bool leader = cta_rank == 0;
+  const int half_bn = BN / 2;                            // B rows held by EACH CTA of the pair
+  const uint32_t a_bytes = kBM * kRow;
+  const uint32_t b_bytes = (uint32_t)half_bn * kRow;
+  const uint32_t stage_bytes = 2u * a_bytes + 2u * b_bytes;
+  // [stages][output staging: 4 KB per epilogue warp][barriers][tmem ptr][colsum scratch]
+  const uint32_t stage_end = (uint32_t)stages * stage_bytes;
+  const uint32_t staging = base + stage_end;
+  const uint32_t bar_off = stage_end + kEpiWarps * kStagingPerWarp;
+  const uint32_t bar0 = base + bar_off;
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 8u * stages;
+  const uint32_t bar_tfull = bar0 + 16u * stages, bar_tempty = bar_tfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (size_t)bar_off + 16 * stages + 32);
+  float* s_colsum = reinterpret_cast<float*>(sm + (size_t)bar_off + 16 * stages + 64);
+  // s_colsum: [4 lane quarters][kMaxBN], only with ep.colsum
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + 2 * kBM - 1) / (2 * kBM), tiles_n = (N + BN - 1) / BN;   // 256-row pairs
+  const int n_tiles = tiles_m * tiles_n;
+  const int nkb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    if (ep.tma_planes) { prefetch_tmap(&tmO_hi); prefetch_tmap(&tmO_lo); }
+    if (ep.tma_f32) prefetch_tmap(&tmO_f32);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8u * s, 1);
+      mbar_init(bar_tempty + 8u * s, 2 * kEpiWarps);   // the epilogue warps of BOTH CTAs (leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(tmem_slot), kTmemCols);   // collective over the CTA pair (same warp id in both)
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync();      // barriers of both CTAs are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int m0 = (tile / tiles_n) * 2 * kBM + (int)cta_rank * kBM;
+        const int n0 = (tile % tiles_n) * BN;
+        int n_cur = N - n0;
+        n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
+        const int nb0 = n0 + (int)cta_rank * (n_cur / 2);     // this CTA's half of the B rows
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u, 0x100u + stage);
+          // transaction bytes of BOTH CTAs land on the leader's barrier (peer bit cleared)
+          const uint32_t full = (bar_full + 8u * stage) & 0xFEFFFFFFu;
+          const uint32_t sA = base + (uint32_t)stage * stage_bytes;
+          if (leader) mbar_expect_tx(bar_full + 8u * stage, 2u * stage_bytes);
+          tma_load_2d_2sm(sA, &tmA_hi, full, kb * BK, m0);
+          tma_load_2d_2sm(sA + a_bytes, &tmA_lo, full, kb * BK, m0);
+          tma_load_2d_2sm(sA + 2u * a_bytes, &tmB_hi, full, kb * BK, nb0);
+          tma_load_2d_2sm(sA + 2u * a_bytes + b_bytes, &tmB_lo, full, kb * BK, nb0);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        const int n0 = (tile % tiles_n) * BN;
+        int n_cur = N - n0;
+        n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
+        const uint32_t idesc = umma_idesc(n_cur, 0, 0, 2 * kBM);   // M = 256 over the two SMs
+        mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u, 0x200u + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccStride;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_full + 8u * stage, phase, 0x300u + stage);
+          tc_fence_after();
+          const uint32_t sA = base + (uint32_t)stage * stage_bytes;
+          const uint32_t sB = sA + 2u * a_bytes;
+          int ksteps = (K - kb * BK + kUK - 1) / kUK;
+          ksteps = ksteps > BK / kUK ? BK / kUK : ksteps;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint32_t ko = (uint32_t)j * (kUK * 2);   // 32 bytes further inside the swizzle row
+            const uint64_t a_hi = umma_desc(sA + ko, 16, kSbo, kLayout);
+            const uint64_t a_lo = umma_desc(sA + a_bytes + ko, 16, kSbo, kLayout);
+            const uint64_t b_hi = umma_desc(sB + ko, 16, kSbo, kLayout);
+            const uint64_t b_lo = umma_desc(sB + b_bytes + ko, 16, kSbo, kLayout);
+            tc_mma2(d_tmem, a_hi, b_hi, idesc, (kb | j) != 0 ? 1u : 0u);
+            tc_mma2(d_tmem, a_lo, b_hi, idesc, 1u);
+            tc_mma2(d_tmem, a_hi, b_lo, idesc, 1u);
+          }
+          tc_commit2(bar_empty + 8u * stage);                 // frees the slot in BOTH CTAs
+          if (kb == nkb - 1) tc_commit2(bar_tfull + 8u * acc);  // both epilogues may start
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // epilogue: a warp may touch TMEM lanes 32*(warp%4) .. +31 only; the two warps that share a
+    // lane quarter take alternate 32-column chunks
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool want_colsum = ep.colsum != nullptr;
+    const bool tma_p = ep.tma_planes != 0 && !want_colsum, tma_f = ep.tma_f32 != 0 && !want_colsum;
+    const uint32_t sbuf = staging + (uint32_t)(warp - 2) * kStagingPerWarp;
+    const bool base_aligned =
+        (ep.out_f32 == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_f32) | (ep.ld_f32 * 4)) & 15u) == 0) &&
+        (ep.out_planes == nullptr || ((reinterpret_cast<uintptr_t>(ep.out_planes) | (ep.ldp * 2)) & 15u) == 0) &&
+        (ep.mask_src == nullptr || ((reinterpret_cast<uintptr_t>(ep.mask_src) | (ep.ld_mask * 2)) & 15u) == 0) &&
+        (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15u) == 0) &&
+        (ep.addend == nullptr || ((reinterpret_cast<uintptr_t>(ep.addend) | (ep.ld_add * 4)) & 15u) == 0) &&
+        (ep.aux_f32 == nullptr || ((reinterpret_cast<uintptr_t>(ep.aux_f32) | (ep.ld_aux * 4)) & 15u) == 0) &&
+        (ep.cross_x0 == nullptr ||
+         ((reinterpret_cast<uintptr_t>(ep.cross_x0) | reinterpret_cast<uintptr_t>(ep.cross_xl) |
+           (ep.ld_cross * 4)) & 15u) == 0);
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      const int m_blk = (tile / tiles_n) * 2 + (int)cta_rank;
+      const int m0 = m_blk * kBM, n0 = (tile % tiles_n) * BN;
+      const int n_tile = (N - n0) < BN ? (N - n0) : BN;
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      // warp-uniform on purpose: tcgen05.ld is .sync.aligned, so the 32 lanes must not split into a
+      // fast and a slow path inside the chunk loop (a partially valid last row block goes slow)
+      const bool fast_ok =
+          base_aligned && ((int64_t)m0 + q * 32 + 31 < M) && (n0 & 7) == 0 && !want_colsum;
+      mbar_wait(bar_tfull + 8u * acc, acc_phase, 0x400u + acc);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccStride;
+      for (int c0 = half * 32; c0 < n_tile; c0 += 64) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        const int nv = (n_tile - c0) < 32 ? (n_tile - c0) : 32;
+        const bool fast = fast_ok && nv == 32;
+        uint4 mk[4];
+        if (fast && ep.mask_src != nullptr) {    // in flight while the TMEM load completes
+          const uint4* mp = reinterpret_cast<const uint4*>(ep.mask_src + row * ep.ld_mask + n0 + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) mk[g] = __ldg(mp + g);
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        // Full 32-column chunks leave through the TMA staging buffer; a partial chunk (tile width
+        // not a multiple of 32) is stored directly: its 32-wide box would spill into the
+        // neighbouring tile's columns (the tensor map clips only at the matrix edge).
+        const bool via_tma = (tma_p || tma_f) && nv == 32;
+        const bool st_f = !(tma_f && via_tma), st_p = !(tma_p && via_tma);
+        if (fast)
+          epilogue_fast(ep, v, row, n0 + c0, mk, st_f, st_p);
+        else
+          epilogue_chunk(ep, v, row, row_ok, n0 + c0, nv, lane,
+                         want_colsum ? s_colsum + q * kMaxBN + c0 : nullptr, st_f, st_p);
+        if (via_tma) {
+          if (lane == 0) bulk_wait_read0();      // the previous store has finished reading sbuf
+          __syncwarp();
+          if (tma_p)
+            stage_planes(sbuf, lane, v);
+          else
+            stage_f32(sbuf, lane, v);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (tma_p) {
+              tma_store_2d(&tmO_hi, sbuf, n0 + c0, m0 + q * 32);
+              tma_store_2d(&tmO_lo, sbuf + 2048u, n0 + c0, m0 + q * 32);
+            } else {
+              tma_store_2d(&tmO_f32, sbuf, n0 + c0, m0 + q * 32);
+            }
+            bulk_commit();
+          }
+        }
+      }
+      if (ep.ones_col && ep.out_planes != nullptr && row_ok && half == 0 && n0 + n_tile == N) {
+        __nv_bfloat16* oh = ep.out_planes + row * 2 * ep.ldp + N;
+        oh[0] = __float2bfloat16_rn(1.f);
+        oh[ep.ldp] = __float2bfloat16_rn(0.f);
+      }
+      // accumulator drained -> the MMA warp may overwrite this stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_tempty + 8u * acc, 0u);   // the leader's MMA warp waits on it
+      if (want_colsum) {
+        named_bar_sync(1, 32 * kEpiWarps);
+        const int t = threadIdx.x - 64;
+        for (int c = t; c < n_tile; c += 32 * kEpiWarps) {
+          const float s = ((s_colsum[c] + s_colsum[kMaxBN + c]) + s_colsum[2 * kMaxBN + c]) +
+                          s_colsum[3 * kMaxBN + c];
+          ep.colsum[(int64_t)m_blk * N + n0 + c] = s;
+        }
+        named_bar_sync(1, 32 * kEpiWarps);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if ((tma_p || tma_f) && lane == 0) bulk_wait0();   // shared memory must outlive the stores
+  }
+  tc_fence_before();
+  cluster_sync();      // nobody leaves while the peer may still signal / read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dW GEMM: P[split][K,N] = sum_{m in split} A[m,K]^T G[m,N]   (both operands MN-major)
 // ------------------------------------------------------------------------------------------------
 struct DwDebug {
@@ -1011,6 +1311,7 @@ static int pick_bn(int N) {
 
 static DwDebug g_dw_debug = {0u, 0u, 0u};
 static int g_bn_override = 0;
+static int g_two_cta = 0;     // K-major GEMM on CTA pairs (cta_group::2): 0 off, 1 on when M >= 4096
 static int g_tma_store = 1;   // epilogue outputs through TMA bulk stores (0: direct stores)
 static int g_bk = 64;   // k-block of the K-major kernel: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
 
@@ -1022,7 +1323,10 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
   if (M == 0) return B200REC_OK;
   const int BN = g_bn_override > 0 ? g_bn_override : pick_bn(N);
   const int BK = g_bk == 64 ? 64 : 32;
-  const uint32_t stage_bytes = (2u * kBM + 2u * (uint32_t)BN) * (uint32_t)BK * 2u;
+  // CTA pairs pay off when there are enough 256-row tiles to fill the 74 clusters
+  const bool pair = g_two_cta != 0 && M >= 4096 && BN % 16 == 0 && ep.colsum == nullptr;
+  const uint32_t stage_bytes =
+      (2u * kBM + 2u * (uint32_t)(pair ? BN / 2 : BN)) * (uint32_t)BK * 2u;
   const uint32_t staging_bytes = kEpiWarps * kStagingPerWarp;
   int stages = (int)((kSmemBudget - 4096u - 16u * kMaxBN - staging_bytes) / stage_bytes);
   stages = stages > 8 ? 8 : stages;
@@ -1035,8 +1339,9 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
   int rc;
   if ((rc = make_map(&ma_hi, a, K, M, 2 * lda, BK, kBM)) != B200REC_OK) return rc;
   if ((rc = make_map(&ma_lo, a + lda, K, M, 2 * lda, BK, kBM)) != B200REC_OK) return rc;
-  if ((rc = make_map(&mb_hi, b, K, N, 2 * ldb, BK, BN)) != B200REC_OK) return rc;
-  if ((rc = make_map(&mb_lo, b + ldb, K, N, 2 * ldb, BK, BN)) != B200REC_OK) return rc;
+  const int b_rows = pair ? BN / 2 : BN;      // each CTA of a pair loads half of the B tile
+  if ((rc = make_map(&mb_hi, b, K, N, 2 * ldb, BK, b_rows)) != B200REC_OK) return rc;
+  if ((rc = make_map(&mb_lo, b + ldb, K, N, 2 * ldb, BK, b_rows)) != B200REC_OK) return rc;
   // outputs through TMA stores where base and pitch allow it (else: direct stores from registers)
   Epilogue e2 = ep;
   CUtensorMap mo_hi = ma_hi, mo_lo = ma_hi, mo_f32 = ma_hi;   // placeholders when unused
@@ -1060,7 +1365,23 @@ static int launch_gemm_kmajor(const void* A, int64_t lda, const void* B, int64_t
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor_kernel<32>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor2_kernel<64>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(tc_gemm_kmajor2_kernel<32>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  if (pair) {
+    const int pair_tiles = (int)((M + 2 * kBM - 1) / (2 * kBM)) * ((N + BN - 1) / BN);
+    const int clusters = pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2;
+    if (BK == 64)
+      tc_gemm_kmajor2_kernel<64><<<2 * clusters, kThreadsK, smem, st>>>(
+          ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mo_f32, (int)M, N, K, BN, stages, e2);
+    else
+      tc_gemm_kmajor2_kernel<32><<<2 * clusters, kThreadsK, smem, st>>>(
+          ma_hi, ma_lo, mb_hi, mb_lo, mo_hi, mo_lo, mo_f32, (int)M, N, K, BN, stages, e2);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
   }
   const int tiles = (int)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();

@@ -337,3 +337,32 @@ def test_tc_head_width1_layer(M, K):
     assert abs(float(db) - float(dy.double().sum())) < 1e-5 * float(dy.abs().sum())
     gp2, dW2, db2 = ops.raw_tc_head_bwd(ap, K, w.to(DEV), dy.to(DEV))
     assert torch.equal(dW, dW2) and torch.equal(db, db2)        # deterministic
+
+
+@pytest.mark.parametrize("M,N,K", [(20000, 400, 624), (4099, 624, 400), (8192, 40, 1560)])
+def test_tc_cta_pair_kernel(M, N, K):
+    """The cta_group::2 variant (two SMs per 256-row tile, B split across the pair, multicast
+    commits, remote barrier arrivals): forward with every output kind, masked dX, odd tile counts."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    a = ops.raw_tc_split(x.to(DEV))
+    Wp, WTp = ops.raw_tc_prep_weight(W.to(DEV))
+    want = (x.double() @ W.double() + b.double()).clamp_min(0)
+    ops.tc_debug(6, 1)
+    try:
+        y, _ = ops.raw_tc_linear_fwd(a, K, WTp, N, b.to(DEV), True, True, False)
+        _, yp = ops.raw_tc_linear_fwd(a, K, WTp, N, b.to(DEV), True, False, True, ones_col=True)
+        gy = torch.randn(M, N, generator=g)
+        gp, _ = ops.raw_tc_split_bwd(gy.to(DEV), None)
+        dx, _, _ = ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, None, True, False, False)
+        _, dxp, _ = ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, a, False, True, False)
+        torch.cuda.synchronize()
+    finally:
+        ops.tc_debug(6, 0)
+    assert _err(y, want) < 5e-5 and _err(_join(yp, N), want) < 5e-5
+    wdx = gy.double() @ W.double().t()
+    assert _err(dx, wdx) < 5e-5
+    assert _err(_join(dxp, K), wdx * (a[:, :K].double().cpu() > 0)) < 5e-5
