@@ -241,7 +241,7 @@ int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_plan
 int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                          const float* bias, const float* x0, const float* xl, int64_t ld_x,
                          float* u_f32, float* out_f32, int64_t ld_f32, void* out_planes,
-                         int64_t ldp, int64_t M, int C, void* stream);
+                         int64_t ldp, int ones_col, int64_t M, int C, void* stream);
 int b200rec_tc_linear_bwd_workspace_bytes(int64_t M, int K, int N, size_t* bytes_host);
 int b200rec_tc_linear_bwd_dx(const void* g_planes, int64_t ldg, const void* w_planes, int64_t ldn,
                              const void* mask_planes, int64_t ld_mask, const float* addend,

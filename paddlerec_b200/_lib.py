@@ -114,7 +114,7 @@ _SIG = {
     "b200rec_tc_linear_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, _P, c_int64, _P, c_int64,
                                       c_int, c_int64, c_int, c_int, _P]),
     "b200rec_tc_cross_fwd": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64,
-                                     _P, c_int64, c_int64, c_int, _P]),
+                                     _P, c_int64, c_int, c_int64, c_int, _P]),
     "b200rec_tc_linear_bwd_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "b200rec_tc_linear_bwd_dx": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P,
                                          c_int64, _P, c_int64, c_int, c_int, _P, c_size_t, _P]),

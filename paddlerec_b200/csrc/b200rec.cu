@@ -317,11 +317,13 @@ int b200rec_tc_linear_fwd(const void* a_planes, int64_t lda, const void* wt_plan
 int b200rec_tc_cross_fwd(const void* xl_planes, int64_t lda, const void* wt_planes, int64_t ldk,
                          const float* bias, const float* x0, const float* xl, int64_t ld_x,
                          float* u_f32, float* out_f32, int64_t ld_f32, void* out_planes,
-                         int64_t ldp, int64_t M, int C, void* stream) {
+                         int64_t ldp, int ones_col, int64_t M, int C, void* stream) {
   if (M > 0) { NOT_NULL(xl_planes); NOT_NULL(wt_planes); NOT_NULL(x0); NOT_NULL(xl); }
   B200_REQUIRE(out_f32 != nullptr || out_planes != nullptr, "tc_cross_fwd: no output");
+  B200_REQUIRE(out_planes == nullptr || ldp >= C + (ones_col ? 1 : 0), "tc_cross_fwd: ldp < C");
   tc::Epilogue ep = {};
   ep.bias = bias;
+  ep.ones_col = ones_col;
   ep.aux_f32 = u_f32; ep.ld_aux = ld_f32;
   ep.cross_x0 = x0; ep.cross_xl = xl; ep.ld_cross = ld_x;
   ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;

@@ -291,19 +291,38 @@ row_adagrad_kernel(float* __restrict__ W, float* __restrict__ g2sum,
   }
 }
 
+// Row geometry for the row-wise optimizers: start from the widest vector D allows and narrow it
+// until the row strides and base addresses fit (column VIEWS of a table — e.g. the embedding part
+// of a [show, click, emb] GPUBox row — start at a 4- or 8-byte offset).
+static bool pick_row_shape_for(int D, int64_t ldw, int64_t ld_rows, const void* const* ptrs, int np,
+                               RowShape* rs) {
+  if (!pick_row_shape(D, rs)) return false;
+  auto fits = [&](int vec) {
+    if (D % vec || ldw % vec || ld_rows % vec) return false;
+    for (int i = 0; i < np; ++i)
+      if (ptrs[i] != nullptr && reinterpret_cast<uintptr_t>(ptrs[i]) % (vec * 4) != 0) return false;
+    return true;
+  };
+  int vec = rs->vec;
+  while (vec > 1 && !fits(vec)) vec >>= 1;
+  const int chunks = D / vec;
+  if (chunks > 32) return false;
+  int tpr = 1;
+  while (tpr < chunks) tpr <<= 1;
+  rs->vec = vec;
+  rs->tpr = tpr;
+  return true;
+}
+
 template <typename Op>
 static int launch_row_update(const char* what, const int64_t* unique_ids, const float* rows,
                              const int32_t* num_unique, int64_t n, int D, int64_t V, int64_t ldw,
                              int64_t ld_rows, Op op, const void* a0, const void* a1,
                              const void* a2, cudaStream_t st) {
   RowShape rs;
-  B200_REQUIRE(pick_row_shape(D, &rs), "%s: unsupported D=%d", what, D);
-  B200_REQUIRE(ldw >= D && ld_rows >= D && ldw % rs.vec == 0 && ld_rows % rs.vec == 0,
-               "%s: bad row strides", what);
-  const int align = rs.vec * 4;
-  auto ok = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) % align) == 0; };
-  B200_REQUIRE(ok(rows) && ok(a0) && ok(a1) && ok(a2), "%s: buffers must be %d-byte aligned", what,
-               align);
+  const void* ptrs[4] = {rows, a0, a1, a2};
+  B200_REQUIRE(ldw >= D && ld_rows >= D, "%s: bad row strides", what);
+  B200_REQUIRE(pick_row_shape_for(D, ldw, ld_rows, ptrs, 4, &rs), "%s: unsupported D=%d", what, D);
   if (n == 0) return B200REC_OK;
   B200_DISPATCH_ROW_SHAPE(rs, {
     constexpr int GPB = kGatherThreads / TPR;
@@ -321,13 +340,10 @@ static int launch_adagrad(float* W, float* g2sum, const int64_t* unique_ids, con
                           int64_t ld_rows, float lr, float g0, float lo, float hi,
                           cudaStream_t st) {
   RowShape rs;
-  B200_REQUIRE(pick_row_shape(D, &rs), "sparse_adagrad: unsupported D=%d", D);
-  B200_REQUIRE(ldw >= D && ld_rows >= D && ldw % rs.vec == 0 && ld_rows % rs.vec == 0,
-               "sparse_adagrad: bad row strides");
-  const int align = rs.vec * 4;
-  B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % align == 0 &&
-                   reinterpret_cast<uintptr_t>(rows) % align == 0,
-               "sparse_adagrad: W/rows must be %d-byte aligned", align);
+  const void* ptrs[2] = {W, rows};
+  B200_REQUIRE(ldw >= D && ld_rows >= D, "sparse_adagrad: bad row strides");
+  B200_REQUIRE(pick_row_shape_for(D, ldw, ld_rows, ptrs, 2, &rs), "sparse_adagrad: unsupported D=%d",
+               D);
   if (n == 0) return B200REC_OK;
   B200_DISPATCH_ROW_SHAPE(rs, {
     constexpr int GPB = kGatherThreads / TPR;

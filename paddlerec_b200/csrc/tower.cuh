@@ -213,23 +213,41 @@ tower_head_fwd_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int K,
   const int64_t nwarps = (int64_t)gridDim.x * (kHeadThreads / 32);
   const float b = bias != nullptr ? __ldg(bias) : 0.f;
   const int chunks = K / 8;
-  for (int64_t m = warp0; m < M; m += nwarps) {
-    const __nv_bfloat16* row = a + m * 2 * lda;
-    float acc = 0.f;
+  constexpr int R = 4;      // rows in flight per warp: one row alone leaves the LSU idle
+  for (int64_t m0 = warp0 * R; m0 < M; m0 += nwarps * R) {
+    float acc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) acc[i] = 0.f;
     for (int c = lane; c < chunks; c += 32) {
-      const uint4 qh = __ldg(reinterpret_cast<const uint4*>(row) + c);
-      const uint4 ql = __ldg(reinterpret_cast<const uint4*>(row + lda) + c);
-      float h[8], l[8];
-      bf16x8_to_float(qh, h);
-      bf16x8_to_float(ql, l);
+      uint4 qh[R], ql[R];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc = fmaf(h[j] + l[j], s_w[c * 8 + j], acc);
+      for (int i = 0; i < R; ++i) {
+        const int64_t m = m0 + i < M ? m0 + i : M - 1;
+        const __nv_bfloat16* row = a + m * 2 * lda;
+        qh[i] = __ldg(reinterpret_cast<const uint4*>(row) + c);
+        ql[i] = __ldg(reinterpret_cast<const uint4*>(row + lda) + c);
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        float h[8], l[8];
+        bf16x8_to_float(qh[i], h);
+        bf16x8_to_float(ql[i], l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i] = fmaf(h[j] + l[j], s_w[c * 8 + j], acc[i]);
+      }
     }
-    for (int k = chunks * 8 + lane; k < K; k += 32)
-      acc = fmaf(__bfloat162float(row[k]) + __bfloat162float(row[lda + k]), s_w[k], acc);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[m] = acc + b;
+    for (int i = 0; i < R; ++i) {
+      const int64_t m = m0 + i;
+      if (m < M) {
+        const __nv_bfloat16* row = a + m * 2 * lda;
+        for (int k = chunks * 8 + lane; k < K; k += 32)
+          acc[i] = fmaf(__bfloat162float(row[k]) + __bfloat162float(row[lda + k]), s_w[k], acc[i]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      if (lane == 0 && m < M) y[m] = acc[i] + b;
+    }
   }
 }
 
@@ -259,12 +277,21 @@ tower_head_bwd_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int K,
     __nv_bfloat16* grow = g + m * 2 * ldg;
     const float d = __ldg(dy + m);
     dsum += d;
+    uint4 qhs[NITER], qls[NITER];        // every load of the row in flight before the first use
 #pragma unroll
     for (int i = 0; i < NITER; ++i) {
       const int c = lane + 32 * i;
       if (c < chunks) {
-        const uint4 qh = __ldg(reinterpret_cast<const uint4*>(row) + c);
-        const uint4 ql = __ldg(reinterpret_cast<const uint4*>(row + lda) + c);
+        qhs[i] = __ldg(reinterpret_cast<const uint4*>(row) + c);
+        qls[i] = __ldg(reinterpret_cast<const uint4*>(row + lda) + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+      const int c = lane + 32 * i;
+      if (c < chunks) {
+        const uint4 qh = qhs[i];
+        const uint4 ql = qls[i];
         float h[8], l[8];
         bf16x8_to_float(qh, h);
         bf16x8_to_float(ql, l);

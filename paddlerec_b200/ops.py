@@ -526,7 +526,7 @@ def raw_tc_cross_fwd(xl_planes, WTp, bias, x0, xl, want_planes: bool, want_u: bo
     check(lib.b200rec_tc_cross_fwd(ptr(xl_planes), xl_planes.shape[1] // 2, ptr(WTp),
                                    WTp.shape[1] // 2, ptr(bias), ptr(x0), ptr(xl), C, ptr(u),
                                    ptr(out), C, ptr(op), op.shape[1] // 2 if op is not None else 0,
-                                   M, C, _stream()), "tc_cross_fwd")
+                                   int(ones_col and want_planes), M, C, _stream()), "tc_cross_fwd")
     _count("tc_cross_fwd")
     return out, op, u
 
