@@ -1311,7 +1311,7 @@ static int pick_bn(int N) {
 
 static DwDebug g_dw_debug = {0u, 0u, 0u};
 static int g_bn_override = 0;
-static int g_two_cta = 0;     // K-major GEMM on CTA pairs (cta_group::2): 0 off, 1 on when M >= 4096
+static int g_two_cta = 1;     // K-major GEMM on CTA pairs (cta_group::2) when M >= 4096 (0: never)
 static int g_tma_store = 1;   // epilogue outputs through TMA bulk stores (0: direct stores)
 static int g_bk = 64;   // k-block of the K-major kernel: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
 

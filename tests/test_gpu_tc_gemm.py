@@ -153,11 +153,13 @@ def test_tc_linear_bwd_dw(M, K, N):
     assert torch.equal(dW, dW2)
 
 
-def test_tc_many_tiles_per_cta():
+@pytest.mark.parametrize("pair", [0, 1])
+def test_tc_many_tiles_per_cta(pair):
     """More output tiles than SMs: every CTA walks several tiles, alternating the two TMEM
     accumulator stages while the epilogue of the previous tile is still draining; rows 39936..
     exercise the partially valid last row block."""
     ops = _ops()
+    ops.tc_debug(6, pair)
     g_ = torch.Generator().manual_seed(77)
     M, K, N = 40003, 400, 64
     x = torch.randn(M, N, generator=g_)
@@ -183,6 +185,7 @@ def test_tc_many_tiles_per_cta():
     torch.cuda.synchronize()
     wantdx = (wantg @ W2.double().t()) * (act.double() > 0)
     assert _err(dx, wantdx) < 5e-5 and _err(_join(dxp, N), wantdx) < 5e-5
+    ops.tc_debug(6, 1)
     # element-wise on the tail rows (a max-norm bound would hide one bad row)
     assert _err(dx[-80:], wantdx[-80:]) < 5e-5
 
@@ -361,7 +364,7 @@ def test_tc_cta_pair_kernel(M, N, K):
         _, dxp, _ = ops.raw_tc_linear_bwd_dx(gp, N, Wp, K, a, False, True, False)
         torch.cuda.synchronize()
     finally:
-        ops.tc_debug(6, 0)
+        ops.tc_debug(6, 1)
     assert _err(y, want) < 5e-5 and _err(_join(yp, N), want) < 5e-5
     wdx = gy.double() @ W.double().t()
     assert _err(dx, wdx) < 5e-5

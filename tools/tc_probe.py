@@ -110,7 +110,7 @@ def stage(name, arg):
                     res["dx f32 " + tag] = [round(t, 4), round(fl / t / 1e9, 1)]
                 ops.tc_debug(4, 64)
                 ops.tc_debug(5, 1)
-                ops.tc_debug(6, 0)
+                ops.tc_debug(6, 1)
                 t = _time(lambda: ops.raw_tc_linear_bwd_dw(a, K, gp, N))
                 res["dw  %dx%d bn%d" % (K, N, bn)] = [round(t, 4), round(fl / t / 1e9, 1)]
             ops.tc_debug(0, 0)
