@@ -183,6 +183,25 @@ int b200rec_din_attn_fwd(const float* hist, const float* tseq, const float* tb, 
                          const float* b3, const int64_t* mask, float* scores, float* weights,
                          float* out, int64_t B, int L, int E, float scale, void* stream);
 
+/* ---- sharded table: the exchange over NVLink peer memory -------------------- */
+/* PSGPU pull_sparse / push_sparse (tools/static_gpubox_trainer.py:152-159,244-259) without a
+ * collective-library call on the data path: every GPU maps its peers' receive buffers (symmetric
+ * memory; `peer_ptrs_host[r]` = base of rank r's buffer in THIS process's address space) and the
+ * kernels store straight into them over NVLink.  seg_dev [world+1] / dst_dev [world] are DEVICE
+ * int64 tables (outputs of the count exchange): rows [seg[r], seg[r+1]) of the local list go to
+ * peer r, starting at row dst[r] of its buffer (row pitch ld_dst floats).
+ *   shard_gather_push  owner side of the pull: gather of the requested rows of `shard` (ids are
+ *                      LOCAL rows; local_pad / out-of-range -> zeros) fused with their transfer
+ *   shard_push_rows    requester side of the push: per-slot gradient rows (bucket order) -> owners
+ * The caller publishes the stores with a barrier over the same symmetric memory. */
+int b200rec_shard_gather_push(const float* shard, int64_t ldw, int D, int64_t V_loc,
+                              int64_t local_pad, const int64_t* recv_ids, const int64_t* seg_dev,
+                              const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
+                              int world, int64_t n, void* stream);
+int b200rec_shard_push_rows(const float* rows, int64_t ld, int D, const int64_t* seg_dev,
+                            const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
+                            int world, int64_t n, void* stream);
+
 /* ---- tower epilogues (bf16 hi/lo split operands for the tensor-core GEMMs) -- */
 /* The MLP tower (DNN.forward, models/rank/deepfm/net.py:169-174) runs its GEMMs on the bf16 tensor
  * cores as a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32 accumulate).  These fuse everything

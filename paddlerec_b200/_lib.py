@@ -107,6 +107,10 @@ _SIG = {
     "b200rec_tower_relu_bwd_split": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "b200rec_tower_prep_weight": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "b200rec_tower_fold_dw": (c_int, [_P, _P, c_int, c_int, _P]),
+    "b200rec_shard_gather_push": (c_int, [_P, c_int64, c_int, c_int64, c_int64, _P, _P, _P,
+                                          POINTER(c_uint64), c_int64, c_int, c_int64, _P]),
+    "b200rec_shard_push_rows": (c_int, [_P, c_int64, c_int, _P, _P, POINTER(c_uint64), c_int64,
+                                        c_int, c_int64, _P]),
     "b200rec_tc_split": (c_int, [_P, c_int64, _P, c_int, _P, c_int64, c_int64, c_int, c_int, _P]),
     "b200rec_tc_split_bwd": (c_int, [_P, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _P, c_size_t,
                                      _P]),

@@ -248,6 +248,25 @@ int b200rec_shard_bucketize(const int64_t* ids, int64_t n, int world, int64_t V,
                                 workspace_bytes, ST(stream));
 }
 
+int b200rec_shard_gather_push(const float* shard, int64_t ldw, int D, int64_t V_loc,
+                              int64_t local_pad, const int64_t* recv_ids, const int64_t* seg_dev,
+                              const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
+                              int world, int64_t n, void* stream) {
+  NOT_NULL(peer_ptrs_host);
+  if (n > 0) { NOT_NULL(shard); NOT_NULL(recv_ids); NOT_NULL(seg_dev); NOT_NULL(dst_dev); }
+  return launch_shard_gather_push(shard, ldw, D, V_loc, local_pad, recv_ids, seg_dev, dst_dev,
+                                  peer_ptrs_host, ld_dst, world, n, ST(stream));
+}
+
+int b200rec_shard_push_rows(const float* rows, int64_t ld, int D, const int64_t* seg_dev,
+                            const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
+                            int world, int64_t n, void* stream) {
+  NOT_NULL(peer_ptrs_host);
+  if (n > 0) { NOT_NULL(rows); NOT_NULL(seg_dev); NOT_NULL(dst_dev); }
+  return launch_shard_push_rows(rows, ld, D, seg_dev, dst_dev, peer_ptrs_host, ld_dst, world, n,
+                                ST(stream));
+}
+
 int b200rec_tower_split(const float* x, const float* bias, int relu, void* out_bf16, int64_t M,
                         int K, void* stream) {
   if (M > 0) { NOT_NULL(x); NOT_NULL(out_bf16); }

@@ -99,4 +99,162 @@ static int launch_shard_bucketize(const int64_t* ids, int64_t n, int world, int6
   return B200REC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The exchange itself over NVLink PEER MEMORY (no NCCL call on the data path): every GPU maps the
+// receive buffers of its peers (symmetric memory) and the kernels below store straight into them.
+//
+//   gather_push : owner side of the pull.  The random gather of the rows that peer r asked for and
+//                 their transfer are ONE kernel: each row is read from the local shard once and
+//                 written once — into r's receive buffer, at the position r's fused K1 expects
+//                 (bucket order).  The transfer of a tile overlaps the gather of the next.
+//   push_rows   : requester side of the push.  The per-slot gradient rows (bucket order) go into
+//                 the owners' receive buffers, aligned with the ids each owner received.
+// Segment tables (who asked for what, where it goes) live on the device: they are the outputs of
+// the count exchange, so the data path needs no host round trip.  A device-side barrier over the
+// same symmetric memory (host: torch's _SymmetricMemory.barrier) publishes the rows.
+// Reference behaviour: pull_sparse / push_sparse of tools/static_gpubox_trainer.py:244-259.
+constexpr int kPushThreads = 256;
+constexpr int kPushRowsPerGroup = 4;
+constexpr int kMaxPeers = 16;
+
+struct PeerTable {
+  float* base[kMaxPeers];     // receive buffer of every rank, mapped in this process
+};
+
+// segment tables on the device: seg_dev [world+1] = rows [seg[r], seg[r+1]) of the local list belong
+// to peer r; dst_dev [world] = first row inside peer r's buffer (int64)
+__device__ __forceinline__ int peer_of(const int64_t* seg, int world, int64_t i) {
+  int r = 0;
+#pragma unroll 1
+  for (int k = 1; k < world; ++k) r += (i >= seg[k]) ? 1 : 0;
+  return r;
+}
+
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kPushThreads)
+shard_gather_push_kernel(const float* __restrict__ W, const int64_t* __restrict__ ids,
+                         const int64_t* __restrict__ seg_dev, const int64_t* __restrict__ dst_dev,
+                         PeerTable peers, int world, int64_t n, int D, int64_t V, int64_t pad,
+                         int64_t ldw, int64_t ld_dst) {
+  __shared__ int64_t s_seg[kMaxPeers + 1];
+  __shared__ int64_t s_dst[kMaxPeers];
+  if (threadIdx.x <= world) s_seg[threadIdx.x] = seg_dev[threadIdx.x];
+  if (threadIdx.x < world) s_dst[threadIdx.x] = dst_dev[threadIdx.x];
+  __syncthreads();
+  constexpr int GPB = kPushThreads / TPR;
+  const int g = threadIdx.x / TPR;
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  const int64_t m = s_seg[world] < n ? s_seg[world] : n;
+  const int64_t base = ((int64_t)blockIdx.x * GPB + g) * kPushRowsPerGroup;
+  Vec<VEC> e[kPushRowsPerGroup];
+#pragma unroll
+  for (int j = 0; j < kPushRowsPerGroup; ++j) {
+    e[j] = vzero<VEC>();
+    const int64_t i = base + j;
+    if (i < m) {
+      const int64_t id = __ldg(ids + i);
+      const bool in_range = (uint64_t)id < (uint64_t)V;
+      if (in_range && id != pad && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * ldw + r * VEC);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPushRowsPerGroup; ++j) {
+    const int64_t i = base + j;
+    if (i < m && lane_ok) {
+      const int p = peer_of(s_seg, world, i);
+      float* out = peers.base[p] + (size_t)(s_dst[p] + (i - s_seg[p])) * ld_dst + r * VEC;
+      st_plain<VEC>(out, e[j]);      // NVLink store (or a local store for p == this rank)
+    }
+  }
+}
+
+template <int VEC, int TPR>
+__global__ void __launch_bounds__(kPushThreads)
+shard_push_rows_kernel(const float* __restrict__ rows, int64_t ld,
+                       const int64_t* __restrict__ seg_dev, const int64_t* __restrict__ dst_dev,
+                       PeerTable peers, int world, int64_t n, int D, int64_t ld_dst) {
+  __shared__ int64_t s_seg[kMaxPeers + 1];
+  __shared__ int64_t s_dst[kMaxPeers];
+  if (threadIdx.x <= world) s_seg[threadIdx.x] = seg_dev[threadIdx.x];
+  if (threadIdx.x < world) s_dst[threadIdx.x] = dst_dev[threadIdx.x];
+  __syncthreads();
+  constexpr int GPB = kPushThreads / TPR;
+  const int g = threadIdx.x / TPR;
+  const int r = threadIdx.x % TPR;
+  const bool lane_ok = r * VEC < D;
+  const int64_t m = s_seg[world] < n ? s_seg[world] : n;
+  const int64_t base = ((int64_t)blockIdx.x * GPB + g) * kPushRowsPerGroup;
+  Vec<VEC> e[kPushRowsPerGroup];
+#pragma unroll
+  for (int j = 0; j < kPushRowsPerGroup; ++j) {
+    e[j] = vzero<VEC>();
+    const int64_t i = base + j;
+    if (i < m && lane_ok) e[j] = ld_row<VEC>(rows + (size_t)i * ld + r * VEC);
+  }
+#pragma unroll
+  for (int j = 0; j < kPushRowsPerGroup; ++j) {
+    const int64_t i = base + j;
+    if (i < m && lane_ok) {
+      const int p = peer_of(s_seg, world, i);
+      float* out = peers.base[p] + (size_t)(s_dst[p] + (i - s_seg[p])) * ld_dst + r * VEC;
+      st_plain<VEC>(out, e[j]);
+    }
+  }
+}
+
+static int fill_peer_table(PeerTable* t, const uint64_t* peer_ptrs_host, int world) {
+  B200_REQUIRE(world >= 1 && world <= kMaxPeers, "shard push: world=%d (max %d)", world, kMaxPeers);
+  for (int r = 0; r < kMaxPeers; ++r)
+    t->base[r] = r < world ? reinterpret_cast<float*>((uintptr_t)peer_ptrs_host[r]) : nullptr;
+  return B200REC_OK;
+}
+
+static int launch_shard_gather_push(const float* W, int64_t ldw, int D, int64_t V, int64_t pad,
+                                    const int64_t* ids, const int64_t* seg_dev,
+                                    const int64_t* dst_dev, const uint64_t* peer_ptrs_host,
+                                    int64_t ld_dst, int world, int64_t n, cudaStream_t st) {
+  PeerTable t;
+  int rc = fill_peer_table(&t, peer_ptrs_host, world);
+  if (rc != B200REC_OK) return rc;
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "shard_gather_push: unsupported D=%d", D);
+  B200_REQUIRE(ldw >= D && ld_dst >= D && ldw % rs.vec == 0 && ld_dst % rs.vec == 0,
+               "shard_gather_push: bad row strides");
+  B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % (rs.vec * 4) == 0,
+               "shard_gather_push: shard must be %d-byte aligned", rs.vec * 4);
+  if (n == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int rows_per_block = (kPushThreads / TPR) * kPushRowsPerGroup;
+    const int64_t grid = (n + rows_per_block - 1) / rows_per_block;
+    shard_gather_push_kernel<VEC, TPR><<<(unsigned)grid, kPushThreads, 0, st>>>(
+        W, ids, seg_dev, dst_dev, t, world, n, D, V, pad, ldw, ld_dst);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static int launch_shard_push_rows(const float* rows, int64_t ld, int D, const int64_t* seg_dev,
+                                  const int64_t* dst_dev, const uint64_t* peer_ptrs_host,
+                                  int64_t ld_dst, int world, int64_t n, cudaStream_t st) {
+  PeerTable t;
+  int rc = fill_peer_table(&t, peer_ptrs_host, world);
+  if (rc != B200REC_OK) return rc;
+  RowShape rs;
+  B200_REQUIRE(pick_row_shape(D, &rs), "shard_push_rows: unsupported D=%d", D);
+  B200_REQUIRE(ld >= D && ld_dst >= D && ld % rs.vec == 0 && ld_dst % rs.vec == 0,
+               "shard_push_rows: bad row strides");
+  B200_REQUIRE(reinterpret_cast<uintptr_t>(rows) % (rs.vec * 4) == 0,
+               "shard_push_rows: rows must be %d-byte aligned", rs.vec * 4);
+  if (n == 0) return B200REC_OK;
+  B200_DISPATCH_ROW_SHAPE(rs, {
+    constexpr int rows_per_block = (kPushThreads / TPR) * kPushRowsPerGroup;
+    const int64_t grid = (n + rows_per_block - 1) / rows_per_block;
+    shard_push_rows_kernel<VEC, TPR><<<(unsigned)grid, kPushThreads, 0, st>>>(
+        rows, ld, seg_dev, dst_dev, t, world, n, D, ld_dst);
+  });
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
 }  // namespace b200rec

@@ -41,7 +41,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 LAUNCHES = 0
 KERNELS_PER_CALL = {
     "embed_fm_fwd": 1, "group_ids": 3, "embed_fm_bwd": 5, "gather": 1, "segment_reduce": 3,
-    "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
+    "shard_gather_push": 1, "shard_push_rows": 1, "rows_to_dense": 1, "sparse_sgd": 1, "sparse_adam": 1, "sparse_adagrad": 1, "cross_v2_fwd": 1,
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
     "tower_prep_weight": 1, "tower_fold_dw": 1, "tc_split": 1, "tc_split_bwd": 2,
     "tc_prep_weight": 1, "tc_linear_fwd": 1, "tc_cross_fwd": 1, "tc_linear_bwd_dx": 1,
@@ -436,6 +436,32 @@ def raw_tower_fold_dw(Mx: torch.Tensor, K: int, N: int) -> torch.Tensor:
     check(lib.b200rec_tower_fold_dw(ptr(Mx), ptr(dW), K, N, _stream()), "tower_fold_dw")
     _count("tower_fold_dw")
     return dW
+
+
+# ---- sharded exchange over NVLink peer memory (csrc/shard.cuh) ----------------------------------
+def raw_shard_gather_push(shard: torch.Tensor, recv_ids: torch.Tensor, local_pad: int, D: int,
+                          seg_dev: torch.Tensor, dst_dev: torch.Tensor, peer_ptrs, ld_dst: int,
+                          world: int) -> None:
+    """Owner side of the pull: the rows peer r asked for are gathered from `shard` and stored
+    directly into r's receive buffer (peer_ptrs: ctypes uint64 array of mapped base pointers)."""
+    lib = _lib.load()
+    shard = _req(shard, torch.float32, "shard") if shard.is_contiguous() else shard
+    check(lib.b200rec_shard_gather_push(ptr(shard), shard.stride(0), D, shard.shape[0],
+                                        int(local_pad), ptr(recv_ids), ptr(seg_dev), ptr(dst_dev),
+                                        peer_ptrs, ld_dst, world, recv_ids.numel(), _stream()),
+          "shard_gather_push")
+    _count("shard_gather_push")
+
+
+def raw_shard_push_rows(rows: torch.Tensor, D: int, seg_dev: torch.Tensor, dst_dev: torch.Tensor,
+                        peer_ptrs, ld_dst: int, world: int) -> None:
+    """Requester side of the push: gradient rows in bucket order -> the owners' receive buffers."""
+    lib = _lib.load()
+    rows = _req(rows, torch.float32, "rows")
+    check(lib.b200rec_shard_push_rows(ptr(rows), rows.stride(0), D, ptr(seg_dev), ptr(dst_dev),
+                                      peer_ptrs, ld_dst, world, rows.shape[0], _stream()),
+          "shard_push_rows")
+    _count("shard_push_rows")
 
 
 # ---- tcgen05 tower GEMMs (csrc/tc_gemm.cuh) ---------------------------------------------------
@@ -1215,6 +1241,7 @@ def _wrap_timed(fn, name):
 
 for _n in ("group_ids", "embed_fm_bwd", "gather", "gather_pool_sum", "segment_reduce", "sparse_sgd",
            "sparse_adam", "sparse_adagrad", "cross_v2_fwd", "cross_v2_bwd", "shard_bucketize",
+           "shard_gather_push", "shard_push_rows",
            "tc_split", "tc_split_bwd", "tc_prep_weight", "tc_linear_fwd", "tc_cross_fwd",
            "tc_linear_bwd_dx", "tc_linear_bwd_dw", "tc_head_fwd", "tc_head_bwd", "din_attn_fwd", "din_attn_bwd", "tower_split",
            "tower_relu_bwd_split", "tower_prep_weight", "tower_fold_dw"):

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -53,6 +54,7 @@ class ExchangePlan:
     recv_splits: List[int]    # ids received from each rank
     recv_ids: torch.Tensor    # int64 [m]: local rows requested from this rank (owner view)
     owner_groups: object = None   # grouping of recv_ids by local row, if it was precomputed
+    tables: object = None         # device segment tables of the peer-memory exchange (or None)
 
 
 class _PendingPlan:
@@ -61,6 +63,37 @@ class _PendingPlan:
     def __init__(self, ids, send_ids, perm, inv_perm, host_counts, event):
         self.ids, self.send_ids, self.perm, self.inv_perm = ids, send_ids, perm, inv_perm
         self.host_counts, self.event = host_counts, event
+
+
+class PeerBuffers:
+    """Receive buffers mapped by every rank (torch symmetric memory over NVLink): rows [cap, cols]
+    for the pull, gradient rows [2*cap, cols] for the push, plus the device-side barrier that
+    publishes the peers' stores.  With these the row / gradient exchange is done by OUR kernels
+    (b200rec_shard_gather_push / _push_rows) storing into peer memory — no NCCL call on the data
+    path, the owner-side gather and its transfer are one kernel."""
+
+    def __init__(self, cap: int, cols: int, world: int, group, device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+        self.cap, self.cap_g, self.cols, self.world = cap, 2 * cap, cols, world
+        self.buf = symm_mem.empty(self.cap + self.cap_g, cols, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.rows = self.buf[:cap]
+        self.grads = self.buf[cap:]
+        ptrs = list(self.hdl.buffer_ptrs)
+        self.rows_ptrs = (ctypes.c_uint64 * world)(*ptrs)
+        self.grads_ptrs = (ctypes.c_uint64 * world)(*[p + cap * cols * 4 for p in ptrs])
+
+    def publish_rows(self):
+        self.hdl.barrier(channel=0)
+
+    def publish_grads(self):
+        self.hdl.barrier(channel=1)
+
+
+def p2p_enabled() -> bool:
+    return os.environ.get("B200REC_P2P", "1") != "0"
 
 
 class ShardExchange:
@@ -80,12 +113,32 @@ class ShardExchange:
         # local padding row of the tables behind this exchange (None = unknown): lets the prefetch
         # also run the OWNER-side grouping of the received ids (a CUB sort) off the critical path
         self.owner_pad = owner_pad
+        # peer-memory exchange (set up lazily by enable_p2p on the first pull; None = NCCL path)
+        self.p2p_cols = None
+        self.peer = None
+        self._p2p_failed = False
 
     def _bucketize_and_count(self, ids):
         send_ids, perm, inv_perm, counts = self.k.raw_shard_bucketize(ids, self.world, self.V)
-        recv_counts = torch.empty_like(counts)
-        dist.all_to_all_single(recv_counts, counts, group=self.group)
-        return send_ids, perm, inv_perm, torch.stack([counts, recv_counts])
+        if self.p2p_cols is None:
+            recv_counts = torch.empty_like(counts)
+            dist.all_to_all_single(recv_counts, counts, group=self.group)
+            return send_ids, perm, inv_perm, torch.stack([counts, recv_counts]), None
+        # peer-memory exchange: besides the counts every owner learns WHERE in the requester's row
+        # buffer its rows go (the requester's bucket offset), and every requester where in the
+        # owner's gradient buffer its rows go (the owner's receive offset).  All on the device.
+        zero = torch.zeros(1, dtype=counts.dtype, device=counts.device)
+        send_seg = torch.cat([zero, counts.cumsum(0)])
+        got = torch.empty(self.world, 2, dtype=counts.dtype, device=counts.device)
+        dist.all_to_all_single(got, torch.stack([counts, send_seg[:-1]], 1).contiguous(),
+                               group=self.group)
+        recv_counts, dst_pull = got[:, 0].contiguous(), got[:, 1].contiguous()
+        recv_seg = torch.cat([zero, recv_counts.cumsum(0)])
+        dst_push = torch.empty_like(counts)
+        dist.all_to_all_single(dst_push, recv_seg[:-1].contiguous(), group=self.group)
+        tables = {"send_seg": send_seg, "recv_seg": recv_seg, "dst_pull": dst_pull,
+                  "dst_push": dst_push}
+        return send_ids, perm, inv_perm, torch.stack([counts, recv_counts]), tables
 
     def prefetch(self, ids: torch.Tensor) -> None:
         """Start planning the exchange of a future batch (CUDA only; a no-op on CPU tensors)."""
@@ -96,7 +149,7 @@ class ShardExchange:
         flat = ids.reshape(-1)
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
-            send_ids, perm, inv_perm, both = self._bucketize_and_count(flat)
+            send_ids, perm, inv_perm, both, tables = self._bucketize_and_count(flat)
             host = torch.empty(both.shape, dtype=both.dtype, pin_memory=True)
             host.copy_(both, non_blocking=True)
             ev = torch.cuda.Event()
@@ -104,6 +157,7 @@ class ShardExchange:
         for t in (flat, send_ids, perm, inv_perm, both):
             t.record_stream(self._side)
         self._pending = _PendingPlan(ids, send_ids, perm, inv_perm, host, ev)
+        self._pending.tables = tables
 
     def finish_prefetch(self) -> None:
         """Second half of the prefetch (call it later in the step, e.g. after backward was
@@ -149,23 +203,67 @@ class ShardExchange:
                 if groups is not None:
                     for t in (groups.unique_ids, groups.seg_offsets, groups.sorted_pos, groups.num):
                         t.record_stream(cur)
+                tables = getattr(pend, "tables", None)
+                if tables is not None:
+                    for t in tables.values():
+                        t.record_stream(cur)
                 return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, pend.recv_ids,
-                                    groups)
+                                    groups, tables)
             pend.event.synchronize()                              # normally long complete
             torch.cuda.current_stream().wait_event(pend.event)
             send_splits, recv_splits = pend.host_counts[0].tolist(), pend.host_counts[1].tolist()
+            tables = getattr(pend, "tables", None)
         else:
-            send_ids, perm, inv_perm, both = self._bucketize_and_count(flat)
+            send_ids, perm, inv_perm, both, tables = self._bucketize_and_count(flat)
             both = both.cpu()                                     # host sync (no prefetch)
             send_splits, recv_splits = both[0].tolist(), both[1].tolist()
         recv_ids = torch.empty(sum(recv_splits), dtype=torch.int64, device=ids.device)
         dist.all_to_all_single(recv_ids, send_ids, recv_splits, send_splits, group=self.group)
-        return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, recv_ids)
+        return ExchangePlan(n, perm, inv_perm, send_splits, recv_splits, recv_ids, None, tables)
+
+    def enable_p2p(self, cols: int) -> None:
+        """Ask for the peer-memory exchange of `cols`-wide rows (takes effect from the next
+        bucketing on; the buffers are created collectively at the first pull)."""
+        if p2p_enabled() and self.world > 1 and torch.cuda.is_available():
+            self.p2p_cols = int(cols)
+
+    def _use_p2p(self, plan: ExchangePlan, cols: int, shard: torch.Tensor) -> bool:
+        if self.p2p_cols is None or plan.tables is None or cols != self.p2p_cols or self._p2p_failed:
+            return False
+        if not shard.is_cuda:
+            return False
+        if self.peer is None or plan.n > self.peer.cap:
+            # collective: every rank sees the same plan.n (B per GPU is fixed) and gets here together
+            cap = max(1024, int(plan.n * 1.25))
+            try:
+                self.peer = PeerBuffers(cap, cols, self.world, self.group, shard.device)
+            except Exception as exc:   # no symmetric memory in this environment: NCCL path
+                import warnings
+                warnings.warn("peer-memory exchange unavailable (%r): using NCCL all-to-all" % (exc,))
+                self._p2p_failed, self.peer = True, None
+                return False
+        if plan.recv_ids.numel() > self.peer.cap_g:
+            # a rank-local fall-back would desynchronise the collectives: fail loudly instead
+            raise RuntimeError(
+                "peer-memory exchange: %d rows requested from this rank exceed the receive capacity "
+                "%d (ids are too skewed for owner = id mod world); set B200REC_P2P=0"
+                % (plan.recv_ids.numel(), self.peer.cap_g))
+        return True
 
     def pull(self, plan: ExchangePlan, shard: torch.Tensor, local_pad: int,
              D: Optional[int] = None) -> torch.Tensor:
         """Owner-side gather of the first D columns (default: all) + rows back to the requesters:
         returns [n, D] in bucket order."""
+        cols = D if D is not None else shard.shape[1]
+        if self._use_p2p(plan, cols, shard):
+            # ONE kernel gathers the requested rows and stores them into the requesters' buffers
+            # over NVLink; the barrier publishes every rank's stores.
+            self.k.raw_shard_gather_push(shard, plan.recv_ids, local_pad, cols,
+                                         plan.tables["recv_seg"], plan.tables["dst_pull"],
+                                         self.peer.rows_ptrs, self.peer.cols, self.world)
+            with _timed("p2p_barrier"):
+                self.peer.publish_rows()
+            return self.peer.rows[:plan.n]
         rows_out = self.k.raw_gather(shard, plan.recv_ids, local_pad, D)
         rows_in = torch.empty(plan.n, rows_out.shape[-1], dtype=shard.dtype, device=shard.device)
         with _timed("nccl_a2a_rows"):
@@ -177,6 +275,14 @@ class ShardExchange:
         """Per-slot gradients [n, D] (bucket order) -> owners: returns [m, D] aligned with
         plan.recv_ids."""
         D = grads_bucket_order.shape[1]
+        if (self.peer is not None and plan.tables is not None and D == self.peer.cols and
+                grads_bucket_order.is_cuda):
+            self.k.raw_shard_push_rows(grads_bucket_order, D, plan.tables["send_seg"],
+                                       plan.tables["dst_push"], self.peer.grads_ptrs,
+                                       self.peer.cols, self.world)
+            with _timed("p2p_barrier"):
+                self.peer.publish_grads()
+            return self.peer.grads[:plan.recv_ids.numel()]
         out = torch.empty(plan.recv_ids.numel(), D, dtype=grads_bucket_order.dtype,
                           device=grads_bucket_order.device)
         with _timed("nccl_a2a_grads"):
@@ -356,6 +462,8 @@ class ShardedFM(bnn.FusedTableOwner):
         tnn.init.trunc_normal_(self.dense_w, 0.0, std, -2 * std, 2 * std)
         self.exchange = ShardExchange(sparse_feature_number, rank, world, group, kernels,
                                       owner_pad=(0 if rank == 0 else -1))   # padding id 0 lives on rank 0
+        if self.fused and kernels is _cuda_ops:
+            self.exchange.enable_p2p(self._fused.grad_cols)
         self._trivial = {}
 
     def table_grad_dense(self):
