@@ -58,6 +58,8 @@ def parse():
     p.add_argument("--cpu-batch", type=int, default=65536)
     p.add_argument("--cpu-steps", type=int, default=4)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--timeline", default="", help="write a CUPTI timeline of 3 steps (rank 0) "
+                   "as <path>.json (chrome trace) and <path>.txt (per-stream summary) and exit")
     return p.parse_args()
 
 
@@ -319,6 +321,9 @@ def run_b200(args, rank, world, local_rank):
         return ms, launches, events, clocks
 
     K, W = args.steps, max(args.warmup, 3)
+    if args.timeline:
+        timeline(args.timeline, step_resident, barrier, rank, W)
+        return
     parity = parity_bit(args, model, dm, resident, label_f, rank, world, dev) if world > 1 else None
     ms, launches, events, clocks = timed(step_resident, K, W, collect_events=True,
                                          event_filter={"embed_fm_fwd"})
@@ -372,6 +377,63 @@ def run_b200(args, rank, world, local_rank):
         except Exception as exc:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
+
+
+def timeline(path, step, barrier, rank, warmup):
+    """CUPTI (torch.profiler) timeline of 3 resident steps: where the GPU idles and what runs on
+    which stream.  nsys is not installed; this is the same data (kernel start/end per stream)."""
+    from torch.profiler import ProfilerActivity, profile
+    for i in range(warmup):
+        step(i)
+    barrier()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for i in range(3):
+            step(warmup + i)
+        barrier()
+    if rank != 0:
+        return
+    prof.export_chrome_trace(path + ".json")
+    ev = [e for e in json.load(open(path + ".json"))["traceEvents"]
+          if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    ev.sort(key=lambda e: e["ts"])
+    t0, t1 = ev[0]["ts"], max(e["ts"] + e["dur"] for e in ev)
+    streams = {}
+    for e in ev:
+        streams.setdefault(e["args"].get("stream", e.get("tid")), []).append(e)
+    lines = ["3 steps: %.1f us wall on the GPU (%.1f us / step)" % (t1 - t0, (t1 - t0) / 3)]
+    main = max(streams, key=lambda k: sum(x["dur"] for x in streams[k]))
+    for k, v in sorted(streams.items(), key=lambda kv: -sum(x["dur"] for x in kv[1])):
+        lines.append("stream %s: %d launches, busy %.1f us%s" % (
+            k, len(v), sum(x["dur"] for x in v), "  <- main" if k == main else ""))
+    # union of busy intervals over all streams -> idle time
+    busy, cur_s, cur_e = 0.0, None, None
+    for e in ev:
+        s0, e0 = e["ts"], e["ts"] + e["dur"]
+        if cur_e is None or s0 > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s0, e0
+        else:
+            cur_e = max(cur_e, e0)
+    busy += cur_e - cur_s
+    lines.append("GPU busy (any stream) %.1f us = %.1f %%; idle %.1f us" % (
+        busy, 100 * busy / (t1 - t0), (t1 - t0) - busy))
+    lines.append("")
+    lines.append("main stream, in order (start offset us, duration us, gap before us, name):")
+    prev = None
+    for e in streams[main]:
+        gap = e["ts"] - prev if prev is not None else 0.0
+        lines.append("%10.1f %9.1f %8.1f  %s" % (e["ts"] - t0, e["dur"], gap, e["name"][:90]))
+        prev = e["ts"] + e["dur"]
+    for k, v in streams.items():
+        if k == main:
+            continue
+        lines.append("")
+        lines.append("stream %s:" % k)
+        for e in v:
+            lines.append("%10.1f %9.1f           %s" % (e["ts"] - t0, e["dur"], e["name"][:90]))
+    open(path + ".txt", "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:12]), flush=True)
 
 
 def roofline_step(args, per_ms, step_ms, step_ms_with_events, world):

@@ -130,7 +130,12 @@ __device__ __forceinline__ int peer_of(const int64_t* seg, int world, int64_t i)
   return r;
 }
 
-template <int VEC, int TPR>
+// Thread mapping: CHUNK-linear.  A row is D/VEC chunks of VEC floats; thread t of a pass handles
+// chunk (pass base + t), so consecutive lanes write consecutive 16-byte pieces of the destination
+// (rows of one peer are contiguous there: a warp store is one 512-byte run over NVLink) while the
+// D/VEC lanes that share a row read its bytes from the shard together.  kPushRowsPerGroup passes are
+// in flight per thread.
+template <int VEC>
 __global__ void __launch_bounds__(kPushThreads)
 shard_gather_push_kernel(const float* __restrict__ W, const int64_t* __restrict__ ids,
                          const int64_t* __restrict__ seg_dev, const int64_t* __restrict__ dst_dev,
@@ -141,35 +146,37 @@ shard_gather_push_kernel(const float* __restrict__ W, const int64_t* __restrict_
   if (threadIdx.x <= world) s_seg[threadIdx.x] = seg_dev[threadIdx.x];
   if (threadIdx.x < world) s_dst[threadIdx.x] = dst_dev[threadIdx.x];
   __syncthreads();
-  constexpr int GPB = kPushThreads / TPR;
-  const int g = threadIdx.x / TPR;
-  const int r = threadIdx.x % TPR;
-  const bool lane_ok = r * VEC < D;
-  const int64_t m = s_seg[world] < n ? s_seg[world] : n;
-  const int64_t base = ((int64_t)blockIdx.x * GPB + g) * kPushRowsPerGroup;
+  const int cpr = D / VEC;                                   // chunks per row
+  const int64_t m = s_seg[world] < n ? s_seg[world] : n;     // rows actually requested
+  const int64_t total = m * cpr;
+  const int64_t base = (int64_t)blockIdx.x * kPushThreads * kPushRowsPerGroup + threadIdx.x;
   Vec<VEC> e[kPushRowsPerGroup];
+  int64_t row[kPushRowsPerGroup];
+  int part[kPushRowsPerGroup];
 #pragma unroll
   for (int j = 0; j < kPushRowsPerGroup; ++j) {
     e[j] = vzero<VEC>();
-    const int64_t i = base + j;
-    if (i < m) {
-      const int64_t id = __ldg(ids + i);
+    const int64_t c = base + (int64_t)j * kPushThreads;
+    row[j] = c / cpr;
+    part[j] = (int)(c - row[j] * cpr);
+    if (c < total) {
+      const int64_t id = __ldg(ids + row[j]);
       const bool in_range = (uint64_t)id < (uint64_t)V;
-      if (in_range && id != pad && lane_ok) e[j] = ld_row<VEC>(W + (size_t)id * ldw + r * VEC);
+      if (in_range && id != pad) e[j] = ld_row<VEC>(W + (size_t)id * ldw + part[j] * VEC);
     }
   }
 #pragma unroll
   for (int j = 0; j < kPushRowsPerGroup; ++j) {
-    const int64_t i = base + j;
-    if (i < m && lane_ok) {
-      const int p = peer_of(s_seg, world, i);
-      float* out = peers.base[p] + (size_t)(s_dst[p] + (i - s_seg[p])) * ld_dst + r * VEC;
+    const int64_t c = base + (int64_t)j * kPushThreads;
+    if (c < total) {
+      const int p = peer_of(s_seg, world, row[j]);
+      float* out = peers.base[p] + (size_t)(s_dst[p] + (row[j] - s_seg[p])) * ld_dst + part[j] * VEC;
       st_plain<VEC>(out, e[j]);      // NVLink store (or a local store for p == this rank)
     }
   }
 }
 
-template <int VEC, int TPR>
+template <int VEC>
 __global__ void __launch_bounds__(kPushThreads)
 shard_push_rows_kernel(const float* __restrict__ rows, int64_t ld,
                        const int64_t* __restrict__ seg_dev, const int64_t* __restrict__ dst_dev,
@@ -179,25 +186,27 @@ shard_push_rows_kernel(const float* __restrict__ rows, int64_t ld,
   if (threadIdx.x <= world) s_seg[threadIdx.x] = seg_dev[threadIdx.x];
   if (threadIdx.x < world) s_dst[threadIdx.x] = dst_dev[threadIdx.x];
   __syncthreads();
-  constexpr int GPB = kPushThreads / TPR;
-  const int g = threadIdx.x / TPR;
-  const int r = threadIdx.x % TPR;
-  const bool lane_ok = r * VEC < D;
+  const int cpr = D / VEC;
   const int64_t m = s_seg[world] < n ? s_seg[world] : n;
-  const int64_t base = ((int64_t)blockIdx.x * GPB + g) * kPushRowsPerGroup;
+  const int64_t total = m * cpr;
+  const int64_t base = (int64_t)blockIdx.x * kPushThreads * kPushRowsPerGroup + threadIdx.x;
   Vec<VEC> e[kPushRowsPerGroup];
+  int64_t row[kPushRowsPerGroup];
+  int part[kPushRowsPerGroup];
 #pragma unroll
   for (int j = 0; j < kPushRowsPerGroup; ++j) {
     e[j] = vzero<VEC>();
-    const int64_t i = base + j;
-    if (i < m && lane_ok) e[j] = ld_row<VEC>(rows + (size_t)i * ld + r * VEC);
+    const int64_t c = base + (int64_t)j * kPushThreads;
+    row[j] = c / cpr;
+    part[j] = (int)(c - row[j] * cpr);
+    if (c < total) e[j] = ld_row<VEC>(rows + (size_t)row[j] * ld + part[j] * VEC);
   }
 #pragma unroll
   for (int j = 0; j < kPushRowsPerGroup; ++j) {
-    const int64_t i = base + j;
-    if (i < m && lane_ok) {
-      const int p = peer_of(s_seg, world, i);
-      float* out = peers.base[p] + (size_t)(s_dst[p] + (i - s_seg[p])) * ld_dst + r * VEC;
+    const int64_t c = base + (int64_t)j * kPushThreads;
+    if (c < total) {
+      const int p = peer_of(s_seg, world, row[j]);
+      float* out = peers.base[p] + (size_t)(s_dst[p] + (row[j] - s_seg[p])) * ld_dst + part[j] * VEC;
       st_plain<VEC>(out, e[j]);
     }
   }
@@ -224,12 +233,18 @@ static int launch_shard_gather_push(const float* W, int64_t ldw, int D, int64_t 
   B200_REQUIRE(reinterpret_cast<uintptr_t>(W) % (rs.vec * 4) == 0,
                "shard_gather_push: shard must be %d-byte aligned", rs.vec * 4);
   if (n == 0) return B200REC_OK;
-  B200_DISPATCH_ROW_SHAPE(rs, {
-    constexpr int rows_per_block = (kPushThreads / TPR) * kPushRowsPerGroup;
-    const int64_t grid = (n + rows_per_block - 1) / rows_per_block;
-    shard_gather_push_kernel<VEC, TPR><<<(unsigned)grid, kPushThreads, 0, st>>>(
-        W, ids, seg_dev, dst_dev, t, world, n, D, V, pad, ldw, ld_dst);
-  });
+  const int64_t chunks = n * (D / rs.vec);
+  const int64_t per_block = (int64_t)kPushThreads * kPushRowsPerGroup;
+  const unsigned grid = (unsigned)((chunks + per_block - 1) / per_block);
+  if (rs.vec == 4)
+    shard_gather_push_kernel<4><<<grid, kPushThreads, 0, st>>>(W, ids, seg_dev, dst_dev, t, world, n, D,
+                                                              V, pad, ldw, ld_dst);
+  else if (rs.vec == 2)
+    shard_gather_push_kernel<2><<<grid, kPushThreads, 0, st>>>(W, ids, seg_dev, dst_dev, t, world, n, D,
+                                                              V, pad, ldw, ld_dst);
+  else
+    shard_gather_push_kernel<1><<<grid, kPushThreads, 0, st>>>(W, ids, seg_dev, dst_dev, t, world, n, D,
+                                                              V, pad, ldw, ld_dst);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }
@@ -247,12 +262,18 @@ static int launch_shard_push_rows(const float* rows, int64_t ld, int D, const in
   B200_REQUIRE(reinterpret_cast<uintptr_t>(rows) % (rs.vec * 4) == 0,
                "shard_push_rows: rows must be %d-byte aligned", rs.vec * 4);
   if (n == 0) return B200REC_OK;
-  B200_DISPATCH_ROW_SHAPE(rs, {
-    constexpr int rows_per_block = (kPushThreads / TPR) * kPushRowsPerGroup;
-    const int64_t grid = (n + rows_per_block - 1) / rows_per_block;
-    shard_push_rows_kernel<VEC, TPR><<<(unsigned)grid, kPushThreads, 0, st>>>(
-        rows, ld, seg_dev, dst_dev, t, world, n, D, ld_dst);
-  });
+  const int64_t chunks = n * (D / rs.vec);
+  const int64_t per_block = (int64_t)kPushThreads * kPushRowsPerGroup;
+  const unsigned grid = (unsigned)((chunks + per_block - 1) / per_block);
+  if (rs.vec == 4)
+    shard_push_rows_kernel<4><<<grid, kPushThreads, 0, st>>>(rows, ld, seg_dev, dst_dev, t, world, n, D,
+                                                            ld_dst);
+  else if (rs.vec == 2)
+    shard_push_rows_kernel<2><<<grid, kPushThreads, 0, st>>>(rows, ld, seg_dev, dst_dev, t, world, n, D,
+                                                            ld_dst);
+  else
+    shard_push_rows_kernel<1><<<grid, kPushThreads, 0, st>>>(rows, ld, seg_dev, dst_dev, t, world, n, D,
+                                                            ld_dst);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }
