@@ -218,6 +218,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     bnn.set_matmul_precision(args.precision)
+    from paddlerec_b200 import tower
+    tower.set_overlap_dw(True)      # dW GEMMs on a side stream; the optimizers wait for them
     fc = [int(x) for x in args.fc.split(",")]
     config = {
         "hyper_parameters.sparse_feature_number": args.vocab,

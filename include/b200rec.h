@@ -281,6 +281,22 @@ int b200rec_tc_head_bwd_workspace_bytes(int K, size_t* bytes_host);
 int b200rec_tc_head_bwd(const void* a_planes, int64_t lda, int K, const float* w, const float* dy,
                         void* g_planes, int64_t ldg, float* dW, float* db, int64_t M,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* ---- CTR head (csrc/ctr_head.cuh) ------------------------------------------ */
+/* pred = sigmoid(a + b + c) (b, c may be NULL) and its backward dlogit = dpred * p (1-p)
+ * (deepfm/net.py:47: sigmoid(y_first_order + y_second_order + y_dnn)); the mean of Paddle's
+ * log_loss (eps inside both logs, deepfm/dygraph_model.py:53-58) as one deterministic reduction
+ * and its backward dpred = dloss/n * (-y/(p+eps) + (1-y)/(1-p+eps)).  label: float32 or int64
+ * [n].  The loss workspace must be zero before its first use. */
+int b200rec_sum_sigmoid_fwd(const float* a, const float* b, const float* c, float* pred, int64_t n,
+                            void* stream);
+int b200rec_sum_sigmoid_bwd(const float* pred, const float* dpred, float* dlogit, int64_t n,
+                            void* stream);
+int b200rec_log_loss_workspace_bytes(size_t* bytes_host);
+int b200rec_log_loss_mean_fwd(const float* pred, const void* label, int label_is_i64, double eps,
+                              float* loss, int64_t n, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int b200rec_log_loss_mean_bwd(const float* pred, const void* label, int label_is_i64, double eps,
+                              const float* dloss, float* dpred, int64_t n, void* stream);
 /* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel;
  * 4: k-block of the K-major kernel, 64 = 128-byte swizzle, 32 = 64-byte swizzle, more stages;
  * 5: epilogue outputs through TMA bulk stores (1) or register stores (0); 6: K-major GEMM on CTA

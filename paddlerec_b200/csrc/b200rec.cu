@@ -12,6 +12,7 @@
 #include "shard.cuh"
 #include "tower.cuh"
 #include "tc_gemm.cuh"
+#include "ctr_head.cuh"
 #include "cvm.cuh"
 #include "hash_keys.cuh"
 #include "dot_interact.cuh"
@@ -426,6 +427,75 @@ int b200rec_tc_head_bwd(const void* a_planes, int64_t lda, int K, const float* w
   if (M > 0) { NOT_NULL(a_planes); NOT_NULL(w); NOT_NULL(dy); NOT_NULL(g_planes); NOT_NULL(workspace); }
   return launch_tower_head_bwd(a_planes, lda, K, w, dy, g_planes, ldg, dW, db, M, workspace,
                                workspace_bytes, ST(stream));
+}
+
+/* ---- CTR head: sigmoid of the summed logits, mean log-loss (csrc/ctr_head.cuh) --------------- */
+int b200rec_sum_sigmoid_fwd(const float* a, const float* b, const float* c, float* pred, int64_t n,
+                            void* stream) {
+  B200_REQUIRE(n >= 0, "sum_sigmoid_fwd: bad n");
+  if (n == 0) return B200REC_OK;
+  NOT_NULL(a); NOT_NULL(pred);
+  sum_sigmoid_fwd_kernel<<<(unsigned)((n + kHeadOpThreads - 1) / kHeadOpThreads), kHeadOpThreads, 0,
+                           ST(stream)>>>(a, b, c, pred, n);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_sum_sigmoid_bwd(const float* pred, const float* dpred, float* dlogit, int64_t n,
+                            void* stream) {
+  B200_REQUIRE(n >= 0, "sum_sigmoid_bwd: bad n");
+  if (n == 0) return B200REC_OK;
+  NOT_NULL(pred); NOT_NULL(dpred); NOT_NULL(dlogit);
+  sum_sigmoid_bwd_kernel<<<(unsigned)((n + kHeadOpThreads - 1) / kHeadOpThreads), kHeadOpThreads, 0,
+                           ST(stream)>>>(pred, dpred, dlogit, n);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_log_loss_workspace_bytes(size_t* bytes_host) {
+  NOT_NULL(bytes_host);
+  *bytes_host = log_loss_ws_bytes();
+  return B200REC_OK;
+}
+
+/* label_is_i64: labels are int64 (as the readers deliver them) or float32.  `workspace` must be
+ * ZERO before its first use (the kernel leaves its ticket word zero again). */
+int b200rec_log_loss_mean_fwd(const float* pred, const void* label, int label_is_i64, double eps,
+                              float* loss, int64_t n, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  B200_REQUIRE(n > 0, "log_loss_mean_fwd: n must be positive");
+  NOT_NULL(pred); NOT_NULL(label); NOT_NULL(loss); NOT_NULL(workspace);
+  if (workspace_bytes < log_loss_ws_bytes()) {
+    set_error("log_loss_mean_fwd: workspace %zu < %zu bytes", workspace_bytes, log_loss_ws_bytes());
+    return B200REC_ERR_WORKSPACE;
+  }
+  unsigned int* ticket = static_cast<unsigned int*>(workspace);
+  float* partials = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 16);
+  const int64_t want = (n + kHeadOpThreads - 1) / kHeadOpThreads;
+  const unsigned grid = (unsigned)(want < kLossBlocks ? want : kLossBlocks);
+  if (label_is_i64)
+    log_loss_mean_fwd_kernel<int64_t><<<grid, kHeadOpThreads, 0, ST(stream)>>>(
+        pred, static_cast<const int64_t*>(label), (float)eps, partials, ticket, loss, n);
+  else
+    log_loss_mean_fwd_kernel<float><<<grid, kHeadOpThreads, 0, ST(stream)>>>(
+        pred, static_cast<const float*>(label), (float)eps, partials, ticket, loss, n);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+int b200rec_log_loss_mean_bwd(const float* pred, const void* label, int label_is_i64, double eps,
+                              const float* dloss, float* dpred, int64_t n, void* stream) {
+  B200_REQUIRE(n > 0, "log_loss_mean_bwd: n must be positive");
+  NOT_NULL(pred); NOT_NULL(label); NOT_NULL(dloss); NOT_NULL(dpred);
+  const unsigned grid = (unsigned)((n + kHeadOpThreads - 1) / kHeadOpThreads);
+  if (label_is_i64)
+    log_loss_mean_bwd_kernel<int64_t><<<grid, kHeadOpThreads, 0, ST(stream)>>>(
+        pred, static_cast<const int64_t*>(label), (float)eps, dloss, dpred, n);
+  else
+    log_loss_mean_bwd_kernel<float><<<grid, kHeadOpThreads, 0, ST(stream)>>>(
+        pred, static_cast<const float*>(label), (float)eps, dloss, dpred, n);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
 }
 
 int b200rec_tc_debug(int key, int value) {

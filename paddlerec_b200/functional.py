@@ -11,6 +11,16 @@ def log_loss(pred: torch.Tensor, label: torch.Tensor, epsilon: float = 1e-4) -> 
     return -label * torch.log(pred + epsilon) - (1.0 - label) * torch.log(1.0 - pred + epsilon)
 
 
+def log_loss_mean(pred: torch.Tensor, label: torch.Tensor, epsilon: float = 1e-4) -> torch.Tensor:
+    """paddle.mean(log_loss(pred, label)) — what every CTR DygraphModel.create_loss computes
+    (deepfm/dygraph_model.py:53-58).  On CUDA one fused reduction kernel each way
+    (b200rec_log_loss_mean_fwd/_bwd); elsewhere the composition of the two torch ops."""
+    if pred.is_cuda:
+        from . import ops
+        return ops.log_loss_mean(pred, label, epsilon)
+    return log_loss(pred, label.to(torch.float32), epsilon).mean()
+
+
 class Auc:
     """paddle.metric.Auc("ROC", num_thresholds=4095): bucketed positive/negative histograms and a
     trapezoid sweep.  Unlike the reference (`.numpy()` every step, dygraph_model.py:83-84) the

@@ -45,7 +45,8 @@ KERNELS_PER_CALL = {
     "cross_v2_bwd": 2, "shard_bucketize": 2, "tower_split": 1, "tower_relu_bwd_split": 2,
     "tower_prep_weight": 1, "tower_fold_dw": 1, "tc_split": 1, "tc_split_bwd": 2,
     "tc_prep_weight": 1, "tc_linear_fwd": 1, "tc_cross_fwd": 1, "tc_linear_bwd_dx": 1,
-    "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "tc_head_fwd": 1, "tc_head_bwd": 2, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
+    "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "tc_head_fwd": 1, "tc_head_bwd": 2,
+    "sum_sigmoid_fwd": 1, "sum_sigmoid_bwd": 1, "log_loss_mean_fwd": 1, "log_loss_mean_bwd": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around the raw_* calls
 # (all of them, or only the names in EVENT_FILTER when that is a set) — bench.py's per-kernel times.
@@ -557,12 +558,12 @@ def raw_tc_cross_fwd(xl_planes, WTp, bias, x0, xl, want_planes: bool, want_u: bo
     return out, op, u
 
 
-def _tc_bwd_ws(M: int, K: int, N: int, device) -> torch.Tensor:
+def _tc_bwd_ws(M: int, K: int, N: int, device, tag: str = "tc_bwd") -> torch.Tensor:
     nbytes = ctypes.c_size_t(0)
     lib = _lib.load()
     check(lib.b200rec_tc_linear_bwd_workspace_bytes(M, K, N, ctypes.byref(nbytes)),
           "tc_linear_bwd_ws")
-    return workspace(nbytes.value, device, "tc_bwd")
+    return workspace(nbytes.value, device, tag)
 
 
 def raw_tc_linear_bwd_dx(g_planes, N: int, Wp, K: int, mask_planes, want_f32: bool,
@@ -588,7 +589,8 @@ def raw_tc_linear_bwd_dx(g_planes, N: int, Wp, K: int, mask_planes, want_f32: bo
     return dx, dxp, db
 
 
-def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int, bias_row: bool = False):
+def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int, bias_row: bool = False,
+                         ws_tag: str = "tc_bwd"):
     """dW [K,N] = a^T @ g (batch-split tcgen05 GEMM + fixed-order reduce).  With bias_row the
     operand `a` carries a column of ones at index K (ones_col of raw_tc_split / raw_tc_linear_fwd)
     and the result is (dW [K,N], dbias [N]) — the bias gradient is row K of the same GEMM."""
@@ -598,7 +600,7 @@ def raw_tc_linear_bwd_dw(a_planes, K: int, g_planes, N: int, bias_row: bool = Fa
     if bias_row:
         K = K + 1
     dW = torch.empty(K, N, dtype=torch.float32, device=dev)
-    ws = _tc_bwd_ws(M, K, N, dev)
+    ws = _tc_bwd_ws(M, K, N, dev, ws_tag)
     check(lib.b200rec_tc_linear_bwd_dw(ptr(a_planes), a_planes.shape[1] // 2, ptr(g_planes),
                                        g_planes.shape[1] // 2, ptr(dW), M, K, N, ptr(ws),
                                        ws.numel(), _stream()), "tc_linear_bwd_dw")
@@ -639,6 +641,88 @@ def raw_tc_head_bwd(a_planes, K: int, w, dy):
                                   _stream()), "tc_head_bwd")
     _count("tc_head_bwd")
     return g, dW, db
+
+
+# ---- CTR head: sigmoid of the summed logits, mean log-loss (csrc/ctr_head.cuh) ------------------
+class _SumSigmoid(torch.autograd.Function):
+    """pred = sigmoid(a + b + c): ONE kernel each way (the reference's add, add, sigmoid and their
+    three backward kernels are pure launch latency at [B,1])."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        lib = _lib.load()
+        a, b, c = (None if t is None else _req(t.reshape(-1), torch.float32, "logit part")
+                   for t in (a, b, c))
+        pred = torch.empty_like(a)
+        check(lib.b200rec_sum_sigmoid_fwd(ptr(a), ptr(b), ptr(c), ptr(pred), a.numel(), _stream()),
+              "sum_sigmoid_fwd")
+        _count("sum_sigmoid_fwd")
+        ctx.save_for_backward(pred)
+        return pred.reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dpred):
+        lib = _lib.load()
+        (pred,) = ctx.saved_tensors
+        dpred = _req(dpred.reshape(-1), torch.float32, "dpred")
+        dlogit = torch.empty_like(pred)
+        check(lib.b200rec_sum_sigmoid_bwd(ptr(pred), ptr(dpred), ptr(dlogit), pred.numel(),
+                                          _stream()), "sum_sigmoid_bwd")
+        _count("sum_sigmoid_bwd")
+        g = dlogit.reshape(-1, 1)
+        return tuple(g if need else None for need in ctx.needs_input_grad)
+
+
+def sum_sigmoid(a, b=None, c=None):
+    """sigmoid(a + b + c) for [B,1] logit parts (b, c optional)."""
+    return _SumSigmoid.apply(a, b, c)
+
+
+_loss_ws = {}
+
+
+class _LogLossMean(torch.autograd.Function):
+    """mean(log_loss(pred, label, eps)) as one deterministic reduction kernel + one backward
+    kernel (paddle.nn.functional.log_loss + paddle.mean, deepfm/dygraph_model.py:53-58)."""
+
+    @staticmethod
+    def forward(ctx, pred, label, eps):
+        lib = _lib.load()
+        p = _req(pred.reshape(-1), torch.float32, "pred")
+        if label.dtype not in (torch.float32, torch.int64):
+            label = label.to(torch.float32)
+        y = label.reshape(-1).contiguous()
+        key = p.device.index
+        ws = _loss_ws.get(key)
+        if ws is None:
+            nbytes = ctypes.c_size_t(0)
+            check(lib.b200rec_log_loss_workspace_bytes(ctypes.byref(nbytes)), "log_loss_ws")
+            ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=p.device)   # ticket starts at 0
+            _loss_ws[key] = ws
+        loss = torch.empty((), dtype=torch.float32, device=p.device)
+        check(lib.b200rec_log_loss_mean_fwd(ptr(p), ptr(y), int(y.dtype == torch.int64), float(eps),
+                                            ptr(loss), p.numel(), ptr(ws), ws.numel(), _stream()),
+              "log_loss_mean_fwd")
+        _count("log_loss_mean_fwd")
+        ctx.save_for_backward(p, y)
+        ctx.eps, ctx.shape = float(eps), pred.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = _lib.load()
+        p, y = ctx.saved_tensors
+        dloss = _req(dloss.reshape(1), torch.float32, "dloss")
+        dpred = torch.empty_like(p)
+        check(lib.b200rec_log_loss_mean_bwd(ptr(p), ptr(y), int(y.dtype == torch.int64), ctx.eps,
+                                            ptr(dloss), ptr(dpred), p.numel(), _stream()),
+              "log_loss_mean_bwd")
+        _count("log_loss_mean_bwd")
+        return dpred.reshape(ctx.shape), None, None
+
+
+def log_loss_mean(pred, label, eps: float = 1e-4):
+    return _LogLossMean.apply(pred, label, eps)
 
 
 def tc_debug(key: int, value: int) -> None:

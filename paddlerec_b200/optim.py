@@ -74,7 +74,14 @@ class _Base:
     def get_lr(self) -> float:
         return float(self._lr()) if callable(self._lr) else float(self._lr)
 
+    @staticmethod
+    def _wait_tower() -> None:
+        """Weight gradients of the tower may still be in flight on its side stream."""
+        from . import tower
+        tower.wait_pending()
+
     def clear_grad(self) -> None:
+        self._wait_tower()
         for p in self._dense:
             p.grad = None
         for p in self._sparse:
@@ -87,6 +94,7 @@ class _Base:
         (models/rank/dcn_v2/dygraph_model.py:81-88).  With row-sharded tables each rank holds only
         its shard's SelectedRows, so that part is summed over the ranks (one scalar all-reduce)
         before the sqrt; every replica then applies the same scale."""
+        self._wait_tower()
         dev = (self._dense + self._sparse)[0].device
         dense_sq = torch.zeros((), device=dev)
         for p in self._dense:
@@ -139,6 +147,7 @@ class _Base:
                 p.grad.add_(p.detach(), alpha=c)
 
     def _prepare_grads(self) -> None:
+        self._wait_tower()
         self._apply_clip()
         self._apply_regularizers()
 
@@ -222,6 +231,7 @@ class Adam(_Base):
     @torch.no_grad()
     def step_dense(self, prepared: bool = False) -> None:
         """Second half of step(): the replicated dense parameters (torch's fused Adam)."""
+        self._wait_tower()
         if not prepared:
             self._apply_regularizers()
         lr = self.get_lr()
@@ -253,6 +263,7 @@ class SparseAdaGrad(_Base):
 
     @torch.no_grad()
     def step(self) -> None:
+        self._wait_tower()
         self._apply_regularizers()
         if self._torch is not None:
             self._torch.step()

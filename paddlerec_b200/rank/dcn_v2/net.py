@@ -63,7 +63,7 @@ class DCN_V2Layer(tnn.Module):
             logit = self.fc(self.DNN_(cross_out))
         else:
             logit = self.fc(torch.cat([self.DNN_(feat), cross_out], dim=-1))
-        return torch.sigmoid(logit)
+        return ops.sum_sigmoid(logit) if logit.is_cuda else torch.sigmoid(logit)
 
 
 class DNNLayer(tnn.Module):

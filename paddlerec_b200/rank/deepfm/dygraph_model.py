@@ -56,8 +56,7 @@ class DygraphModel:
 
     def create_loss(self, pred, label):
         """Mean log-loss with Paddle's epsilon 1e-4 on the sigmoid output (reference :53-58)."""
-        cost = BF.log_loss(pred, label.to(torch.float32))
-        return cost.mean()
+        return BF.log_loss_mean(pred, label)
 
     def create_optimizer(self, dy_model, config):
         """Adam over every parameter; the two tables are updated row-wise from their SelectedRows

@@ -36,6 +36,8 @@ class DeepFMLayer(tnn.Module):
     def forward(self, sparse_inputs, dense_inputs):
         y_first_order, y_second_order, feat_embeddings = self.fm(sparse_inputs, dense_inputs)
         y_dnn = self.dnn(feat_embeddings)
+        if y_dnn.is_cuda:   # net.py:47 — the two adds and the sigmoid as one kernel each way
+            return ops.sum_sigmoid(y_first_order, y_second_order, y_dnn)
         return torch.sigmoid(y_first_order + y_second_order + y_dnn)
 
 

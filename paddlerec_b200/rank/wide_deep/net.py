@@ -77,4 +77,6 @@ class WideDeepLayer(tnn.Module):
         else:
             for layer in self._mlp_layers:
                 deep = layer(deep)
+        if deep.is_cuda:
+            return ops.sum_sigmoid(wide_output, deep)                             # :99-101, fused
         return torch.sigmoid(wide_output + deep)                                  # :99-101

@@ -224,6 +224,8 @@ def train(config: dict, max_steps=None, save=True):
 
     dy_model = dy_model_class.create_model(config)
     optimizer = dy_model_class.create_optimizer(dy_model, config)
+    from . import tower
+    tower.set_overlap_dw(True)          # the optimizers wait for the side-stream dW GEMMs
     if model_init_path is not None:     # warm start (trainer.py:106-107); also resumes rec.pdopt
         load_model(model_init_path, dy_model, optimizer=optimizer)
     train_dataloader = create_data_loader(config, "train")

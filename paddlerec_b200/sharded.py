@@ -507,7 +507,10 @@ class ShardedDeepFMLayer(tnn.Module):
 
     def forward(self, sparse_inputs, dense_inputs):
         y1, y2, feat = self.fm(sparse_inputs, dense_inputs)
-        return torch.sigmoid(y1 + y2 + self.dnn(feat))
+        y_dnn = self.dnn(feat)
+        if y_dnn.is_cuda and self.fm.k is _cuda_ops:
+            return _cuda_ops.sum_sigmoid(y1, y2, y_dnn)
+        return torch.sigmoid(y1 + y2 + y_dnn)
 
     def prefetch(self, next_sparse_inputs) -> None:
         """Hint: the ids of the NEXT batch (the very tensor that will be passed to forward)."""
@@ -557,6 +560,8 @@ class DistributedOptimizer:
         self.inner.clear_grad()
 
     def _allreduce_dense(self):
+        from . import tower
+        tower.wait_pending()        # the tower's dW GEMMs may still run on their side stream
         grads = [p.grad for p in self._dense if p.grad is not None]
         if grads and self.world > 1:
             with _timed("nccl_allreduce_dense"):

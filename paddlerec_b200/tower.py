@@ -35,6 +35,38 @@ F32 = torch.float32
 BACKEND = os.environ.get("B200REC_TOWER", "tcgen05")
 
 
+# The weight-gradient GEMMs do not feed the rest of the backward pass (only the optimizer needs
+# them), so they can run on a side stream while the main stream continues with the embedding
+# backward, the gradient exchange and the row-wise table update — tensor-core / L2-bound work beside
+# HBM- and NVLink-bound work.  Whoever consumes the gradients must call wait_pending() first: the
+# optimizers of this package do.  Off by default (ad-hoc code that reads .grad right after
+# backward() is then safe without it); runner.train and bench.py switch it on.
+OVERLAP_DW = False
+_PENDING: List["torch.cuda.Event"] = []
+_SIDE = {}
+
+
+def set_overlap_dw(on: bool) -> None:
+    global OVERLAP_DW
+    OVERLAP_DW = bool(on)
+
+
+def wait_pending() -> None:
+    """Make the current stream wait for the weight-gradient GEMMs still running on the side stream."""
+    if _PENDING:
+        cur = torch.cuda.current_stream()
+        for ev in _PENDING:
+            cur.wait_event(ev)
+        _PENDING.clear()
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = device.index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 def set_backend(name: str) -> None:
     global BACKEND
     if name not in ("tcgen05", "cublas"):
@@ -104,9 +136,13 @@ class _TowerTcFn(torch.autograd.Function):
         else:
             g, db = ops.raw_tc_split_bwd(dy.contiguous(), acts[n] if ctx.last_act else None)
         dx0 = None
+        overlap = OVERLAP_DW and dy.is_cuda
+        deferred = []
         for i in range(top, -1, -1):
             K, N = ctx.shapes[i]
-            if ones[i]:
+            if overlap:
+                deferred.append((i, acts[i], K, g, N, db))
+            elif ones[i]:
                 dWs[i], dbs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N, bias_row=True)
             else:
                 dWs[i] = ops.raw_tc_linear_bwd_dw(acts[i], K, g, N)
@@ -120,6 +156,25 @@ class _TowerTcFn(torch.autograd.Function):
             elif ctx.needs_input_grad[0]:
                 dx0, _, _ = ops.raw_tc_linear_bwd_dx(g, N, wps[i], K, None, want_f32=True,
                                                      want_planes=False, want_dbias=False)
+        if deferred:
+            # the dX chain is enqueued; the dW GEMMs follow on the side stream and overlap whatever
+            # the main stream does next (embedding backward, exchange, table update)
+            cur = torch.cuda.current_stream()
+            side = _side_stream(dy.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for i, a_i, K, g_i, N, db_i in deferred:
+                    if ones[i]:
+                        dWs[i], dbs[i] = ops.raw_tc_linear_bwd_dw(a_i, K, g_i, N, bias_row=True,
+                                                                  ws_tag="tc_bwd_side")
+                    else:
+                        dWs[i] = ops.raw_tc_linear_bwd_dw(a_i, K, g_i, N, ws_tag="tc_bwd_side")
+                        dbs[i] = db_i if ctx.has_bias[i] else None
+                    a_i.record_stream(side)      # allocated on the main stream, read on the side
+                    g_i.record_stream(side)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            _PENDING.append(ev)
         ctx.acts = ctx.wps = None
         return (dx0, None, None, *dWs, *dbs)
 

@@ -267,7 +267,7 @@ def test_tc_linear_autograd_small_and_odd_shapes():
 
 @pytest.mark.parametrize("sizes", [[624, 400, 400, 400, 1], [429, 512, 256, 128, 32]])
 @pytest.mark.parametrize("last_act", [False, True])
-@pytest.mark.parametrize("backend", ["tcgen05", "cublas"])
+@pytest.mark.parametrize("backend", ["tcgen05", "tcgen05+overlap", "cublas"])
 def test_tower_backends_match_fp64(backend, last_act, sizes):
     """The whole tower (forward + every gradient) on both back ends, headline shape."""
     from paddlerec_b200 import tower
@@ -305,13 +305,17 @@ def test_tower_backends_match_fp64(backend, last_act, sizes):
     Wc = [w.to(DEV).requires_grad_(True) for w in Ws]
     bc = [b.to(DEV).requires_grad_(True) for b in bs]
     prev = tower.BACKEND
-    tower.set_backend(backend)
+    tower.set_backend(backend.split("+")[0])
+    tower.set_overlap_dw(backend.endswith("overlap"))   # dW GEMMs on the side stream
     try:
         y = tower.mlp(xc, Wc, bc, last_act=last_act)
         (y * gy.to(DEV)).sum().backward()
-        torch.cuda.synchronize()
+        assert bool(tower._PENDING) == backend.endswith("overlap")
+        tower.wait_pending()        # what the optimizers do before they touch the gradients
+        torch.cuda.current_stream().synchronize()
     finally:
         tower.set_backend(prev)
+        tower.set_overlap_dw(False)
     assert rel_err(y, h) < 1e-4
     assert rel_err(xc.grad, xd.grad) < 1e-4
     for a, b in zip(Wc + bc, Wd + bd):
@@ -369,3 +373,32 @@ def test_tc_cta_pair_kernel(M, N, K):
     wdx = gy.double() @ W.double().t()
     assert _err(dx, wdx) < 5e-5
     assert _err(_join(dxp, K), wdx * (a[:, :K].double().cpu() > 0)) < 5e-5
+
+
+def test_ctr_head_fused_ops():
+    """sum_sigmoid and log_loss_mean (one kernel each way) vs the torch composition in fp64, float
+    and int64 labels, gradients through both."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    n = 70001
+    parts = [torch.randn(n, 1, generator=g) for _ in range(3)]
+    label_f = (torch.rand(n, 1, generator=g) < 0.3).float()
+    for label in (label_f, label_f.long()):
+        pd = [t.double().requires_grad_(True) for t in parts]
+        pr = torch.sigmoid(pd[0] + pd[1] + pd[2])
+        y = label.double()
+        lr = (-y * torch.log(pr + 1e-4) - (1 - y) * torch.log(1 - pr + 1e-4)).mean()
+        lr.backward()
+        pc = [t.to(DEV).requires_grad_(True) for t in parts]
+        pred = ops.sum_sigmoid(*pc)
+        loss = ops.log_loss_mean(pred, label.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        assert pred.shape == (n, 1) and _err(pred, pr.detach()) < 1e-6
+        assert abs(float(loss) - float(lr)) < 1e-6 * abs(float(lr))
+        for a, b in zip(pc, pd):
+            assert _err(a.grad, b.grad) < 1e-5
+        loss2 = ops.log_loss_mean(pred.detach(), label.to(DEV))
+        assert float(loss2) == float(loss)           # deterministic reduction
+    two = ops.sum_sigmoid(parts[0].to(DEV), parts[1].to(DEV))
+    assert _err(two, torch.sigmoid(parts[0].double() + parts[1].double())) < 1e-6
