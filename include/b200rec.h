@@ -297,6 +297,10 @@ int b200rec_log_loss_mean_fwd(const float* pred, const void* label, int label_is
                               void* stream);
 int b200rec_log_loss_mean_bwd(const float* pred, const void* label, int label_is_i64, double eps,
                               const float* dloss, float* dpred, int64_t n, void* stream);
+/* paddle.metric.Auc.update on the device: stat_pos / stat_neg [num_thresholds+1] int64 histograms,
+ * bucket = clamp(int(pred * num_thresholds)).  One launch, no host sync. */
+int b200rec_auc_update(const float* pred, const void* label, int label_is_i64, int64_t* stat_pos,
+                       int64_t* stat_neg, int num_thresholds, int64_t n, void* stream);
 /* tuning / bring-up knobs (key 0: force tile width BN; 1-3: descriptor overrides of the dW kernel;
  * 4: k-block of the K-major kernel, 64 = 128-byte swizzle, 32 = 64-byte swizzle, more stages;
  * 5: epilogue outputs through TMA bulk stores (1) or register stores (0); 6: K-major GEMM on CTA

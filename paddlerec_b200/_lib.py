@@ -133,6 +133,7 @@ _SIG = {
     "b200rec_log_loss_workspace_bytes": (c_int, [POINTER(c_size_t)]),
     "b200rec_log_loss_mean_fwd": (c_int, [_P, _P, c_int, c_double, _P, c_int64, _P, c_size_t, _P]),
     "b200rec_log_loss_mean_bwd": (c_int, [_P, _P, c_int, c_double, _P, _P, c_int64, _P]),
+    "b200rec_auc_update": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int64, _P]),
     "b200rec_tc_debug": (c_int, [c_int, c_int]),
     "b200rec_tc_timeout_word": (c_int, [POINTER(ctypes.c_uint)]),
     "b200rec_dot_interact_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),

@@ -498,6 +498,24 @@ int b200rec_log_loss_mean_bwd(const float* pred, const void* label, int label_is
   return B200REC_OK;
 }
 
+int b200rec_auc_update(const float* pred, const void* label, int label_is_i64, int64_t* stat_pos,
+                       int64_t* stat_neg, int num_thresholds, int64_t n, void* stream) {
+  B200_REQUIRE(n >= 0 && num_thresholds > 0, "auc_update: bad sizes");
+  if (n == 0) return B200REC_OK;
+  NOT_NULL(pred); NOT_NULL(label); NOT_NULL(stat_pos); NOT_NULL(stat_neg);
+  const unsigned grid = (unsigned)((n + kHeadOpThreads - 1) / kHeadOpThreads);
+  long long* p = reinterpret_cast<long long*>(stat_pos);
+  long long* q = reinterpret_cast<long long*>(stat_neg);
+  if (label_is_i64)
+    auc_update_kernel<int64_t><<<grid, kHeadOpThreads, 0, ST(stream)>>>(
+        pred, static_cast<const int64_t*>(label), p, q, num_thresholds, n);
+  else
+    auc_update_kernel<float><<<grid, kHeadOpThreads, 0, ST(stream)>>>(
+        pred, static_cast<const float*>(label), p, q, num_thresholds, n);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
 int b200rec_tc_debug(int key, int value) {
   switch (key) {
     case 0: tc::g_bn_override = value; break;

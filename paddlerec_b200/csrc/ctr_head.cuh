@@ -86,6 +86,20 @@ __global__ void log_loss_mean_bwd_kernel(const float* __restrict__ pred,
   dpred[i] = g * (-y / (p + eps) + (1.f - y) / (1.f - p + eps));
 }
 
+// paddle.metric.Auc.update (deepfm/dygraph_model.py:75-87): bucket = clamp(int(p * T), 0, T);
+// stat_pos / stat_neg [T+1] += 1.  Integer atomics: the result does not depend on their order.
+template <typename LabelT>
+__global__ void auc_update_kernel(const float* __restrict__ pred, const LabelT* __restrict__ label,
+                                  long long* __restrict__ pos, long long* __restrict__ neg,
+                                  int num_thresholds, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long b = (long long)(pred[i] * (float)num_thresholds);
+  b = b < 0 ? 0 : (b > num_thresholds ? num_thresholds : b);
+  const bool is_pos = label[i] != (LabelT)0;
+  atomicAdd(reinterpret_cast<unsigned long long*>(is_pos ? pos : neg) + b, 1ull);
+}
+
 constexpr int kLossBlocks = 148;
 static size_t log_loss_ws_bytes() { return (size_t)kLossBlocks * sizeof(float) + 16; }
 

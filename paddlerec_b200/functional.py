@@ -44,10 +44,14 @@ class Auc:
         p = preds[:, 1] if (preds.dim() == 2 and preds.shape[1] == 2) else preds.reshape(-1)
         y = labels.reshape(-1).to(p.device)
         nb = self.num_thresholds + 1
-        idx = (p.detach().float() * self.num_thresholds).to(torch.int64).clamp_(0, nb - 1)
         if self._pos is None:
             self._pos = torch.zeros(nb, dtype=torch.int64, device=p.device)
             self._neg = torch.zeros(nb, dtype=torch.int64, device=p.device)
+        if p.is_cuda and p.dtype == torch.float32:
+            from . import ops       # one kernel, integer atomics, no host sync
+            ops.raw_auc_update(p.detach(), y, self._pos, self._neg, self.num_thresholds)
+            return
+        idx = (p.detach().float() * self.num_thresholds).to(torch.int64).clamp_(0, nb - 1)
         # index_add_ into preallocated histograms: no data-dependent shape, hence no host sync
         # (boolean indexing / bincount would synchronise every step like the reference's .numpy())
         is_pos = (y != 0).to(torch.int64)

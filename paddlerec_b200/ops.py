@@ -46,7 +46,7 @@ KERNELS_PER_CALL = {
     "tower_prep_weight": 1, "tower_fold_dw": 1, "tc_split": 1, "tc_split_bwd": 2,
     "tc_prep_weight": 1, "tc_linear_fwd": 1, "tc_cross_fwd": 1, "tc_linear_bwd_dx": 1,
     "tc_linear_bwd_dx_db": 2, "tc_linear_bwd_dw": 2, "tc_head_fwd": 1, "tc_head_bwd": 2,
-    "sum_sigmoid_fwd": 1, "sum_sigmoid_bwd": 1, "log_loss_mean_fwd": 1, "log_loss_mean_bwd": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
+    "auc_update": 1, "sum_sigmoid_fwd": 1, "sum_sigmoid_bwd": 1, "log_loss_mean_fwd": 1, "log_loss_mean_bwd": 1, "din_attn_fwd": 2, "din_attn_bwd": 3, "gather_pool_sum": 2, "cvm_fwd": 1, "cvm_bwd": 1, "hash_keys": 1, "dot_interact_fwd": 1, "dot_interact_bwd": 1,
 }
 # When set to a list, (name, start_event, end_event) triples are appended around the raw_* calls
 # (all of them, or only the names in EVENT_FILTER when that is a set) — bench.py's per-kernel times.
@@ -723,6 +723,20 @@ class _LogLossMean(torch.autograd.Function):
 
 def log_loss_mean(pred, label, eps: float = 1e-4):
     return _LogLossMean.apply(pred, label, eps)
+
+
+def raw_auc_update(pred: torch.Tensor, label: torch.Tensor, stat_pos: torch.Tensor,
+                   stat_neg: torch.Tensor, num_thresholds: int) -> None:
+    """paddle.metric.Auc.update as one kernel on the device-resident int64 histograms."""
+    lib = _lib.load()
+    p = _req(pred.reshape(-1), torch.float32, "pred")
+    if label.dtype not in (torch.float32, torch.int64):
+        label = label.to(torch.float32)
+    y = label.reshape(-1).contiguous()
+    check(lib.b200rec_auc_update(ptr(p), ptr(y), int(y.dtype == torch.int64), ptr(stat_pos),
+                                 ptr(stat_neg), int(num_thresholds), p.numel(), _stream()),
+          "auc_update")
+    _count("auc_update")
 
 
 def tc_debug(key: int, value: int) -> None:

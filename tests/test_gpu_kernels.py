@@ -629,3 +629,22 @@ def test_embedding_used_twice_merges_selected_rows():
     ((Wd[ids1] * m1 * w1.double()).sum() + (Wd[ids2] * m2 * w2.double()).sum()).backward()
     assert rel_err(got, Wd.grad) < 1e-6
     assert not got[0].any()
+
+
+def test_auc_update_kernel_matches_host_metric():
+    """b200rec_auc_update (device histograms, one launch) == the torch bucketing of functional.Auc
+    on the CPU, and the AUC itself against sklearn's exact value."""
+    from sklearn.metrics import roc_auc_score
+    from paddlerec_b200 import functional as BF
+    g = torch.Generator().manual_seed(17)
+    n = 50000
+    y = (torch.rand(n, generator=g) < 0.3).long()
+    p = (torch.rand(n, generator=g) * 0.6 + 0.3 * y.float() * torch.rand(n, generator=g)).clamp(0, 1)
+    p[0], p[1] = 0.0, 1.0
+    dev, host = BF.Auc(), BF.Auc()
+    for lo in range(0, n, 12500):
+        dev.update(p[lo:lo + 12500].to(DEV).reshape(-1, 1), y[lo:lo + 12500].to(DEV).reshape(-1, 1))
+        host.update(p[lo:lo + 12500].reshape(-1, 1), y[lo:lo + 12500].reshape(-1, 1))
+    assert torch.equal(dev.stats()[0].cpu(), host.stats()[0])
+    assert torch.equal(dev.stats()[1].cpu(), host.stats()[1])
+    assert abs(dev.accumulate() - roc_auc_score(y.numpy(), p.numpy())) < 2e-3
