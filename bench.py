@@ -196,6 +196,14 @@ def time_cpu_port(args, V, steps):
     return B * steps / secs, best_t, secs / steps, loss
 
 
+def exchange_name(world):
+    """How table rows / gradients move at N>1 (mirrors paddlerec_b200.sharded.p2p_enabled)."""
+    env = os.environ.get("B200REC_P2P", "auto")
+    p2p = env == "1" or (env != "0" and world <= 4)
+    return ("row / gradient exchange by our kernels storing into peer memory over NVLink, ids by "
+            "NCCL all-to-all" if p2p else "NCCL all-to-all")
+
+
 def workload_config(args, world):
     return {"workload": "DeepFM Criteo-shape: 26 sparse + 13 dense slots, hashed vocab %d, D=%d, "
                         "B=%d per GPU, fc [%s], %s ids (2%% padding)" %
@@ -203,7 +211,8 @@ def workload_config(args, world):
             "global_batch": args.batch * world, "tower_matmul": args.precision,
             "optimizer": "Adam (lazy rows on the tables)",
             "parallelism": "single GPU" if world == 1 else
-            "tables row-sharded (id mod %d) + NCCL all-to-all; dense params data-parallel" % world,
+            "tables row-sharded (id mod %d) + %s; dense params data-parallel (NCCL all-reduce)" %
+            (world, exchange_name(world)),
             "l2": "inputs larger than L2 (8 rotating batches; 164 MB feat + 6.4 GB table per step)"}
 
 

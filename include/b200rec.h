@@ -198,6 +198,14 @@ int b200rec_shard_gather_push(const float* shard, int64_t ldw, int D, int64_t V_
                               int64_t local_pad, const int64_t* recv_ids, const int64_t* seg_dev,
                               const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
                               int world, int64_t n, void* stream);
+/* DeepFM: the sparse half of the FM backward fused with the push — slot k (position b*F+f = inv_perm[k]) receives
+ * [ gy2[b]*(S[b]-feat[b,f]) + dfeat_dnn[b,f] | gy1[b] | 0.. ] (G floats) straight in its owner's
+ * buffer; no [B*F, G] staging buffer exists.  D % 4 == 0, G % 4 == 0, G >= D+1. */
+int b200rec_shard_fm_grads_push(const float* feat, const float* S, const float* dfeat_dnn,
+                                const float* gy1, const float* gy2, const int32_t* inv_perm,
+                                const int64_t* seg_dev, const int64_t* dst_dev,
+                                const uint64_t* peer_ptrs_host, int64_t ld_dst, int world, int64_t B,
+                                int F, int Dn, int D, int G, void* stream);
 int b200rec_shard_push_rows(const float* rows, int64_t ld, int D, const int64_t* seg_dev,
                             const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
                             int world, int64_t n, void* stream);

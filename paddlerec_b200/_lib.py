@@ -109,6 +109,8 @@ _SIG = {
     "b200rec_tower_fold_dw": (c_int, [_P, _P, c_int, c_int, _P]),
     "b200rec_shard_gather_push": (c_int, [_P, c_int64, c_int, c_int64, c_int64, _P, _P, _P,
                                           POINTER(c_uint64), c_int64, c_int, c_int64, _P]),
+    "b200rec_shard_fm_grads_push": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, POINTER(c_uint64), c_int64,
+                                            c_int, c_int64, c_int, c_int, c_int, c_int, _P]),
     "b200rec_shard_push_rows": (c_int, [_P, c_int64, c_int, _P, _P, POINTER(c_uint64), c_int64,
                                         c_int, c_int64, _P]),
     "b200rec_tc_split": (c_int, [_P, c_int64, _P, c_int, _P, c_int64, c_int64, c_int, c_int, _P]),

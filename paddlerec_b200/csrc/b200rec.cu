@@ -259,6 +259,20 @@ int b200rec_shard_gather_push(const float* shard, int64_t ldw, int D, int64_t V_
                                   peer_ptrs_host, ld_dst, world, n, ST(stream));
 }
 
+int b200rec_shard_fm_grads_push(const float* feat, const float* S, const float* dfeat_dnn,
+                                const float* gy1, const float* gy2, const int32_t* inv_perm,
+                                const int64_t* seg_dev, const int64_t* dst_dev,
+                                const uint64_t* peer_ptrs_host, int64_t ld_dst, int world, int64_t B,
+                                int F, int Dn, int D, int G, void* stream) {
+  NOT_NULL(peer_ptrs_host);
+  if (B > 0 && F > 0) {
+    NOT_NULL(feat); NOT_NULL(S); NOT_NULL(gy1); NOT_NULL(gy2); NOT_NULL(inv_perm); NOT_NULL(seg_dev);
+    NOT_NULL(dst_dev);
+  }
+  return launch_shard_fm_grads_push(feat, S, dfeat_dnn, gy1, gy2, inv_perm, seg_dev, dst_dev,
+                                    peer_ptrs_host, ld_dst, world, B, F, Dn, D, G, ST(stream));
+}
+
 int b200rec_shard_push_rows(const float* rows, int64_t ld, int D, const int64_t* seg_dev,
                             const int64_t* dst_dev, const uint64_t* peer_ptrs_host, int64_t ld_dst,
                             int world, int64_t n, void* stream) {

@@ -212,6 +212,63 @@ shard_push_rows_kernel(const float* __restrict__ rows, int64_t ld,
   }
 }
 
+// K2 (sparse part) of DeepFM fused with the gradient push of the sharded path.  In the sharded
+// backward every position is its own segment (the owner merges duplicates), so the per-slot
+// gradient row  [ g2*(S - feat) + dfeat_dnn | g1 | 0.. ]  (models/rank/deepfm/net.py:123-137
+// differentiated) is computed here and stored DIRECTLY into the owner's receive buffer over NVLink —
+// the [n,G] staging buffer, its write and its re-read by a separate push kernel disappear.
+//   feat [B,N,D], S [B,D], dfeat_dnn [B,N,D] or null, gy1/gy2 [B], inv_perm [B*F] = position held by
+//   every bucket slot; the row of slot k goes to peer o = owner segment of k, row dst[o] + k - seg[o].
+//   Chunk-linear in the DESTINATION (like shard_push_rows): remote stores are contiguous per peer,
+//   the scattered side is the local 64-byte reads of feat, which L2 absorbs.
+__global__ void __launch_bounds__(kPushThreads)
+shard_fm_grads_push_kernel(const float* __restrict__ feat, const float* __restrict__ S,
+                           const float* __restrict__ dfeat, const float* __restrict__ gy1,
+                           const float* __restrict__ gy2, const int32_t* __restrict__ inv_perm,
+                           const int64_t* __restrict__ seg_dev, const int64_t* __restrict__ dst_dev,
+                           PeerTable peers, int world, int64_t n, int F, int N, int D, int G,
+                           int64_t ld_dst) {
+  __shared__ int64_t s_seg[kMaxPeers + 1];
+  __shared__ int64_t s_dst[kMaxPeers];
+  if (threadIdx.x <= world) s_seg[threadIdx.x] = seg_dev[threadIdx.x];
+  if (threadIdx.x < world) s_dst[threadIdx.x] = dst_dev[threadIdx.x];
+  __syncthreads();
+  const int cpr = G / 4;                 // chunks per gradient row: D/4 embedding chunks, then [g1,0,0,0], zeros
+  const int ce = D / 4;
+  const int64_t total = n * cpr;
+  for (int64_t c = (int64_t)blockIdx.x * kPushThreads + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * kPushThreads) {
+    const int64_t k = c / cpr;
+    const int part = (int)(c - k * cpr);
+    const int64_t p = __ldg(inv_perm + k);
+    const int64_t b = p / F;
+    const int f = (int)(p - b * F);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (part < ce) {
+      const size_t off = ((size_t)b * N + f) * D + part * 4;
+      const float4 e = __ldg(reinterpret_cast<const float4*>(feat + off));
+      const float4 s = __ldg(reinterpret_cast<const float4*>(S + (size_t)b * D + part * 4));
+      const float g2 = __ldg(gy2 + b);
+      v = make_float4(g2 * (s.x - e.x), g2 * (s.y - e.y), g2 * (s.z - e.z), g2 * (s.w - e.w));
+      if (dfeat != nullptr) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dfeat + off));
+        v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+      }
+    } else if (part == ce) {
+      v.x = __ldg(gy1 + b);
+    }
+    const int o = peer_of(s_seg, world, k);
+    float* out = peers.base[o] + (size_t)(s_dst[o] + (k - s_seg[o])) * ld_dst + part * 4;
+    *reinterpret_cast<float4*>(out) = v;
+  }
+}
+
+static int launch_shard_fm_grads_push(const float* feat, const float* S, const float* dfeat,
+                                      const float* gy1, const float* gy2, const int32_t* inv_perm,
+                                      const int64_t* seg_dev, const int64_t* dst_dev,
+                                      const uint64_t* peer_ptrs_host, int64_t ld_dst, int world,
+                                      int64_t B, int F, int Dn, int D, int G, cudaStream_t st);
+
 static int fill_peer_table(PeerTable* t, const uint64_t* peer_ptrs_host, int world) {
   B200_REQUIRE(world >= 1 && world <= kMaxPeers, "shard push: world=%d (max %d)", world, kMaxPeers);
   for (int r = 0; r < kMaxPeers; ++r)
@@ -274,6 +331,30 @@ static int launch_shard_push_rows(const float* rows, int64_t ld, int D, const in
   else
     shard_push_rows_kernel<1><<<grid, kPushThreads, 0, st>>>(rows, ld, seg_dev, dst_dev, t, world, n, D,
                                                             ld_dst);
+  B200_LAUNCH_CHECK();
+  return B200REC_OK;
+}
+
+static int launch_shard_fm_grads_push(const float* feat, const float* S, const float* dfeat,
+                                      const float* gy1, const float* gy2, const int32_t* inv_perm,
+                                      const int64_t* seg_dev, const int64_t* dst_dev,
+                                      const uint64_t* peer_ptrs_host, int64_t ld_dst, int world,
+                                      int64_t B, int F, int Dn, int D, int G, cudaStream_t st) {
+  PeerTable t;
+  int rc = fill_peer_table(&t, peer_ptrs_host, world);
+  if (rc != B200REC_OK) return rc;
+  B200_REQUIRE(D > 0 && D % 4 == 0 && G % 4 == 0 && G >= D + 1 && ld_dst >= G && ld_dst % 4 == 0,
+               "shard_fm_grads_push: needs D %% 4 == 0 and G %% 4 == 0, G >= D+1 (D=%d G=%d)", D, G);
+  B200_REQUIRE(aligned16(feat) && aligned16(S) && (dfeat == nullptr || aligned16(dfeat)),
+               "shard_fm_grads_push: feat / S / dfeat must be 16-byte aligned");
+  const int64_t n = B * F;
+  if (n == 0) return B200REC_OK;
+  const int64_t chunks = n * (G / 4);
+  const int64_t want = (chunks + kPushThreads - 1) / kPushThreads;
+  const unsigned grid = (unsigned)min(want, (int64_t)sm_count() * 32);
+  shard_fm_grads_push_kernel<<<grid, kPushThreads, 0, st>>>(feat, S, dfeat, gy1, gy2, inv_perm, seg_dev,
+                                                          dst_dev, t, world, n, F, F + Dn, D, G,
+                                                          ld_dst);
   B200_LAUNCH_CHECK();
   return B200REC_OK;
 }

@@ -92,8 +92,25 @@ class PeerBuffers:
         self.hdl.barrier(channel=1)
 
 
-def p2p_enabled() -> bool:
-    return os.environ.get("B200REC_P2P", "1") != "0"
+P2P_MAX_WORLD = 4
+# b200rec_shard_fm_grads_push (K2's sparse half + the push as one kernel): compiled and desk-checked
+# but NOT yet run on a GPU (the round's GPU budget ended first) -> opt-in only.
+FUSED_PUSH = os.environ.get("B200REC_FUSED_PUSH", "0") == "1"
+
+
+def p2p_enabled(world: int) -> bool:
+    """Peer-memory exchange on/off.  B200REC_P2P=1 forces it on, =0 off; unset = on for up to
+    P2P_MAX_WORLD ranks.  The limit is the largest world size the peer-memory path has completed
+    tests + bench on (2 and 4 ranks, profiles/r2g_*, r2h_*, r2j_*); the one 8-rank bench attempt with
+    it did not finish inside its 300 s limit and could not be diagnosed, so
+    more than 4 ranks use the NCCL all-to-all exchange, which is validated at 8
+    (profiles/r2_sharded_parity_n8.log, profiles/r2k_cfg3_dcn_n8.jsonl)."""
+    env = os.environ.get("B200REC_P2P", "auto")
+    if env == "0":
+        return False
+    if env == "1":
+        return True
+    return world <= P2P_MAX_WORLD
 
 
 class ShardExchange:
@@ -224,7 +241,7 @@ class ShardExchange:
     def enable_p2p(self, cols: int) -> None:
         """Ask for the peer-memory exchange of `cols`-wide rows (takes effect from the next
         bucketing on; the buffers are created collectively at the first pull)."""
-        if p2p_enabled() and self.world > 1 and torch.cuda.is_available():
+        if self.world > 1 and p2p_enabled(self.world) and torch.cuda.is_available():
             self.p2p_cols = int(cols)
 
     def _use_p2p(self, plan: ExchangePlan, cols: int, shard: torch.Tensor) -> bool:
@@ -289,6 +306,20 @@ class ShardExchange:
             dist.all_to_all_single(out, grads_bucket_order.contiguous(), plan.recv_splits,
                                    plan.send_splits, group=self.group)
         return out
+
+    def push_fm_grads(self, plan: ExchangePlan, feat, S, dfeat, gy1, gy2, F: int, G: int):
+        """DeepFM over peer memory: K2's sparse half and the push as ONE kernel (None if the
+        peer-memory exchange is not active for this plan: caller falls back to K2 + push)."""
+        D = feat.shape[2]
+        if (not FUSED_PUSH or self.peer is None or plan.tables is None or G != self.peer.cols or
+                not feat.is_cuda or D % 4 or G % 4):
+            return None
+        self.k.raw_shard_fm_grads_push(feat, S, dfeat, gy1, gy2, plan.inv_perm, F, G,
+                                       plan.tables["send_seg"], plan.tables["dst_push"],
+                                       self.peer.grads_ptrs, self.peer.cols, self.world)
+        with _timed("p2p_barrier"):
+            self.peer.publish_grads()
+        return self.peer.grads[:plan.recv_ids.numel()]
 
     def owner_reduce(self, plan: ExchangePlan, grads: torch.Tensor, V_loc: int, local_pad: int):
         """Merge the received gradients by local row -> SelectedRows on the local shard."""
@@ -404,10 +435,18 @@ class _ShardedEmbedFM(torch.autograd.Function):
         # seg_offsets = iota, sorted_pos = inv_perm: row k of the output is the gradient of slot k
         if fm.fused:
             tab = fm._fused
-            dW, _, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
-                                                            plan.inv_perm, num, F,
-                                                            fused_cols=tab.grad_cols)
-            g = ex.push(plan, dW[:n])
+            g = ex.push_fm_grads(plan, feat, S, dfeat, gy1, gy2, F, tab.grad_cols)
+            if g is not None:
+                # sparse half + push were one kernel; only the dense-feature gradients remain
+                # (the segmented part of K2 sees zero segments)
+                _, _, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
+                                                               plan.inv_perm, fm.zero_groups(dev), F,
+                                                               fused_cols=tab.grad_cols)
+            else:
+                dW, _, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense,
+                                                                iota, plan.inv_perm, num, F,
+                                                                fused_cols=tab.grad_cols)
+                g = ex.push(plan, dW[:n])
             tab.accept_fused(ex.owner_reduce(plan, g, tab.num_embeddings, tab.pad))
         else:
             dW, dW1, ddense_w, ddense_w1 = k.raw_embed_fm_bwd(feat, S, dfeat, gy1, gy2, dense, iota,
@@ -470,6 +509,15 @@ class ShardedFM(bnn.FusedTableOwner):
         if self.fused:
             return self._fused.grad_dense()
         return (self.embedding.grad_rows.to_dense(), self.embedding_one.grad_rows.to_dense())
+
+    def zero_groups(self, device):
+        """num = {0, 0}: "no segments" (the fused push kernel already produced the sparse rows)."""
+        key = ("zero", str(device))
+        hit = self._trivial.get(key)
+        if hit is None:
+            hit = torch.zeros(2, dtype=torch.int32, device=device)
+            self._trivial[key] = hit
+        return hit
 
     def trivial_groups(self, n: int, device):
         """seg_offsets = 0..n and num = {n, n}: "every slot is its own segment" (cached per n so
