@@ -249,11 +249,11 @@ shard_fm_grads_push_kernel(const float* __restrict__ feat, const float* __restri
       const float4 e = __ldg(reinterpret_cast<const float4*>(feat + off));
       const float4 s = __ldg(reinterpret_cast<const float4*>(S + (size_t)b * D + part * 4));
       const float g2 = __ldg(gy2 + b);
-      v = make_float4(g2 * (s.x - e.x), g2 * (s.y - e.y), g2 * (s.z - e.z), g2 * (s.w - e.w));
-      if (dfeat != nullptr) {
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dfeat + off));
-        v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
-      }
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dfeat != nullptr) d = __ldg(reinterpret_cast<const float4*>(dfeat + off));
+      // same rounding as FmRowContrib::add (embed_fm.cuh): one fma per element
+      v = make_float4(fmaf(g2, s.x - e.x, d.x), fmaf(g2, s.y - e.y, d.y), fmaf(g2, s.z - e.z, d.z),
+                      fmaf(g2, s.w - e.w, d.w));
     } else if (part == ce) {
       v.x = __ldg(gy1 + b);
     }

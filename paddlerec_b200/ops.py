@@ -830,7 +830,8 @@ class _EmbedFM(torch.autograd.Function):
         ctx.padding_idx = padding_idx
         ctx.sink = sink
         ctx.V = W.shape[0]
-        ctx.ahead = group_ids_ahead(ids, ctx.V, padding_idx) if any(ctx.needs_input_grad) else None
+        ctx.ahead = (group_ids_ahead(ids, ctx.V, padding_idx)
+                     if GROUP_AHEAD and any(ctx.needs_input_grad) else None)
         ctx.fused = W1 is None
         ctx.dense_w_shape = dense_w.shape
         ctx.mark_non_differentiable(S)
@@ -881,7 +882,8 @@ class _Gather(torch.autograd.Function):
         ctx.padding_idx = padding_idx
         ctx.sink = sink
         ctx.V = W.shape[0]
-        ctx.ahead = group_ids_ahead(ids, ctx.V, padding_idx) if any(ctx.needs_input_grad) else None
+        ctx.ahead = (group_ids_ahead(ids, ctx.V, padding_idx)
+                     if GROUP_AHEAD and any(ctx.needs_input_grad) else None)
         return out
 
     @staticmethod
@@ -904,7 +906,8 @@ class _GatherPool(torch.autograd.Function):
         out, bag_of_pos = raw_gather_pool_sum(W, keys, offsets, padding_idx)
         ctx.save_for_backward(keys, bag_of_pos)
         ctx.padding_idx, ctx.sink, ctx.V = padding_idx, sink, W.shape[0]
-        ctx.ahead = group_ids_ahead(keys, ctx.V, padding_idx) if any(ctx.needs_input_grad) else None
+        ctx.ahead = (group_ids_ahead(keys, ctx.V, padding_idx)
+                     if GROUP_AHEAD and any(ctx.needs_input_grad) else None)
         return out
 
     @staticmethod

@@ -224,3 +224,19 @@ def test_optimizer_step_does_not_advance_the_lr_scheduler():
     lin(torch.ones(1, 3)).sum().backward()
     opt.step()
     assert opt.get_lr() == 0.05
+
+
+def test_peer_memory_exchange_default_is_limited_to_validated_world_sizes(monkeypatch):
+    """sharded.p2p_enabled: on for <= 4 ranks unless B200REC_P2P says otherwise; bench.py names the
+    exchange it will actually use in config.parallelism."""
+    import importlib
+
+    from paddlerec_b200 import sharded
+    bench = importlib.import_module("bench")
+    monkeypatch.delenv("B200REC_P2P", raising=False)
+    assert [sharded.p2p_enabled(w) for w in (2, 4, 8)] == [True, True, False]
+    assert "peer memory" in bench.exchange_name(4) and bench.exchange_name(8) == "NCCL all-to-all"
+    monkeypatch.setenv("B200REC_P2P", "0")
+    assert not sharded.p2p_enabled(2) and bench.exchange_name(2) == "NCCL all-to-all"
+    monkeypatch.setenv("B200REC_P2P", "1")
+    assert sharded.p2p_enabled(8) and "peer memory" in bench.exchange_name(8)

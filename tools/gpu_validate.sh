@@ -15,6 +15,9 @@ if [ "$M" = "final" ]; then
   # compute-sanitizer on the smoke step (K1, K2, tcgen05 tower at a small size, lazy Adam)
   timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/${P}_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/${P}_sanitizer_memcheck.log
   B200REC_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_kernels.py -q -k "v2" -rf 2>&1 | tail -5 > $O/${P}_k6_v2.log
+  # opt-in paths that have not run on a GPU yet (ahead-of-time grouping; fused push needs >= 2 GPUs)
+  B200REC_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -q -rf 2>&1 | tail -8 > $O/${P}_experimental.log
+  B200REC_GROUP_AHEAD=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 > $O/${P}_bench_n1_group_ahead.json
   timeout 200 python tools/config_bench.py --what dcn --iters 6 2>&1 | grep "^{" > $O/${P}_cfg3_dcn_n1.jsonl
   timeout 120 python tools/config_bench.py --what din --B 4096 --iters 6 2>&1 | grep "^{" > $O/${P}_cfg4_din_n1.jsonl
   timeout 300 python tools/config_bench.py --what gather --vocabs 1e6,1e7,1e8,1e9 --dims 16,64,128 --iters 6 2>&1 | grep "^{" > $O/${P}_cfg5_gather_n1.jsonl
