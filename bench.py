@@ -590,6 +590,12 @@ def main():
         run_reference(args, rank)
         return
     if world > 1:
+        # a multi-rank job that stops making progress (a rank waiting in a collective its peers
+        # never entered) would otherwise sit until the caller's limit with no trace: after
+        # B200REC_BENCH_WATCHDOG_S seconds dump every thread's Python stack to stderr and exit.
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("B200REC_BENCH_WATCHDOG_S", "420")),
+                                          exit=True)
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -600,8 +606,11 @@ def main():
         run_b200(args, rank, world, local_rank)
     finally:
         if world > 1:
+            import faulthandler
+
             import torch.distributed as dist
             dist.destroy_process_group()
+            faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":

@@ -44,6 +44,10 @@ def _full_problem(B=B):
     return p, ids, dense, label
 
 
+def _batch_for(world):
+    return B if B % world == 0 else 2 * world
+
+
 def _worker(rank, world, port, out_dir, fused=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -51,7 +55,8 @@ def _worker(rank, world, port, out_dir, fused=True):
     try:
         from paddlerec_b200 import functional as BF
         from paddlerec_b200 import sharded
-        p, ids, dense, label = _full_problem()
+        B = _batch_for(world)
+        p, ids, dense, label = _full_problem(B)
         torch.manual_seed(100 + rank)   # different init per rank: broadcast must fix the tower
         model = sharded.ShardedDeepFMLayer(V, D, Dn, F, FC, rank, world, device="cpu",
                                            kernels=cpu_kernels, fused_table=fused)
@@ -88,11 +93,12 @@ class _NoStep:
         pass
 
 
-@pytest.mark.parametrize("world,fused", [(2, True), (2, False)])
+@pytest.mark.parametrize("world,fused", [(2, True), (2, False), (8, True)])
 def test_sharded_deepfm_matches_oracle(world, fused, tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path), fused), nprocs=world, join=True)
-    p, ids, dense, label = _full_problem()
+    B = _batch_for(world)
+    p, ids, dense, label = _full_problem(B)
     pp = {k: v.double().requires_grad_(True) for k, v in p.items()}
     ids_ok = ids.clone()
     ids_ok[ids_ok >= V] = 0
