@@ -319,3 +319,69 @@ def test_sharded_global_norm_clip_is_global(tmp_path):
         else:
             np.testing.assert_array_equal(r[0][k], r[1][k])          # replicas stay identical
             np.testing.assert_allclose(r[0][k], want, rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+def _exchange_blocks(blocks, recv_lens):
+    """Variable-size all-to-all of int64 blocks (gloo has all_to_all_single only)."""
+    out = torch.empty(sum(recv_lens), dtype=torch.int64)
+    dist.all_to_all_single(out, torch.cat(blocks), recv_lens, [b.numel() for b in blocks])
+    return list(out.split(recv_lens))
+
+
+def _tables_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paddlerec_b200 import sharded
+        Vt, n = 1000, 517
+        ex = sharded.ShardExchange(Vt, rank, world, kernels=cpu_kernels)
+        ex.p2p_cols = 4          # forces the segment / destination tables of the peer-memory exchange
+        g = torch.Generator().manual_seed(900 + rank)
+        ids = torch.randint(0, Vt, (n,), generator=g)
+        ids[:5] = torch.tensor([0, Vt + 3, -1, rank, Vt - 1])      # padding, out of range, edge rows
+        send_ids, perm, inv_perm, both, tables = ex._bucketize_and_count(ids)
+        counts, recv_counts = both[0], both[1]
+        recv_ids = torch.empty(int(recv_counts.sum()), dtype=torch.int64)
+        dist.all_to_all_single(recv_ids, send_ids, recv_counts.tolist(), counts.tolist())
+        # --- what b200rec_shard_gather_push does: the owner stores row i of its segment for requester
+        # r at row dst_pull[r] + i of r's buffer.  Row content here = the global id it stands for.
+        rows = torch.where(recv_ids >= 0, recv_ids * world + rank, torch.full_like(recv_ids, -7))
+        seg, dst = tables["recv_seg"], tables["dst_pull"]
+        blocks = [torch.cat([dst[r:r + 1], rows[int(seg[r]):int(seg[r + 1])]]) for r in range(world)]
+        got = _exchange_blocks(blocks, [1 + int(counts[o]) for o in range(world)])
+        buf = torch.full((n,), -99, dtype=torch.int64)
+        for o in range(world):
+            d = int(got[o][0])
+            buf[d:d + int(counts[o])] = got[o][1:]
+        valid = (ids >= 0) & (ids < Vt)
+        want = torch.where(valid, ids, torch.full_like(ids, -7))
+        assert torch.equal(buf[perm], want), "pull tables"
+        # --- b200rec_shard_push_rows: slot k of owner o's bucket goes to row dst_push[o] + k - send_seg[o]
+        # of o's gradient buffer; the owner expects requester r's rows at recv_seg[r].
+        sseg, dpush = tables["send_seg"], tables["dst_push"]
+        payload = inv_perm.to(torch.int64) * world + rank          # (position, requester) tag per slot
+        blocks = [torch.cat([dpush[o:o + 1], payload[int(sseg[o]):int(sseg[o + 1])]])
+                  for o in range(world)]
+        got = _exchange_blocks(blocks, [1 + int(recv_counts[r]) for r in range(world)])
+        gbuf = torch.full((int(recv_counts.sum()),), -99, dtype=torch.int64)
+        for r in range(world):
+            d = int(got[r][0])
+            assert d == int(seg[r]), "push destination != owner's receive segment"
+            gbuf[d:d + int(recv_counts[r])] = got[r][1:]
+        assert (gbuf >= 0).all()
+        for r in range(world):      # every row of requester r's segment really came from r
+            assert ((gbuf[int(seg[r]):int(seg[r + 1])] % world) == r).all()
+        with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_memory_exchange_tables(world, tmp_path):
+    """The device tables that steer the peer-memory exchange (send_seg / recv_seg / dst_pull /
+    dst_push of ShardExchange._bucketize_and_count), replayed with gloo: rows land where K1's `perm`
+    expects them, gradient rows land in the owner's receive segments."""
+    mp.spawn(_tables_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
