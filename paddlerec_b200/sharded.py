@@ -134,6 +134,7 @@ class ShardExchange:
         self.p2p_cols = None
         self.peer = None
         self._p2p_failed = False
+        self._peer_injected = False   # tests only: a host-memory stand-in for PeerBuffers (inject_peer)
 
     def _bucketize_and_count(self, ids):
         send_ids, perm, inv_perm, counts = self.k.raw_shard_bucketize(ids, self.world, self.V)
@@ -244,10 +245,16 @@ class ShardExchange:
         if self.world > 1 and p2p_enabled(self.world) and torch.cuda.is_available():
             self.p2p_cols = int(cols)
 
+    def inject_peer(self, peer, cols: int) -> None:
+        """TEST HOOK (tests/test_sharded_cpu.py): run the peer-memory choreography of pull / push on
+        host tensors — `peer` quacks like PeerBuffers with shared-memory tensors instead of NVLink
+        mappings and `kernels` are the torch stand-ins.  Never used by the product path."""
+        self.peer, self.p2p_cols, self._peer_injected = peer, int(cols), True
+
     def _use_p2p(self, plan: ExchangePlan, cols: int, shard: torch.Tensor) -> bool:
         if self.p2p_cols is None or plan.tables is None or cols != self.p2p_cols or self._p2p_failed:
             return False
-        if not shard.is_cuda:
+        if not (shard.is_cuda or self._peer_injected):
             return False
         if self.peer is None or plan.n > self.peer.cap:
             # collective: every rank sees the same plan.n (B per GPU is fixed) and gets here together
@@ -293,7 +300,7 @@ class ShardExchange:
         plan.recv_ids."""
         D = grads_bucket_order.shape[1]
         if (self.peer is not None and plan.tables is not None and D == self.peer.cols and
-                grads_bucket_order.is_cuda):
+                (grads_bucket_order.is_cuda or self._peer_injected)):
             self.k.raw_shard_push_rows(grads_bucket_order, D, plan.tables["send_seg"],
                                        plan.tables["dst_push"], self.peer.grads_ptrs,
                                        self.peer.cols, self.world)
@@ -312,7 +319,7 @@ class ShardExchange:
         peer-memory exchange is not active for this plan: caller falls back to K2 + push)."""
         D = feat.shape[2]
         if (not FUSED_PUSH or self.peer is None or plan.tables is None or G != self.peer.cols or
-                not feat.is_cuda or D % 4 or G % 4):
+                not (feat.is_cuda or self._peer_injected) or D % 4 or G % 4):
             return None
         self.k.raw_shard_fm_grads_push(feat, S, dfeat, gy1, gy2, plan.inv_perm, F, G,
                                        plan.tables["send_seg"], plan.tables["dst_push"],

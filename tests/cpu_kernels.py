@@ -200,3 +200,42 @@ def raw_cvm_fwd(x, use_cvm):
 
 def raw_cvm_bwd(dy, show_click, D, use_cvm):
     return torch.cat([show_click[:, :2], dy[:, 2:] if use_cvm else dy], 1)
+
+
+# ---- peer-memory exchange stand-ins: `ptrs` is a list of every rank's receive buffer (host tensors
+# in shared memory) instead of NVLink mappings; same argument order as ops.raw_shard_*.
+def _peer_of(seg, k):
+    return int(torch.searchsorted(seg[1:].contiguous(), torch.tensor(k), right=True))
+
+
+def raw_shard_gather_push(shard, recv_ids, local_pad, cols, recv_seg, dst_pull, ptrs, ld_dst, world):
+    rows = raw_gather(shard, recv_ids, local_pad, cols)
+    for r in range(world):
+        a, b = int(recv_seg[r]), int(recv_seg[r + 1])
+        d = int(dst_pull[r])
+        ptrs[r][d:d + (b - a), :cols] = rows[a:b]
+
+
+def _store_rows(rows, D, send_seg, dst_push, ptrs, world):
+    for o in range(world):
+        a, b = int(send_seg[o]), int(send_seg[o + 1])
+        d = int(dst_push[o])
+        ptrs[o][d:d + (b - a), :D] = rows[a:b, :D]
+
+
+def raw_shard_push_rows(rows, D, send_seg, dst_push, ptrs, ld_dst, world):
+    _store_rows(rows, D, send_seg, dst_push, ptrs, world)
+
+
+def raw_shard_fm_grads_push(feat, S, dfeat_dnn, gy1, gy2, inv_perm, F, G, send_seg, dst_push, ptrs,
+                            ld_dst, world):
+    """Slot k (position p = inv_perm[k] = b*F + f) gets [gy2[b]*(S[b]-feat[b,f]) + dfeat[b,f] | gy1[b] | 0]."""
+    B, N, D = feat.shape
+    p = inv_perm.to(torch.int64)
+    b, f = p // F, p % F
+    rows = torch.zeros(p.numel(), G, dtype=feat.dtype)
+    rows[:, :D] = gy2[b].unsqueeze(1) * (S[b] - feat[b, f])
+    if dfeat_dnn is not None:
+        rows[:, :D] += dfeat_dnn[b, f]
+    rows[:, D] = gy1[b]
+    _store_rows(rows, G, send_seg, dst_push, ptrs, world)

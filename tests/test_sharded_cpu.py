@@ -385,3 +385,106 @@ def test_peer_memory_exchange_tables(world, tmp_path):
     expects them, gradient rows land in the owner's receive segments."""
     mp.spawn(_tables_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+class _HostPeer:
+    """PeerBuffers made of shared-memory host tensors: every rank holds every rank's buffer, a store
+    into `ptrs[r]` is a store into rank r's memory, the publishing barrier is a gloo barrier."""
+
+    def __init__(self, bufs, rank, cap, cols, world):
+        self.cap, self.cap_g, self.cols, self.world = cap, 2 * cap, cols, world
+        self.rows, self.grads = bufs[rank][:cap], bufs[rank][cap:]
+        self.rows_ptrs = [b[:cap] for b in bufs]
+        self.grads_ptrs = [b[cap:] for b in bufs]
+
+    def publish_rows(self):
+        dist.barrier()
+
+    def publish_grads(self):
+        dist.barrier()
+
+
+def _peer_worker(rank, world, port, out_dir, bufs, cap, fused_push):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paddlerec_b200 import functional as BF
+        from paddlerec_b200 import sharded
+        sharded.FUSED_PUSH = bool(fused_push)
+        B = _batch_for(world)
+        p, ids, dense, label = _full_problem(B)
+        torch.manual_seed(100 + rank)
+        model = sharded.ShardedDeepFMLayer(V, D, Dn, F, FC, rank, world, device="cpu",
+                                           kernels=cpu_kernels, fused_table=True)
+        cols = model.fm._fused.grad_cols
+        model.fm.exchange.inject_peer(_HostPeer(bufs, rank, cap, cols, world), cols)
+        calls = {"gather_push": 0, "push_rows": 0, "fm_grads_push": 0}
+        for name in calls:        # count what the exchange really called
+
+            def counted(*a, _f=getattr(cpu_kernels, "raw_shard_" + name), _n=name, **kw):
+                calls[_n] += 1
+                return _f(*a, **kw)
+            setattr(cpu_kernels, "raw_shard_" + name, counted)
+        with torch.no_grad():
+            sd = model.state_dict()
+            for k, v in p.items():
+                sd[k].copy_(v[rank::world] if k.startswith("fm.embedding") else v)
+        per = B // world
+        sl = slice(rank * per, (rank + 1) * per)
+        res = {}
+        for step in range(2):          # twice: the buffers are reused, stale rows must not leak
+            for q in model.parameters():
+                q.grad = None
+            model.fm._fused.weight.grad_rows = None
+            pred = model(ids[sl], dense[sl])
+            loss = BF.log_loss(pred, label[sl]).mean()
+            opt = sharded.DistributedOptimizer(_NoStep(), model, world)
+            opt.scale_loss(loss).backward()
+            opt.step()
+            dist.barrier()
+        want = {"gather_push": 2, "push_rows": 0 if fused_push else 2,
+                "fm_grads_push": 2 if fused_push else 0}
+        assert calls == want, calls          # the peer-memory path ran, not the all-to-all fallback
+        res = {"pred": pred.detach().numpy(),
+               "dW": model.fm.table_grad_dense()[0].numpy(),
+               "dW1": model.fm.table_grad_dense()[1].numpy()}
+        for k, v in model.named_parameters():
+            if v.grad is not None:
+                res["g:" + k] = v.grad.numpy()
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,fused_push", [(2, False), (2, True), (8, False), (8, True)])
+def test_peer_memory_choreography_on_host_buffers(world, fused_push, tmp_path):
+    """The peer-memory pull / push of ShardExchange (and, with fused_push, the one-kernel
+    FM-gradient push) replayed on shared host tensors: same oracle, same tolerances as the all-to-all
+    path.  Covers the host logic (tables, buffer offsets, barriers, zero-segment K2 call); the CUDA
+    kernels themselves are covered by tests/test_sharded_gpu.py."""
+    B = _batch_for(world)
+    cols = (D + 1 + 3) // 4 * 4
+    cap = B // world * F + 8
+    bufs = [torch.full((3 * cap, cols), float("nan")).share_memory_() for _ in range(world)]
+    mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path), bufs, cap, fused_push),
+             nprocs=world, join=True)
+    p, ids, dense, label = _full_problem(B)
+    pp = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    ids_ok = ids.clone()
+    ids_ok[ids_ok >= V] = 0
+    pred = nets.deepfm_forward(pp, [ids_ok[:, i:i + 1] for i in range(F)], dense.double(), len(FC))
+    nets.log_loss(pred, label.double()).mean().backward()
+    per = B // world
+    for rank in range(world):
+        r = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        np.testing.assert_allclose(r["pred"], pred.detach().numpy()[rank * per:(rank + 1) * per],
+                                   rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(r["dW"], pp["fm.embedding.weight"].grad.numpy()[rank::world],
+                                   rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(r["dW1"], pp["fm.embedding_one.weight"].grad.numpy()[rank::world],
+                                   rtol=2e-4, atol=1e-7)
+        for k in pp:
+            if not k.startswith("fm.embedding"):
+                np.testing.assert_allclose(r["g:" + k], pp[k].grad.numpy(), rtol=2e-4, atol=1e-7,
+                                           err_msg=k)
