@@ -370,7 +370,7 @@ def run_b200(args, rank, world, local_rank):
         "roofline": {"kernel": "embed_fm_fwd_kernel (fused 26-slot gather + FM, forward)" +
                      ("" if world == 1 else
                       " over the RECEIVED rows (contiguous reads: the random gather is the owner-side "
-                      "shard_gather_push, see roofline_step)"),
+                      "shard_gather_push / gather kernel, see roofline_step)"),
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": kernel_ms,
